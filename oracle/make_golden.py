@@ -1,0 +1,115 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference.  Build-container only.
+
+    python -m oracle.make_golden
+
+Each fixture records the constructor arguments, the weight seed (weights are
+regenerated with ``oracle.seeded.seeded_state_dict`` from the model's own state_dict
+template), the input seed/shape and the reference outputs (eval mode, no_grad, fp32,
+torch CPU).  Stage taps are stored sub-sampled ([:, ::8, ::8]) to keep fixtures small.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_import
+from .seeded import seeded_state_dict, synthetic_mel, synthetic_speaker
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _sub(t):
+    t = t.detach()
+    if t.dim() == 3:
+        return t[:, ::8, ::8].contiguous().numpy()
+    return t.numpy()
+
+
+def _hook_taps(model, names):
+    taps = {}
+    handles = []
+    for tap_name, module, post in names:
+        def fn(_m, _i, o, tap_name=tap_name, post=post):
+            o = o[0] if isinstance(o, tuple) else o
+            taps[tap_name] = post(o)
+        handles.append(module.register_forward_hook(fn))
+    return taps, handles
+
+
+def golden_autovc(ref, name, cls_name, args, B, T, wseed, xseed):
+    torch.manual_seed(0)
+    model = getattr(ref, cls_name)(*args).eval()
+    sd = seeded_state_dict(model.state_dict(), wseed)
+    model.load_state_dict(sd)
+    x = synthetic_mel(B, T, xseed)
+    c_org = synthetic_speaker(B, xseed, "org")
+    c_trg = synthetic_speaker(B, xseed, "trg")
+    tl = lambda o: o.transpose(1, 2)
+    ident = lambda o: o
+    hooks = []
+    if cls_name == "AutoVC":
+        for i in range(3):
+            hooks.append((f"enc_conv{i}", model.encoder.convolutions[i], lambda o: torch.relu(o).transpose(1, 2)))
+            hooks.append((f"dec_conv{i}", model.decoder.convolutions[i], lambda o: torch.relu(o).transpose(1, 2)))
+        hooks.append(("enc_lstm", model.encoder.lstm, ident))
+        hooks.append(("dec_lstm1", model.decoder.lstm1, ident))
+        hooks.append(("dec_lstm2", model.decoder.lstm2, ident))
+    for i in range(4):
+        hooks.append((f"post_conv{i}", model.postnet.convolutions[i], lambda o: torch.tanh(o).transpose(1, 2)))
+    taps, handles = _hook_taps(model, hooks)
+    with torch.no_grad():
+        mel, post, codes = model(x, c_org, c_trg)
+    for h in handles:                                  # taps belong to the first call only
+        h.remove()
+    with torch.no_grad():
+        codes_only = model(mel, c_org, None)          # 4-D input path, train.py:90-92
+    rec = dict(cls=cls_name, args=np.array(args), B=B, T=T, wseed=wseed, xseed=xseed,
+               mel=mel.numpy(), mel_postnet=post.numpy(), codes=codes.numpy(),
+               codes_of_mel=codes_only.numpy())
+    for k, v in taps.items():
+        rec["tap_" + k] = _sub(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "mel", tuple(mel.shape), "|mel|", float(mel.norm()), "taps", sorted(taps))
+
+
+def golden_lstmdv(ref, name, B, T, wseed, xseed):
+    model = ref.LstmDV().eval()
+    sd = seeded_state_dict(model.state_dict(), wseed, lstm_gain=1.5)
+    model.load_state_dict(sd)
+    x = synthetic_mel(B, T, xseed)
+    with torch.no_grad():
+        e = model(x)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cls="LstmDV", B=B, T=T, wseed=wseed,
+                        xseed=xseed, lstm_gain=1.5, emb=e.numpy())
+    print(name, tuple(e.shape))
+
+
+def golden_melgan(ref, name, B, T, wseed, xseed):
+    model = ref.Generator(80, 32, 3).eval()
+    sd = seeded_state_dict(model.state_dict(), wseed)
+    model.load_state_dict(sd)
+    mel = synthetic_mel(B, T, xseed).transpose(1, 2).contiguous()
+    with torch.no_grad():
+        wav = model(mel)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cls="Generator", B=B, T=T, wseed=wseed,
+                        xseed=xseed, wav=wav.numpy())
+    print(name, tuple(wav.shape), "std", float(wav.std()), "mean", float(wav.mean()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_import.load()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    golden_autovc(ref, "autovc_A_b2_t128", "AutoVC", (32, 256, 512, 32), 2, 128, 0, 1234)
+    golden_autovc(ref, "autovc_A_b3_t64", "AutoVC", (32, 256, 512, 32), 3, 64, 1, 77)
+    golden_autovc(ref, "autovc_R_b2_t176", "AutoVC", (44, 256, 512, 22), 2, 176, 2, 99)
+    golden_lstmdv(ref, "lstmdv_b2_t100", 2, 100, 3, 5)
+    golden_melgan(ref, "melgan_b1_t40", 1, 40, 4, 6)
+    golden_melgan(ref, "melgan_b2_t17", 2, 17, 5, 7)
+    golden_autovc(ref, "metapool_b1_t176", "MetaPool", (44, 256, 512, 22), 1, 176, 6, 8)
+    golden_autovc(ref, "metaconv_b1_t176", "MetaConv", (44, 256, 512, 22), 1, 176, 7, 9)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
