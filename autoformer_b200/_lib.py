@@ -1,0 +1,112 @@
+"""ctypes binding of libavc_b200.so (C ABI in include/avc_b200.h).  Fails loudly when the library is missing."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libavc_b200.so")
+
+DTYPE_TF32 = 0
+DTYPE_BF16 = 1
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
+ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU}
+
+EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm", "avc_lstm_seq",
+           "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm"]
+
+
+class GemmDesc(ctypes.Structure):
+    """struct avc_gemm_desc"""
+    _fields_ = [
+        ("a_ptr", ctypes.c_void_p * 2),
+        ("a_channels", ctypes.c_int * 2),
+        ("a_ld", ctypes.c_longlong * 2),
+        ("a_rows_per_utt", ctypes.c_int * 2),
+        ("a_taps", ctypes.c_int * 2),
+        ("a_tap_t0", ctypes.c_int * 2),
+        ("a_tap_dt", ctypes.c_int * 2),
+        ("w_ptr", ctypes.c_void_p),
+        ("n_pad", ctypes.c_int),
+        ("k_pad", ctypes.c_int),
+        ("dtype", ctypes.c_int),
+        ("B", ctypes.c_int),
+        ("T", ctypes.c_int),
+        ("N", ctypes.c_int),
+        ("bias", ctypes.c_void_p),
+        ("act", ctypes.c_int),
+        ("out", ctypes.c_void_p),
+        ("out_ld", ctypes.c_longlong),
+        ("out_rows_per_utt", ctypes.c_int),
+        ("out_row0", ctypes.c_int),
+        ("out_dtype", ctypes.c_int),
+        ("out_round_tf32", ctypes.c_int),
+        ("out_reflect", ctypes.c_int),
+        ("out2", ctypes.c_void_p),
+        ("out2_ld", ctypes.c_longlong),
+        ("residual", ctypes.c_void_p),
+        ("res_ld", ctypes.c_longlong),
+        ("block_n", ctypes.c_int),
+    ]
+
+
+class LstmDesc(ctypes.Structure):
+    """struct avc_lstm_desc"""
+    _fields_ = [
+        ("xproj", ctypes.c_void_p),
+        ("w_hh", ctypes.c_void_p),
+        ("hseq", ctypes.c_void_p),
+        ("hseq_f32", ctypes.c_void_p),
+        ("h_last", ctypes.c_void_p),
+        ("c_state", ctypes.c_void_p),
+        ("B", ctypes.c_int),
+        ("T", ctypes.c_int),
+        ("H", ctypes.c_int),
+        ("dtype", ctypes.c_int),
+        ("gate_group", ctypes.c_int),
+        ("persistent", ctypes.c_int),
+        ("grid_barrier", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the library once; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the conversion path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.avc_version.restype = ctypes.c_int
+    lib.avc_last_error.restype = ctypes.c_char_p
+    lib.avc_launch_count.restype = ctypes.c_longlong
+    lib.avc_conv_gemm.argtypes = [ctypes.POINTER(GemmDesc), ctypes.c_void_p]
+    lib.avc_conv_gemm.restype = ctypes.c_int
+    lib.avc_lstm_seq.argtypes = [ctypes.POINTER(LstmDesc), ctypes.c_void_p]
+    lib.avc_lstm_seq.restype = ctypes.c_int
+    lib.avc_bilstm_small.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p]
+    lib.avc_bilstm_small.restype = ctypes.c_int
+    lib.avc_concat_bcast.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_void_p]
+    lib.avc_concat_bcast.restype = ctypes.c_int
+    lib.avc_linear_l2norm.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.avc_linear_l2norm.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().avc_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def launch_count():
+    return int(load().avc_launch_count())

@@ -1,0 +1,295 @@
+// Implicit-GEMM convolution / dense GEMM on tcgen05 (see include/avc_b200.h: avc_conv_gemm).
+//
+// Tile = 128 output rows x BN output channels.  The 128 rows are `bb` utterances x `tb` consecutive
+// frames (tb * bb = 128, tb = largest power of two <= 128 dividing T), so one 3-D TMA box
+// {128 bytes of channels, tb frames, bb utterances} fetches the A tile of one (tap, channel chunk) k-block,
+// shifted in time by the tap offset; frames outside the utterance are zero-filled by TMA, which IS the
+// convolution's zero padding -- tiles never bleed across utterances.
+#include <cuda_bf16.h>
+
+#include "../../include/avc_b200.h"
+#include "avc_host.h"
+#include "avc_pipe.cuh"
+
+namespace avc {
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmap_a[2];
+  CUtensorMap tmap_b;
+  // k-block schedule: source s contributes taps[s] * chunks[s] k-blocks, tap-major
+  int kb_src0;           // k-blocks of source 0
+  int num_kb;            // total k-blocks
+  int chunks[2];         // channel chunks per tap
+  int tap_t0[2];
+  int tap_dt[2];
+  int kc_elems;          // channels per k-block (32 tf32 / 64 bf16)
+  // tiling
+  int B, T, N;
+  int tb_log2, bb;       // tile = bb utterances x (1 << tb_log2) frames
+  int tiles_t, n_tiles;
+  // epilogue
+  const float* bias;
+  int act;
+  void* out;
+  long long out_ld;
+  int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16
+  float* out2;
+  long long out2_ld;
+  const float* residual;
+  long long res_ld;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case AVC_ACT_RELU: return fmaxf(v, 0.0f);
+    case AVC_ACT_TANH: return tanh_fast(v);
+    case AVC_ACT_LRELU: return v > 0.0f ? v : 0.2f * v;
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void store4(const GemmParams& p, long long row, int n, const float (&v)[4]) {
+  if (p.out_mode == 2) {
+    float lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+    __nv_bfloat16* base = static_cast<__nv_bfloat16*>(p.out) + row * p.out_ld + n;
+    *reinterpret_cast<uint2*>(base) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    *reinterpret_cast<uint2*>(base + p.N) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+  } else if (p.out_mode == 1) {
+    uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + row * p.out_ld + n) = pk;
+  } else {
+    float4 o = p.out_round ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
+                           : make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.out_ld + n) = o;
+  }
+}
+
+template <int BN, bool BF16>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = PipeCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const PipeSmem s = carve_smem<BN>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates: n fastest so CTAs sharing an A tile are co-scheduled (A stays in L2)
+  const int tile = blockIdx.x;
+  const int n_tile = tile % p.n_tiles;
+  const int m_tile = tile / p.n_tiles;
+  const int tt = m_tile % p.tiles_t;
+  const int bt = m_tile / p.tiles_t;
+  const int tb = 1 << p.tb_log2;
+  const int t0 = tt * tb;
+  const int b0 = bt * p.bb;
+  const int n0 = n_tile * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmap_a[0]);
+    prefetch_tmap(&p.tmap_b);
+    if (p.num_kb > p.kb_src0) prefetch_tmap(&p.tmap_a[1]);
+  }
+  const uint32_t tmem_base = pipe_setup<BN>(s);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      RingState rs;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        const int src = kb >= p.kb_src0 ? 1 : 0;
+        const int local = src ? kb - p.kb_src0 : kb;
+        const int tap = local / p.chunks[src];
+        const int chunk = local - tap * p.chunks[src];
+        mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
+        uint8_t* a_dst = s.base + rs.stage * C::kStageBytes;
+        mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
+        tma_load_3d(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
+                    t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
+        tma_load_2d(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems, n0);
+        rs.advance<C::kStages>();
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      RingState rs;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&s.full[rs.stage], rs.phase);
+        tc_fence_after();
+        issue_kblock<BN, BF16>(s, rs.stage, tmem_base, kb == 0);
+        umma_commit(&s.empty[rs.stage]);   // frees the smem slot once these MMAs have read it
+        rs.advance<C::kStages>();
+      }
+      umma_commit(s.tmem_full);
+    }
+  } else {
+    // ---------------- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int bi = m >> p.tb_log2;
+    const int ti = m & (tb - 1);
+    const int b = b0 + bi;
+    const int t = t0 + ti;
+    const bool valid = (b < p.B) && (t < p.T);
+    const long long orow = (long long)b * p.out_rows_per_utt + p.out_row0 + t;
+    const long long lrow = (long long)b * p.T + t;
+    // reflected halo rows this thread also writes (ReflectionPad1d of the consumer)
+    long long rrow_l = -1, rrow_r = -1;
+    if (p.out_reflect > 0) {
+      if (t >= 1 && t <= p.out_reflect) rrow_l = orow - 2LL * t;
+      if (t <= p.T - 2 && t >= p.T - 1 - p.out_reflect) rrow_r = orow + 2LL * (p.T - 1 - t);
+    }
+    mbar_wait(s.tmem_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(lane_addr + c * 32, v);
+      tmem_ld_wait();
+      const int nc = n0 + c * 32;
+      if (valid && nc < p.N) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = nc + 4 * j;
+          if (n < p.N) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            float o[4];
+            o[0] = apply_act(__uint_as_float(v[4 * j + 0]) + bv.x, p.act);
+            o[1] = apply_act(__uint_as_float(v[4 * j + 1]) + bv.y, p.act);
+            o[2] = apply_act(__uint_as_float(v[4 * j + 2]) + bv.z, p.act);
+            o[3] = apply_act(__uint_as_float(v[4 * j + 3]) + bv.w, p.act);
+            if (p.residual) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + lrow * p.res_ld + n));
+              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+            }
+            if (p.out) {
+              store4(p, orow, n, o);
+              if (rrow_l >= 0) store4(p, rrow_l, n, o);
+              if (rrow_r >= 0) store4(p, rrow_r, n, o);
+            }
+            if (p.out2)
+              *reinterpret_cast<float4*>(p.out2 + lrow * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+  pipe_teardown<BN>(tmem_base);
+}
+
+template <int BN, bool BF16>
+static int launch(const GemmParams& p, int grid, cudaStream_t stream) {
+  auto kern = conv_gemm_kernel<BN, BF16>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, PipeCfg<BN>::kSmemBytes, stream>>>(p);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace avc
+
+extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(d != nullptr, "avc_conv_gemm: null descriptor");
+  AVC_REQUIRE(d->dtype == AVC_DTYPE_TF32 || d->dtype == AVC_DTYPE_BF16, "avc_conv_gemm: bad dtype %d", d->dtype);
+  AVC_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->N % 4 == 0, "avc_conv_gemm: bad shape B=%d T=%d N=%d", d->B,
+              d->T, d->N);
+  AVC_REQUIRE(d->a_taps[0] > 0 && d->a_ptr[0] && d->w_ptr && d->bias, "avc_conv_gemm: missing operand");
+  AVC_REQUIRE(d->out || d->out2, "avc_conv_gemm: no output");
+  const int es = d->dtype == AVC_DTYPE_BF16 ? 2 : 4;
+  const int kc = kRowBytes / es;
+
+  int bn = d->block_n;
+  if (bn == 0) bn = d->n_pad % 256 == 0 ? 256 : (d->n_pad % 128 == 0 ? 128 : 64);
+  AVC_REQUIRE(bn == 64 || bn == 128 || bn == 256, "avc_conv_gemm: block_n %d", bn);
+  AVC_REQUIRE(d->n_pad % bn == 0 && d->n_pad >= d->N, "avc_conv_gemm: n_pad %d not a multiple of block_n %d", d->n_pad,
+              bn);
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  // tile = bb utterances x tb frames: pick the power-of-two split of 128 rows that wastes the fewest rows
+  int tb_log2 = 7;
+  long long best = -1;
+  for (int l = 7; l >= 0; --l) {
+    const long long tbc = 1LL << l, bbc = kBlockM >> l;
+    const long long rows = ((d->T + tbc - 1) / tbc) * ((d->B + bbc - 1) / bbc);
+    if (best < 0 || rows < best) {
+      best = rows;
+      tb_log2 = l;
+    }
+  }
+  const int tb = 1 << tb_log2;
+  p.tb_log2 = tb_log2;
+  p.bb = kBlockM / tb;
+  p.tiles_t = (d->T + tb - 1) / tb;
+  const int tiles_b = (d->B + p.bb - 1) / p.bb;
+  p.n_tiles = d->n_pad / bn;
+  p.B = d->B;
+  p.T = d->T;
+  p.N = d->N;
+  p.kc_elems = kc;
+
+  int kb_total = 0;
+  for (int s = 0; s < 2; ++s) {
+    if (d->a_taps[s] <= 0) {
+      AVC_REQUIRE(s == 1, "avc_conv_gemm: source 0 unused");
+      continue;
+    }
+    AVC_REQUIRE(d->a_ptr[s] != nullptr, "avc_conv_gemm: source %d null", s);
+    p.chunks[s] = (d->a_channels[s] + kc - 1) / kc;
+    p.tap_t0[s] = d->a_tap_t0[s];
+    p.tap_dt[s] = d->a_tap_dt[s];
+    const int kbs = d->a_taps[s] * p.chunks[s];
+    if (s == 0) p.kb_src0 = kbs;
+    kb_total += kbs;
+    if (!encode_tmap_3d(&p.tmap_a[s], es, d->a_ptr[s], (uint64_t)d->a_channels[s], (uint64_t)d->a_rows_per_utt[s],
+                        (uint64_t)d->B, (uint64_t)d->a_ld[s] * es,
+                        (uint64_t)d->a_rows_per_utt[s] * (uint64_t)d->a_ld[s] * es, kc, tb, p.bb))
+      return -3;
+  }
+  p.num_kb = kb_total;
+  AVC_REQUIRE(kb_total * kc == d->k_pad, "avc_conv_gemm: k_pad %d != %d k-blocks x %d", d->k_pad, kb_total, kc);
+  if (!encode_tmap_2d(&p.tmap_b, es, d->w_ptr, (uint64_t)d->k_pad, (uint64_t)d->n_pad, (uint64_t)d->k_pad * es, kc, bn))
+    return -3;
+
+  p.bias = d->bias;
+  p.act = d->act;
+  p.out = d->out;
+  p.out_ld = d->out_ld;
+  p.out_rows_per_utt = d->out_rows_per_utt;
+  p.out_row0 = d->out_row0;
+  p.out_mode = d->out_dtype;
+  AVC_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 2, "avc_conv_gemm: out_dtype %d", d->out_dtype);
+  if (d->out && d->out_dtype == 2) AVC_REQUIRE(d->out_ld >= 2LL * d->N, "avc_conv_gemm: split output needs out_ld >= 2N");
+  p.out_round = d->out_round_tf32;
+  p.out_reflect = d->out_reflect;
+  p.out2 = d->out2;
+  p.out2_ld = d->out2_ld;
+  p.residual = d->residual;
+  p.res_ld = d->res_ld;
+  if (d->out) {
+    AVC_REQUIRE(d->out_ld % 4 == 0 && d->out_rows_per_utt >= d->out_row0 + d->T + d->out_reflect &&
+                    d->out_row0 >= d->out_reflect,
+                "avc_conv_gemm: bad output geometry");
+    AVC_REQUIRE(d->out_reflect < d->T, "avc_conv_gemm: reflect %d needs T > reflect", d->out_reflect);
+  }
+  if (d->out2) AVC_REQUIRE(d->out2_ld % 4 == 0, "avc_conv_gemm: out2_ld");
+  if (d->residual) AVC_REQUIRE(d->res_ld % 4 == 0, "avc_conv_gemm: res_ld");
+
+  const long long grid = (long long)p.tiles_t * tiles_b * p.n_tiles;
+  AVC_REQUIRE(grid > 0 && grid < (1LL << 31), "avc_conv_gemm: grid %lld", grid);
+  const bool bf16 = d->dtype == AVC_DTYPE_BF16;
+  switch (bn) {
+    case 64: return bf16 ? launch<64, true>(p, (int)grid, stream) : launch<64, false>(p, (int)grid, stream);
+    case 128: return bf16 ? launch<128, true>(p, (int)grid, stream) : launch<128, false>(p, (int)grid, stream);
+    default: return bf16 ? launch<256, true>(p, (int)grid, stream) : launch<256, false>(p, (int)grid, stream);
+  }
+}

@@ -1,0 +1,43 @@
+// Host-side helpers shared by the translation units of libavc_b200.so: error text, launch counter,
+// TMA tensor-map encoding through the driver entry point (no link-time dependency on libcuda, so the
+// library also loads on a box without a GPU driver).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+namespace avc {
+
+void set_error(const char* fmt, ...);
+void count_launch(long long n = 1);
+
+// 3-D tiled tensor map over a [d2][d1][d0] array (d0 contiguous), 128-byte swizzle, zero OOB fill.
+// elem_bytes = 4 (fp32 read as TF32) or 2 (bf16).  Box = {box0, box1, box2} elements; box0*elem_bytes == 128.
+bool encode_tmap_3d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+// 2-D variant over [d1][d0].
+bool encode_tmap_2d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
+                    uint64_t stride1_bytes, uint32_t box0, uint32_t box1);
+
+int num_sms();
+
+#define AVC_CHECK_CUDA(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t e__ = (expr);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      avc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define AVC_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      avc::set_error(__VA_ARGS__);    \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+}  // namespace avc

@@ -1,0 +1,261 @@
+// HBM-bound glue and the small-H bidirectional LSTM (see include/avc_b200.h).
+#include <cuda_bf16.h>
+
+#include "../../include/avc_b200.h"
+#include "avc_host.h"
+#include "avc_pipe.cuh"
+
+namespace avc {
+
+// ---------------------------------------------------------------------------------------------
+// concat with broadcast: out[b,t,:] = [seq[b, t/div, :C1] || vec[b, :C2]], float4 granularity
+// ---------------------------------------------------------------------------------------------
+template <int MODE>   // 0 fp32 (optionally TF32-rounded), 1 bf16, 2 split bf16 [hi | lo]
+__global__ void __launch_bounds__(256) concat_bcast_kernel(const float* __restrict__ seq, const float* __restrict__ vec,
+                                                           void* __restrict__ out, long long rows, int T, int C1,
+                                                           int C2, int div, int round) {
+  const int c4 = (C1 + C2) >> 2;   // float4 groups per output row
+  const long long total = rows * c4;
+  const int Tin = T / div;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int c = static_cast<int>(i - r * c4) << 2;
+    const long long b = r / T;
+    const int t = static_cast<int>(r - b * T);
+    float4 v;
+    if (c < C1)
+      v = __ldg(reinterpret_cast<const float4*>(seq + (b * Tin + t / div) * C1 + c));
+    else
+      v = __ldg(reinterpret_cast<const float4*>(vec + b * C2 + (c - C1)));
+    if (MODE == 2) {
+      const int C = C1 + C2;
+      __nv_bfloat16* base = static_cast<__nv_bfloat16*>(out) + r * (2LL * C) + c;
+      const float lx = v.x - __bfloat162float(__float2bfloat16_rn(v.x));
+      const float ly = v.y - __bfloat162float(__float2bfloat16_rn(v.y));
+      const float lz = v.z - __bfloat162float(__float2bfloat16_rn(v.z));
+      const float lw = v.w - __bfloat162float(__float2bfloat16_rn(v.w));
+      *reinterpret_cast<uint2*>(base) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      *reinterpret_cast<uint2*>(base + C) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+    } else if (MODE == 1) {
+      uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * (C1 + C2) + c) = pk;
+    } else {
+      if (round) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      *reinterpret_cast<float4*>(static_cast<float*>(out) + r * (C1 + C2) + c) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small-H bidirectional LSTM: one warp per (utterance, direction); W_hh transposed in shared memory
+// as Wt[dir][k][unit][gate] so that a lane's four gate weights for input k are one 16-byte load and the
+// 32 lanes of a warp read consecutive units (conflict free); h_{t-1} is broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSmallWarps = 8;   // 4 utterances x 2 directions per CTA
+
+template <int UPL>   // hidden units per lane: 1 (H <= 32) or 2 (H <= 64)
+__global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
+    const float* __restrict__ xproj, const float* __restrict__ w_hh, void* __restrict__ out, int out_mode, int round,
+    float* __restrict__ codes, int B, int T, int H, int freq) {
+  extern __shared__ float4 smem4[];
+  constexpr int HP = UPL * 32;
+  float4* Wt = smem4;                                              // [2][H][HP]
+  float* hbuf = reinterpret_cast<float*>(smem4 + 2 * H * HP);      // [kSmallWarps][HP]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * H * HP; i += blockDim.x) {
+    const int u = i % HP;
+    const int k = (i / HP) % H;
+    const int d = i / (HP * H);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < H) {
+      const float* base = w_hh + (long long)d * 4 * H * H;
+      w.x = base[(0 * H + u) * H + k];
+      w.y = base[(1 * H + u) * H + k];
+      w.z = base[(2 * H + u) * H + k];
+      w.w = base[(3 * H + u) * H + k];
+    }
+    Wt[i] = w;
+  }
+  float* hb = hbuf + warp * HP;
+  for (int e = 0; e < UPL; ++e) hb[lane + 32 * e] = 0.0f;
+  __syncthreads();
+
+  const int b = blockIdx.x * (kSmallWarps / 2) + (warp >> 1);
+  const int dir = warp & 1;
+  if (b >= B) return;
+  const float4* W = Wt + dir * H * HP;
+  const int n_codes = T / freq;
+  float c[UPL];
+  float zx[UPL][4];
+  for (int e = 0; e < UPL; ++e) c[e] = 0.0f;
+
+  auto load_x = [&](int t, float (&dst)[UPL][4]) {
+    const float* xp = xproj + ((long long)b * T + t) * (8LL * H) + dir * 4 * H;
+#pragma unroll
+    for (int e = 0; e < UPL; ++e) {
+      const int u = lane + 32 * e;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dst[e][g] = (u < H) ? __ldg(xp + g * H + u) : 0.0f;
+    }
+  };
+  load_x(dir ? T - 1 : 0, zx);
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? T - 1 - s : s;
+    float z[UPL][4];
+#pragma unroll
+    for (int e = 0; e < UPL; ++e)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) z[e][g] = zx[e][g];
+    if (s + 1 < T) load_x(dir ? t - 1 : t + 1, zx);   // prefetch the next frame's projection
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+      const float hk = hb[k];
+#pragma unroll
+      for (int e = 0; e < UPL; ++e) {
+        const float4 w = W[k * HP + lane + 32 * e];
+        z[e][0] = fmaf(w.x, hk, z[e][0]);
+        z[e][1] = fmaf(w.y, hk, z[e][1]);
+        z[e][2] = fmaf(w.z, hk, z[e][2]);
+        z[e][3] = fmaf(w.w, hk, z[e][3]);
+      }
+    }
+    __syncwarp();
+    float h[UPL];
+#pragma unroll
+    for (int e = 0; e < UPL; ++e) {
+      const float ig = sigmoid_fast(z[e][0]);
+      const float fg = sigmoid_fast(z[e][1]);
+      const float gg = tanh_fast(z[e][2]);
+      const float og = sigmoid_fast(z[e][3]);
+      c[e] = fg * c[e] + ig * gg;
+      h[e] = og * tanh_fast(c[e]);
+      hb[lane + 32 * e] = h[e];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < UPL; ++e) {
+      const int u = lane + 32 * e;
+      if (u < H) {
+        if (out) {
+          const long long o = ((long long)b * T + t) * (2LL * H) + dir * H + u;
+          if (out_mode == 2) {   // split bf16: [hi(2H) | lo(2H)]
+            const __nv_bfloat16 hi = __float2bfloat16_rn(h[e]);
+            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(out) + ((long long)b * T + t) * (4LL * H) + dir * H + u;
+            base[0] = hi;
+            base[2 * H] = __float2bfloat16_rn(h[e] - __bfloat162float(hi));
+          } else if (out_mode == 1)
+            static_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(h[e]);
+          else
+            static_cast<float*>(out)[o] = round ? round_tf32(h[e]) : h[e];
+        }
+        if (codes) {
+          // code_j = [h_fwd[j*freq + freq-1] || h_bwd[j*freq]]  (factory/AutoVC.py:56-66)
+          const int r = t % freq;
+          if (dir == 0 ? (r == freq - 1) : (r == 0))
+            codes[((long long)b * n_codes + t / freq) * (2LL * H) + dir * H + u] = h[e];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LstmDV tail: e = W h + b; out = e / ||e||   one CTA per utterance, one thread per output
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_l2norm_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            int K, int N) {
+  extern __shared__ float sh[];   // [K] input row, then 8 partial sums
+  float* red = sh + K;
+  const int b = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sh[k] = h[(long long)b * K + k];
+  __syncthreads();
+  float sq = 0.0f;
+  float e_val[4];   // up to N = 1024 outputs with 256 threads
+  int cnt = 0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x, ++cnt) {
+    const float4* wr = reinterpret_cast<const float4*>(w + (long long)n * K);
+    float acc = bias[n];
+    for (int k = 0; k < K / 4; ++k) {
+      const float4 wv = __ldg(wr + k);
+      acc = fmaf(wv.x, sh[4 * k], acc);
+      acc = fmaf(wv.y, sh[4 * k + 1], acc);
+      acc = fmaf(wv.z, sh[4 * k + 2], acc);
+      acc = fmaf(wv.w, sh[4 * k + 3], acc);
+    }
+    e_val[cnt] = acc;
+    sq += acc * acc;
+  }
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float inv = rsqrtf(tot);
+  cnt = 0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x, ++cnt) out[(long long)b * N + n] = e_val[cnt] * inv;
+}
+
+}  // namespace avc
+
+extern "C" int avc_concat_bcast(const float* seq, const float* vec, void* out, int B, int T, int C1, int C2, int div,
+                                int out_dtype, int out_round_tf32, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(seq && vec && out, "avc_concat_bcast: null buffer");
+  AVC_REQUIRE(B > 0 && T > 0 && C1 > 0 && C2 > 0 && C1 % 4 == 0 && C2 % 4 == 0 && div > 0 && T % div == 0,
+              "avc_concat_bcast: bad shape B=%d T=%d C1=%d C2=%d div=%d", B, T, C1, C2, div);
+  const long long rows = (long long)B * T;
+  const long long total = rows * ((C1 + C2) / 4);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (out_dtype == 2)
+    concat_bcast_kernel<2><<<(int)blocks, 256, 0, stream>>>(seq, vec, out, rows, T, C1, C2, div, 0);
+  else if (out_dtype == 1)
+    concat_bcast_kernel<1><<<(int)blocks, 256, 0, stream>>>(seq, vec, out, rows, T, C1, C2, div, 0);
+  else
+    concat_bcast_kernel<0><<<(int)blocks, 256, 0, stream>>>(seq, vec, out, rows, T, C1, C2, div, out_round_tf32);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_bilstm_small(const float* xproj, const float* w_hh, void* out, int out_dtype, int out_round_tf32,
+                                float* codes, int B, int T, int H, int freq, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(xproj && w_hh && (out || codes), "avc_bilstm_small: null buffer");
+  AVC_REQUIRE(B > 0 && T > 0 && H > 0 && H <= 64, "avc_bilstm_small: bad shape B=%d T=%d H=%d", B, T, H);
+  if (codes) AVC_REQUIRE(freq > 0 && T % freq == 0, "avc_bilstm_small: T=%d is not a multiple of freq=%d", T, freq);
+  if (freq <= 0) freq = 1;
+  const int upl = H <= 32 ? 1 : 2;
+  const int hp = upl * 32;
+  const size_t smem = (size_t)2 * H * hp * sizeof(float4) + (size_t)kSmallWarps * hp * sizeof(float);
+  const int grid = (B + kSmallWarps / 2 - 1) / (kSmallWarps / 2);
+  if (upl == 1) {
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(bilstm_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bilstm_small_kernel<1><<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32,
+                                                                     codes, B, T, H, freq);
+  } else {
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(bilstm_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bilstm_small_kernel<2><<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32,
+                                                                     codes, B, T, H, freq);
+  }
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_linear_l2norm(const float* h, const float* w, const float* bias, float* out, int B, int K, int N,
+                                 void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(h && w && bias && out, "avc_linear_l2norm: null buffer");
+  AVC_REQUIRE(B > 0 && K > 0 && K % 4 == 0 && N > 0 && N <= 1024, "avc_linear_l2norm: bad shape B=%d K=%d N=%d", B, K, N);
+  linear_l2norm_kernel<<<B, 256, (K + 8) * sizeof(float), stream>>>(h, w, bias, out, K, N);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}

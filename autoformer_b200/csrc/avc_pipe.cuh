@@ -1,0 +1,131 @@
+// The TMA -> shared memory -> tcgen05.mma pipeline shared by the convolution/GEMM kernel and the
+// LSTM step kernel.  One CTA computes a 128 x BN fp32 accumulator tile in tensor memory:
+//   warp 0 (one lane)  : TMA producer, ring of STAGES {A 128x128B, B BNx128B} tiles, 128-byte swizzle
+//   warp 1 (one lane)  : tcgen05.mma issuer, 4 MMAs (32 bytes of K each) per k-block
+//   warps 2..5         : epilogue (TMEM -> registers -> global)
+// K is consumed in k-blocks of 128 bytes per row: 32 TF32 or 64 bf16 elements.
+#pragma once
+#include "avc_ptx.cuh"
+
+namespace avc {
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;                 // one swizzle row = one k-block of one row
+constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
+constexpr int kNumThreads = 192;               // 6 warps
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN>
+struct PipeCfg {
+  static constexpr int kBTileBytes = BN * kRowBytes;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  // full[kStages], empty[kStages], tmem_full, then the TMEM base address word
+  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024 /* alignment slack */;
+  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+};
+
+struct PipeSmem {
+  uint8_t* base;        // 1024-byte aligned
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* tmem_full;
+  uint32_t* tmem_ptr;
+};
+
+template <int BN>
+__device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
+  using C = PipeCfg<BN>;
+  PipeSmem s;
+  const uint32_t addr = smem_u32(raw);
+  s.base = raw + ((1024u - (addr & 1023u)) & 1023u);
+  s.full = reinterpret_cast<uint64_t*>(s.base + C::kBarOffset);
+  s.empty = s.full + C::kStages;
+  s.tmem_full = s.empty + C::kStages;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_full + 1);
+  return s;
+}
+
+// Barrier init (thread 0) + TMEM allocation (warp 1) + CTA sync.  Returns the TMEM base address.
+template <int BN>
+__device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
+  using C = PipeCfg<BN>;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(s.tmem_ptr, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(s.tmem_ptr);
+}
+
+template <int BN>
+__device__ __forceinline__ void pipe_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, PipeCfg<BN>::kTmemCols);
+  }
+}
+
+struct RingState {
+  uint32_t stage = 0;
+  uint32_t phase = 0;
+  template <int STAGES>
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
+// MMA issue for one k-block that has landed in `stage`: 4 x (128 x BN x 32 bytes of K).
+template <int BN, bool BF16>
+__device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, uint32_t tmem_acc, bool first) {
+  using C = PipeCfg<BN>;
+  constexpr uint32_t idesc = umma_idesc(kBlockM, BN, !BF16);
+  const uint32_t a_addr = smem_u32(s.base + stage * C::kStageBytes);
+  const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
+    const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32);
+    const uint32_t acc = (first && k == 0) ? 0u : 1u;
+    if (BF16)
+      umma_bf16(tmem_acc, adesc, bdesc, idesc, acc);
+    else
+      umma_tf32(tmem_acc, adesc, bdesc, idesc, acc);
+  }
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// tanh with ~1e-7 absolute error (tanh.approx is only good to 2^-11, too coarse for a 1e-3 end-to-end gate).
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(-2.0f * fabsf(x));
+  const float r = __fdividef(1.0f - e, 1.0f + e);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace avc

@@ -1,0 +1,122 @@
+"""Packed layer objects shared by the drop-in models: they own folded/re-packed weights and call ``ops``."""
+import torch
+
+from . import ops, packing
+from .packing import TORCH_DTYPE
+
+
+class PlanCache:
+    """Re-pack weights only when a parameter/buffer was replaced or modified in place."""
+
+    def __init__(self):
+        self.key = None
+        self.plan = None
+
+    @staticmethod
+    def fingerprint(module, extra=()):
+        items = []
+        for t in list(module.parameters()) + list(module.buffers()):
+            items.append((t.data_ptr(), t._version, t.device))
+        return (tuple(items), tuple(extra))
+
+    def get(self, module, extra, builder):
+        key = self.fingerprint(module, extra)
+        if key != self.key:
+            self.plan = builder()
+            self.key = key
+        return self.plan
+
+
+def conv_bn_layer(sd, prefix, precision, act):
+    """nn.Sequential(ConvNorm(k5,p2), BatchNorm1d) (+act) -> one packed conv (factory/AutoVC.py:26-39)."""
+    w, b = packing.fold_bn(sd[f"{prefix}.0.conv.weight"], sd[f"{prefix}.0.conv.bias"], sd[f"{prefix}.1.weight"],
+                           sd[f"{prefix}.1.bias"], sd[f"{prefix}.1.running_mean"], sd[f"{prefix}.1.running_var"])
+    return ops.ConvGemm(*packing.pack_conv(w, b, precision), act=act)
+
+
+class LstmLayer:
+    """One uni-directional nn.LSTM layer: dense input projection + tensor-core recurrence."""
+
+    def __init__(self, w_ih, w_hh, b_ih, b_hh, precision):
+        self.w_ih, self.w_hh, self.b_ih, self.b_hh = w_ih.detach(), w_hh.detach(), b_ih.detach(), b_hh.detach()
+        self.precision = precision
+        self.H = w_hh.shape[1]
+        self._packs = {}
+
+    def packs(self, group):
+        if group not in self._packs:
+            ih = ops.ConvGemm(*packing.pack_lstm_ih(self.w_ih, self.b_ih, self.b_hh, self.precision, group))
+            hh = packing.pack_lstm_hh(self.w_hh, self.precision, group)
+            self._packs[group] = (ih, hh)
+        return self._packs[group]
+
+    def __call__(self, x, B, T, hseq_f32=None, h_last=None, persistent=False):
+        group = ops.choose_gate_group(B, self.H, persistent)
+        ih, hh = self.packs(group)
+        xp = torch.empty(B * T, 4 * self.H, dtype=torch.float32, device=x.device)
+        ih(x, B, T, out2=xp)
+        return ops.lstm_seq(xp, hh, B, T, self.H, self.precision, group, hseq_f32=hseq_f32, h_last=h_last,
+                            persistent=persistent)
+
+
+def lstm_layers(sd, prefix, num_layers, precision):
+    return [LstmLayer(sd[f"{prefix}.weight_ih_l{l}"], sd[f"{prefix}.weight_hh_l{l}"], sd[f"{prefix}.bias_ih_l{l}"],
+                      sd[f"{prefix}.bias_hh_l{l}"], precision) for l in range(num_layers)]
+
+
+class BiLstmSmall:
+    """Bidirectional nn.LSTM with a small hidden size (the AutoVC content encoder, factory/AutoVC.py:43)."""
+
+    def __init__(self, sd, prefix, num_layers, precision):
+        self.precision = precision
+        self.layers = []
+        for l in range(num_layers):
+            g = lambda n, d="": sd[f"{prefix}.{n}_l{l}{d}"].detach()
+            ih = ops.ConvGemm(*packing.pack_bilstm_ih(g("weight_ih"), g("bias_ih"), g("bias_hh"),
+                                                      g("weight_ih", "_reverse"), g("bias_ih", "_reverse"),
+                                                      g("bias_hh", "_reverse"), precision))
+            hh = torch.stack([g("weight_hh"), g("weight_hh", "_reverse")]).float().contiguous()
+            self.layers.append((ih, hh))
+        self.H = self.layers[0][1].shape[2]
+
+    def __call__(self, x, B, T, freq=None, want_out=False):
+        """Returns (out [B][T][2H] of the last layer or None, codes [B][T/freq][2H] fp32 or None)."""
+        H = self.H
+        out = None
+        codes = None
+        for i, (ih, hh) in enumerate(self.layers):
+            last = i == len(self.layers) - 1
+            xp = torch.empty(B * T, 8 * H, dtype=torch.float32, device=x.device)
+            ih(x, B, T, out2=xp)
+            if not last:
+                out = ops.alloc_act(B, T, 2 * H, self.precision, x.device)
+                ops.bilstm_small(xp, hh, B, T, H, out=out, split=self.precision == "fp32")
+                x = out
+            else:
+                out = torch.empty(B, T, 2 * H, dtype=torch.float32, device=x.device) if (want_out or freq is None) else None
+                if freq is not None:
+                    codes = torch.empty(B, T // freq, 2 * H, dtype=torch.float32, device=x.device)
+                ops.bilstm_small(xp, hh, B, T, H, out=out, codes=codes, freq=freq or 1, round_tf32=False)
+        return out, codes
+
+
+class Postnet:
+    """Five conv+BN layers, tanh on the first four, residual add fused into the last (factory/AutoVC.py:117-179,206-209)."""
+
+    def __init__(self, sd, prefix, precision):
+        self.precision = precision
+        self.convs = [conv_bn_layer(sd, f"{prefix}.convolutions.{i}", precision, "tanh" if i < 4 else "none")
+                      for i in range(5)]
+
+    def __call__(self, mel_op, mel_f32, B, T, taps=None):
+        """mel_op: [B][T][80] operand dtype; mel_f32: exact fp32 [B][T][80].  Returns mel + postnet(mel), fp32."""
+        h = mel_op
+        for i in range(4):
+            o = ops.alloc_act(B, T, 512, self.precision, h.device)
+            self.convs[i](h, B, T, out=o)
+            h = o
+            if taps is not None:
+                taps[f"post_conv{i}"] = packing.act_to_float(h, self.precision)
+        out = torch.empty(B, T, 80, dtype=torch.float32, device=h.device)
+        self.convs[4](h, B, T, out2=out.view(B * T, 80), residual=mel_f32.view(B * T, 80))
+        return out

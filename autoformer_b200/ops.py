@@ -1,0 +1,203 @@
+"""Thin Python wrappers over the C ABI (include/avc_b200.h).  torch is used only for device memory and the
+current stream; every arithmetic operation runs in libavc_b200.so.  Nothing here falls back to torch math."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import packing
+from .packing import KC, TORCH_DTYPE
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("autoformer_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _dt(precision):
+    return {"tf32": _lib.DTYPE_TF32, "bf16": _lib.DTYPE_BF16, "fp32": 2}[precision]
+
+
+def alloc_act(B, rows, C, precision, device):
+    """Activation buffer carrying C logical channels in the storage format of `precision`."""
+    return torch.empty(B, rows, packing.act_channels(C, precision), dtype=TORCH_DTYPE[precision], device=device)
+
+
+class ConvGemm:
+    """A packed conv / linear layer bound to avc_conv_gemm.
+
+    ``w``/``bias``/``meta`` come from ``packing.pack_conv*``; ``tap_t0``/``tap_dt`` per source give the buffer row
+    read by tap 0 for output frame 0 (``-pad`` for an unpadded input buffer) and the dilation."""
+
+    def __init__(self, w, bias, meta, tap_t0=None, tap_dt=None, act="none"):
+        self.w, self.bias, self.meta = w, bias, meta
+        n_src = len(meta["taps"])
+        self.tap_t0 = list(tap_t0) if tap_t0 is not None else [-(k // 2) for k in meta["taps"]]
+        self.tap_dt = list(tap_dt) if tap_dt is not None else [1] * n_src
+        self.act = _lib.ACTS[act]
+        self.precision = meta["precision"]
+
+    def to(self, device):
+        self.w = self.w.to(device)
+        self.bias = self.bias.to(device)
+        return self
+
+    def __call__(self, srcs, B, T, out=None, out_row0=0, out_dtype=None, round_tf32=True, reflect=0, out2=None,
+                 residual=None):
+        """srcs: list of channels-last activation tensors [B][rows][C_s] (one per packed source).
+        out: [B][rows_out][N] (operand dtype) written at rows out_row0 + t, or None; out2: fp32 [B*T][N] exact."""
+        lib = _lib.load()
+        meta = self.meta
+        if not isinstance(srcs, (list, tuple)):
+            srcs = [srcs]
+        _require_cuda(self.w, *srcs)
+        split = bool(meta.get("split"))
+        if split:      # one buffer [hi | lo]: source 0 = all 2C channels, source 1 = the hi half
+            assert len(srcs) == 1 and srcs[0].shape[2] == 2 * meta["logical_channels"], srcs[0].shape
+            srcs = [srcs[0], srcs[0][:, :, :meta["logical_channels"]]]
+        assert len(srcs) == len(meta["taps"])
+        d = _lib.GemmDesc()
+        want = TORCH_DTYPE[self.precision]
+        for s, a in enumerate(srcs):
+            assert a.dim() == 3 and a.shape[0] == B and a.dtype == want and a.stride(2) == 1, (a.shape, a.dtype)
+            assert a.shape[2] == meta["channels"][s], (a.shape, meta["channels"])
+            assert a.stride(0) == a.shape[1] * a.stride(1)
+            d.a_ptr[s] = a.data_ptr()
+            d.a_channels[s] = a.shape[2]
+            d.a_ld[s] = a.stride(1)
+            d.a_rows_per_utt[s] = a.shape[1]
+            d.a_taps[s] = meta["taps"][s]
+            d.a_tap_t0[s] = self.tap_t0[s]
+            d.a_tap_dt[s] = self.tap_dt[s]
+        d.w_ptr = self.w.data_ptr()
+        d.n_pad, d.k_pad = meta["n_pad"], meta["k_pad"]
+        d.dtype = _lib.DTYPE_TF32 if self.precision == "tf32" else _lib.DTYPE_BF16
+        d.B, d.T, d.N = B, T, meta["N"]
+        d.bias = self.bias.data_ptr()
+        d.act = self.act
+        if out is not None:
+            assert out.is_cuda and out.dim() == 3 and out.shape[0] == B and out.stride(2) == 1
+            assert out.shape[2] >= packing.act_channels(meta["N"], self.precision)
+            assert out.stride(0) == out.shape[1] * out.stride(1)
+            d.out = out.data_ptr()
+            d.out_ld = out.stride(1)
+            d.out_rows_per_utt = out.shape[1]
+            d.out_row0 = out_row0
+            d.out_dtype = (2 if split else 1) if out.dtype == torch.bfloat16 else 0
+            assert out.dtype in (torch.float32, torch.bfloat16)
+            d.out_round_tf32 = 1 if (round_tf32 and out.dtype == torch.float32) else 0
+            d.out_reflect = reflect
+        if out2 is not None:
+            assert out2.is_cuda and out2.dtype == torch.float32 and out2.stride(-1) == 1
+            d.out2 = out2.data_ptr()
+            d.out2_ld = out2.stride(-2)
+        if residual is not None:
+            assert residual.is_cuda and residual.dtype == torch.float32 and residual.stride(-1) == 1
+            d.residual = residual.data_ptr()
+            d.res_ld = residual.stride(-2)
+        d.block_n = meta["block_n"]
+        _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
+        return out if out is not None else out2
+
+
+def choose_gate_group(B, H, persistent=False, n_sm=148):
+    """Hidden units per accumulator tile (tile width 4G): fill the SMs without exceeding one wave when persistent."""
+    m_tiles = (B + 127) // 128
+    for g in (64, 32, 16):
+        if H % g:
+            continue
+        ctas = m_tiles * (H // g)
+        if ctas >= 96 and (not persistent or ctas <= n_sm):
+            return g
+    for g in (16, 32, 64):
+        if H % g == 0 and (not persistent or m_tiles * (H // g) <= n_sm):
+            return g
+    raise RuntimeError(f"no gate group fits B={B} H={H} persistent={persistent}")
+
+
+def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False):
+    """Run the recurrence of one uni-directional layer.  xproj [B*T][4H] fp32 (packed gate order, bias included)."""
+    lib = _lib.load()
+    _require_cuda(xproj, w_hh)
+    dev = xproj.device
+    assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
+    wk = 3 * H if precision == "fp32" else H
+    assert w_hh.dtype == TORCH_DTYPE[precision] and w_hh.shape == (4 * H, wk) and w_hh.is_contiguous()
+    if hseq is None:
+        hseq = alloc_act(B, T, H, precision, dev)
+    assert hseq.is_contiguous() and hseq.shape == (B, T, packing.act_channels(H, precision))
+    assert hseq.dtype == TORCH_DTYPE[precision]
+    c_state = torch.empty(B, H, dtype=torch.float32, device=dev)
+    d = _lib.LstmDesc()
+    d.xproj = xproj.data_ptr()
+    d.w_hh = w_hh.data_ptr()
+    d.hseq = hseq.data_ptr()
+    if hseq_f32 is not None:
+        assert hseq_f32.is_contiguous() and hseq_f32.shape == (B, T, H) and hseq_f32.dtype == torch.float32
+        d.hseq_f32 = hseq_f32.data_ptr()
+    if h_last is not None:
+        assert h_last.is_contiguous() and h_last.shape == (B, H) and h_last.dtype == torch.float32
+        d.h_last = h_last.data_ptr()
+    d.c_state = c_state.data_ptr()
+    d.B, d.T, d.H = B, T, H
+    d.dtype = _dt(precision)
+    d.gate_group = group
+    d.persistent = 1 if persistent else 0
+    bar = None
+    if persistent:
+        bar = torch.zeros(4, dtype=torch.int32, device=dev)
+        d.grid_barrier = bar.data_ptr()
+    _lib.check(lib.avc_lstm_seq(ctypes.byref(d), _stream()), "avc_lstm_seq")
+    return hseq
+
+
+def bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=True, split=False):
+    """xproj [B*T][8H] fp32; w_hh [2][4H][H] fp32; out [B][T][2H] (fp32/bf16; split: [B][T][4H] bf16) and/or
+    codes [B][T/freq][2H] fp32."""
+    lib = _lib.load()
+    _require_cuda(xproj, w_hh)
+    assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 8 * H
+    assert w_hh.dtype == torch.float32 and w_hh.is_contiguous() and w_hh.shape == (2, 4 * H, H)
+    out_ptr, out_dtype = None, 0
+    if out is not None:
+        assert out.is_contiguous() and out.shape == (B, T, (4 if split else 2) * H)
+        out_ptr, out_dtype = out.data_ptr(), ((2 if split else 1) if out.dtype == torch.bfloat16 else 0)
+    codes_ptr = None
+    if codes is not None:
+        assert codes.is_contiguous() and codes.dtype == torch.float32 and codes.shape == (B, T // freq, 2 * H)
+        codes_ptr = codes.data_ptr()
+    _lib.check(lib.avc_bilstm_small(xproj.data_ptr(), w_hh.data_ptr(), out_ptr, out_dtype, 1 if round_tf32 else 0,
+                                    codes_ptr, B, T, H, freq, _stream()), "avc_bilstm_small")
+    return out, codes
+
+
+def concat_bcast(seq, vec, T, div, precision, round_tf32=True):
+    """[seq[b, t // div, :] || vec[b, :]] -> [B][T][C1+C2] in the operand dtype of `precision`."""
+    lib = _lib.load()
+    _require_cuda(seq, vec)
+    assert seq.dtype == torch.float32 and vec.dtype == torch.float32 and seq.is_contiguous() and vec.is_contiguous()
+    B, Tin, C1 = seq.shape
+    C2 = vec.shape[1]
+    assert Tin * div == T and vec.shape[0] == B
+    out = alloc_act(B, T, C1 + C2, precision, seq.device)
+    _lib.check(lib.avc_concat_bcast(seq.data_ptr(), vec.data_ptr(), out.data_ptr(), B, T, C1, C2, div,
+                                    _dt(precision), 1 if round_tf32 else 0, _stream()),
+               "avc_concat_bcast")
+    return out
+
+
+def linear_l2norm(h, w, bias):
+    lib = _lib.load()
+    _require_cuda(h, w, bias)
+    assert h.dtype == torch.float32 and h.is_contiguous() and w.is_contiguous() and bias.is_contiguous()
+    B, K = h.shape
+    N = w.shape[0]
+    out = torch.empty(B, N, dtype=torch.float32, device=h.device)
+    _lib.check(lib.avc_linear_l2norm(h.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, K, N, _stream()),
+               "avc_linear_l2norm")
+    return out

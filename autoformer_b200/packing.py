@@ -1,0 +1,191 @@
+"""Host-side weight folding / re-packing for the sm_100a kernels.  Pure tensor code: runs on CPU or GPU.
+
+Everything here happens once per ``load_state_dict`` (not per forward):
+  * BatchNorm (eval) folded into the preceding conv: scale into the weights, shift into the bias
+    (factory/AutoVC.py:26-39 + nn.BatchNorm1d running statistics)
+  * conv weights (C_out, C_in, K) -> K-major GEMM operand [n_pad][taps * chunks * kc], tap-major, each tap's
+    channels zero-padded to a whole number of 128-byte k-blocks (kc = 32 TF32 / 64 bf16 channels)
+  * LSTM gate rows interleaved in groups of G hidden units so one accumulator tile holds i,f,g,o of G units
+  * weight norm folded (melgan/modules.py:18-23)
+  * fp32 operands rounded to TF32 (round-to-nearest, ties away) so the tensor core's truncation is exact
+"""
+import torch
+
+# precision modes: "tf32" (fp32 storage, one TF32 pass), "bf16" (one bf16 pass),
+# "fp32" (split bf16: hi + lo channels, three bf16 products per fp32 product -- fp32-grade accuracy)
+KC = {"tf32": 32, "bf16": 64, "fp32": 64}
+TORCH_DTYPE = {"tf32": torch.float32, "bf16": torch.bfloat16, "fp32": torch.bfloat16}
+PRECISIONS = tuple(KC)
+
+
+def act_channels(c: int, precision: str) -> int:
+    """Channels of the activation buffer that carries c logical channels."""
+    return 2 * c if precision == "fp32" else c
+
+
+def split_bf16(t: torch.Tensor):
+    """v -> (hi, lo) with hi = bf16(v), lo = bf16(v - hi): v ~ hi + lo to ~2^-17 relative."""
+    t = t.float()
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def to_act(t: torch.Tensor, precision: str) -> torch.Tensor:
+    """fp32 channels-last activation -> the buffer format of `precision` (tests / host-side staging)."""
+    if precision == "tf32":
+        return round_tf32(t.float())
+    if precision == "bf16":
+        return t.to(torch.bfloat16)
+    hi, lo = split_bf16(t)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def act_to_float(buf: torch.Tensor, precision: str) -> torch.Tensor:
+    if precision == "fp32":
+        c = buf.shape[-1] // 2
+        return buf[..., :c].float() + buf[..., c:].float()
+    return buf.float()
+
+
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """cvt.rna.tf32.f32 on the host: keep 10 mantissa bits, round to nearest, ties away from zero."""
+    assert t.dtype == torch.float32
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def to_operand(t: torch.Tensor, precision: str) -> torch.Tensor:
+    """Weights / activations as the tensor core reads them (for "fp32" use split_bf16 / to_act instead)."""
+    if precision == "tf32":
+        return round_tf32(t.float())
+    if precision == "bf16":
+        return t.to(torch.bfloat16)
+    raise ValueError("split precision has no single-tensor operand form")
+
+
+def _ceil_to(x, m):
+    return (x + m - 1) // m * m
+
+
+def choose_block_n(n: int) -> int:
+    """Output-channel tile: 256 when the layer is wide enough, otherwise the smallest tile that covers n."""
+    if n >= 256:
+        return 256
+    if n > 64:
+        return 128
+    return 64
+
+
+def fold_bn(weight, bias, bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
+    """conv + BatchNorm(eval) -> conv:  w' = s w,  b' = beta + s (b - mean),  s = gamma / sqrt(var + eps)."""
+    s = bn_weight.double() / torch.sqrt(running_var.double() + eps)
+    w = weight.double() * s.view(-1, *([1] * (weight.dim() - 1)))
+    b = bn_bias.double() + s * (bias.double() - running_mean.double())
+    return w.float(), b.float()
+
+
+def pack_conv_sources(weights, bias, precision, block_n=None):
+    """weights: list of (C_out, C_in_s, K_s) tensors, one per K-concatenated activation source.
+
+    Returns (W [n_pad][k_pad] operand dtype, bias [n_pad] fp32, meta dict)."""
+    kc = KC[precision]
+    n = weights[0].shape[0]
+    if precision == "fp32":
+        # a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: source 0 = [a_hi|a_lo] x [w_hi|w_hi], source 1 = a_hi x w_lo
+        assert len(weights) == 1, "split precision uses both source slots for one logical source"
+        hi, lo = split_bf16(weights[0])
+        w_p, b_p, meta = pack_conv_sources([torch.cat([hi, hi], dim=1).float(), lo.float()], bias, "bf16", block_n)
+        meta.update(precision="fp32", split=True, logical_channels=weights[0].shape[1])
+        return w_p, b_p, meta
+    bn_tile = block_n or choose_block_n(n)
+    n_pad = _ceil_to(n, bn_tile)
+    cols = []
+    taps, chans = [], []
+    for w in weights:
+        assert w.dim() == 3 and w.shape[0] == n
+        c_in, k = w.shape[1], w.shape[2]
+        chunks = (c_in + kc - 1) // kc
+        wp = torch.zeros(n, k, chunks * kc, dtype=torch.float32, device=w.device)
+        wp[:, :, :c_in] = w.float().permute(0, 2, 1)
+        cols.append(wp.reshape(n, k * chunks * kc))
+        taps.append(k)
+        chans.append(c_in)
+    wk = torch.cat(cols, dim=1)
+    k_pad = wk.shape[1]
+    wfull = torch.zeros(n_pad, k_pad, dtype=torch.float32, device=wk.device)
+    wfull[:n] = wk
+    bfull = torch.zeros(n_pad, dtype=torch.float32, device=wk.device)
+    bfull[:n] = bias.float()
+    meta = dict(N=n, n_pad=n_pad, k_pad=k_pad, block_n=bn_tile, taps=taps, channels=chans, precision=precision)
+    return to_operand(wfull, precision).contiguous(), bfull.contiguous(), meta
+
+
+def pack_conv(weight, bias, precision, block_n=None):
+    return pack_conv_sources([weight], bias, precision, block_n)
+
+
+def pack_linear(weight, bias, precision, block_n=None):
+    """nn.Linear (N, K) as a 1-tap convolution."""
+    return pack_conv_sources([weight.unsqueeze(-1)], bias, precision, block_n)
+
+
+def gate_permutation(hidden: int, group: int, device=None) -> torch.Tensor:
+    """index[p] = PyTorch gate row (g*H + u) stored at packed position p = (u//G)*4G + g*G + u%G."""
+    assert hidden % group == 0
+    p = torch.arange(4 * hidden, device=device)
+    blk = p // (4 * group)
+    g = (p % (4 * group)) // group
+    u = blk * group + p % group
+    return g * hidden + u
+
+
+def pack_lstm_ih(w_ih, b_ih, b_hh, precision, group):
+    """Input projection of one uni-directional layer with gate-interleaved output columns."""
+    h = w_ih.shape[0] // 4
+    perm = gate_permutation(h, group, w_ih.device)
+    return pack_linear(w_ih[perm], (b_ih + b_hh)[perm], precision)
+
+
+def pack_lstm_hh(w_hh, precision, group):
+    h = w_hh.shape[1]
+    perm = gate_permutation(h, group, w_hh.device)
+    w = w_hh[perm].float()
+    if precision == "fp32":
+        hi, lo = split_bf16(w)
+        return torch.cat([hi, hi, lo], dim=1).contiguous()      # against [h_hi | h_lo | h_hi]
+    return to_operand(w, precision).contiguous()
+
+
+def pack_bilstm_ih(w_ih_f, b_ih_f, b_hh_f, w_ih_r, b_ih_r, b_hh_r, precision):
+    """Both directions of a bidirectional layer in one projection: columns dir*4H + gate*H + u."""
+    w = torch.cat([w_ih_f, w_ih_r], dim=0)
+    b = torch.cat([b_ih_f + b_hh_f, b_ih_r + b_hh_r], dim=0)
+    return pack_linear(w, b, precision)
+
+
+def fold_weight_norm(weight_g, weight_v):
+    """Old-style torch.nn.utils.weight_norm, dim=0: W = g * v / ||v|| (norm over all axes but 0)."""
+    v = weight_v.double()
+    norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape([-1] + [1] * (v.dim() - 1))
+    return (weight_g.double() * v / norm).float()
+
+
+def conv_transpose_as_conv(weight, stride, padding):
+    """ConvTranspose1d(C_in, C_out, K=2r, stride=r, padding=p) as a 3-tap convolution producing r phases.
+
+    weight (C_in, C_out, K).  Output sample n = r*q + phi of the transposed conv equals
+        sum_i sum_{d in -1,0,1} x[i, q + d] * w[i, o, phi + p - r*d]        (terms with k outside [0,K) vanish)
+    so with output channel index (phi*C_out + o) and taps d = -1,0,1 (tap_t0 = -1) it is an ordinary conv whose
+    channels-last output [B][L][r*C_out] IS the up-sampled signal [B][r*L][C_out] (melgan/modules.py:101-112).
+    Returns (C_out*r, C_in, 3)."""
+    c_in, c_out, k = weight.shape
+    r = stride
+    w = torch.zeros(r, c_out, c_in, 3, dtype=weight.dtype, device=weight.device)
+    for phi in range(r):
+        for di, d in enumerate((-1, 0, 1)):
+            kk = phi + padding - r * d
+            if 0 <= kk < k:
+                w[phi, :, :, di] = weight[:, :, kk].t()
+    return w.reshape(r * c_out, c_in, 3)

@@ -1,0 +1,148 @@
+/*
+ * avc_b200.h -- C ABI of libavc_b200.so, the sm_100a kernel library behind the drop-in
+ * model classes in autoformer_b200/ (factory.AutoVC / LstmDV / melgan Generator ...).
+ *
+ * The reference (achyun/Autoformer) has no FFI of its own: its boundary is the Python
+ * nn.Module surface.  Each entry point below replaces the torch.nn calls the
+ * reference makes on the conversion forward path; the citation names the reference lines
+ * whose arithmetic the entry point performs.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless said otherwise
+ *   - the caller owns every buffer (incl. scratch); the library never allocates device memory
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no host sync inside
+ *   - return 0 on success, negative on error; avc_last_error() gives the text (thread local)
+ *   - activations are channels-last:  [utterance][frame][channel], channel contiguous
+ *   - dtype: 0 = fp32 storage, TF32 tensor-core operands, fp32 accumulate
+ *            1 = bf16 storage and operands, fp32 accumulate
+ *            2 = "split bf16" (fp32-grade): every fp32 value v is stored as two bf16 channels
+ *                hi = bf16(v), lo = bf16(v - hi) in a buffer of 2C channels laid out [hi(0..C) | lo(0..C)];
+ *                a product a*w is evaluated as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo by K-concatenating the three
+ *                terms into one bf16 tensor-core GEMM (error ~2^-16 instead of TF32's 2^-11, 1.5x the MMA work).
+ *                For avc_conv_gemm this is expressed with dtype = 1 and two sources over the same buffer
+ *                (source 0: all 2C channels against [w_hi|w_hi]; source 1: the first C channels against w_lo);
+ *                out_dtype = 2 makes the epilogue write the split format.
+ */
+#ifndef AVC_B200_H_
+#define AVC_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVC_DTYPE_TF32 0
+#define AVC_DTYPE_BF16 1
+#define AVC_DTYPE_BF16X3 2
+
+#define AVC_ACT_NONE 0
+#define AVC_ACT_RELU 1
+#define AVC_ACT_TANH 2
+#define AVC_ACT_LRELU 3 /* slope 0.2, melgan/modules.py:75,100,120 */
+
+int avc_version(void);
+const char* avc_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+long long avc_launch_count(void);
+
+/*
+ * Implicit-GEMM convolution / dense GEMM on the tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *
+ *   out[b, t, n] = act( bias[n] + sum_s sum_k sum_c  W[n, (s,k,c)] * A_s[b, tap_t0_s + t + k*tap_dt_s, c] ) (+ residual)
+ *
+ * Replaces: nn.Conv1d + nn.BatchNorm1d(eval) + relu/tanh  (factory/AutoVC.py:26-41,50-51,79-94,104-108,
+ * 127-179; factory/Norm.py:21-37), nn.Linear (factory/Norm.py:40-50, factory/AutoVC.py:98,112),
+ * the LSTM input projections W_ih x + b_ih + b_hh of nn.LSTM (factory/AutoVC.py:43,77,96;
+ * factory/LstmDV.py:12), and the MelGAN Conv1d / ConvTranspose1d layers (melgan/modules.py:72-130).
+ * BatchNorm is folded by the caller: scale into W, shift into bias.
+ *
+ * Rows of A outside [0, a_rows_per_utt) read as zero (the convolution's zero padding).
+ * Weights are packed [n_pad][k_pad], K contiguous, k_pad = sum_s taps_s * ceil(C_s / KC) * KC with
+ * KC = 32 (tf32) or 64 (bf16) channels per k-block, zero filled; n_pad is a multiple of block_n.
+ */
+typedef struct avc_gemm_desc {
+  const void* a_ptr[2];      /* up to two activation sources (K-concatenated) */
+  int a_channels[2];         /* C_s */
+  long long a_ld[2];         /* elements between consecutive rows (>= C_s, 16-byte multiple) */
+  int a_rows_per_utt[2];     /* rows per utterance in the buffer (frames + halo rows) */
+  int a_taps[2];             /* taps of source s; 0 = source unused */
+  int a_tap_t0[2];           /* buffer row that tap 0 reads for output frame 0 (negative => zero pad) */
+  int a_tap_dt[2];           /* row step between taps (dilation) */
+  const void* w_ptr;         /* packed weights */
+  int n_pad, k_pad;
+  int dtype;                 /* AVC_DTYPE_* of A and W */
+  int B, T;                  /* output index space: B utterances x T frames */
+  int N;                     /* real output channels (multiple of 4) */
+  const float* bias;         /* [n_pad] fp32 */
+  int act;                   /* AVC_ACT_* */
+  void* out;                 /* [B][out_rows_per_utt][out_ld], written at row out_row0 + t */
+  long long out_ld;
+  int out_rows_per_utt, out_row0;
+  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column n, lo at column N + n (out_ld >= 2N) */
+  int out_round_tf32;        /* round fp32 outputs to TF32 (rna) so the next GEMM reads them exactly */
+  int out_reflect;           /* also write `out_reflect` reflected halo rows each side (ReflectionPad1d,
+                                melgan/modules.py:77,96,121); needs out_row0 >= out_reflect */
+  float* out2;               /* optional exact fp32 copy, rows b*T+t, ld out2_ld (may be NULL) */
+  long long out2_ld;
+  const float* residual;     /* optional fp32 [B*T][res_ld], added after the activation */
+  long long res_ld;
+  int block_n;               /* 64 / 128 / 256; 0 = choose */
+} avc_gemm_desc;
+
+int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
+
+/*
+ * Recurrence of one uni-directional LSTM layer with hidden size H (multiple of gate_group, >= 64):
+ * for t = 0..T-1:  z = xproj[b,t,:] + W_hh h_{t-1};  c = s(z_f) c + s(z_i) tanh(z_g);  h = s(z_o) tanh(c)
+ * (nn.LSTM semantics, gate order i,f,g,o, zero initial state; factory/AutoVC.py:77,96,103,110;
+ * factory/LstmDV.py:12,20).  Each step is a [B x H] x [H x 4H] tensor-core GEMM whose epilogue is the
+ * cell update; rows of W_hh and columns of xproj are gate-interleaved in groups of `gate_group`
+ * hidden units:  packed index = (u / G) * 4G + gate * G + (u % G).
+ */
+typedef struct avc_lstm_desc {
+  const float* xproj;        /* [B*T][4H] fp32, packed column order, biases included */
+  const void* w_hh;          /* [4H][H] packed row order, dtype; dtype 2: [4H][3H] = [w_hi | w_hi | w_lo] bf16 */
+  void* hseq;                /* [B][T][H] dtype (dtype 2: [B][T][2H] split bf16): output sequence and recurrent operand */
+  float* hseq_f32;           /* optional exact fp32 copy of the output sequence (may be NULL) */
+  float* h_last;             /* optional [B][H] fp32: h_{T-1} only (LstmDV.py:21) (may be NULL) */
+  float* c_state;            /* [B][H] fp32 scratch */
+  int B, T, H;
+  int dtype;
+  int gate_group;            /* G: 16, 32 or 64 */
+  int persistent;            /* 0 = one launch per step; 1 = one cooperative launch, grid barrier per step */
+  unsigned int* grid_barrier;/* 1 word of scratch (persistent mode) */
+} avc_lstm_desc;
+
+int avc_lstm_seq(const avc_lstm_desc* d, void* stream);
+
+/*
+ * Bidirectional small-H LSTM layer (H <= 64) with the recurrent weights held in shared memory, one warp
+ * per (utterance, direction); optionally emits only the down-sampled content code
+ * code_j = [h_fwd[jF+F-1] || h_bwd[jF]]  (factory/AutoVC.py:43,54-66).
+ *   xproj  [B*T][8H] fp32: columns dir*4H + gate*H + u, biases included
+ *   w_hh   [2][4H][H] fp32 (PyTorch row order i,f,g,o)
+ *   out    [B][T][2H] (fwd | bwd) in out_dtype (2: [B][T][4H] split bf16), or NULL
+ *   codes  [B][T/freq][2H] fp32, or NULL
+ */
+int avc_bilstm_small(const float* xproj, const float* w_hh, void* out, int out_dtype, int out_round_tf32,
+                     float* codes, int B, int T, int H, int freq, void* stream);
+
+/*
+ * out[b,t,:] = [ seq[b, t / div, 0:C1] || vec[b, 0:C2] ]   (channels-last concat with broadcast)
+ * Replaces the speaker-code concat of Encoder.forward (factory/AutoVC.py:46-48; div = 1) and the code
+ * up-sampling + target-speaker concat of AutoVC.forward (factory/AutoVC.py:197-204; div = freq).
+ *   seq [B][T/div][C1] fp32, vec [B][C2] fp32, out [B][T][C1+C2] in out_dtype (2: [B][T][2(C1+C2)] split bf16).
+ *   C1, C2 multiples of 4.
+ */
+int avc_concat_bcast(const float* seq, const float* vec, void* out, int B, int T, int C1, int C2, int div,
+                     int out_dtype, int out_round_tf32, void* stream);
+
+/*
+ * LstmDV tail: e = W h_last + b;  out = e / ||e||_2   (factory/LstmDV.py:21-24).  h [B][K], W [N][K], out [B][N].
+ */
+int avc_linear_l2norm(const float* h, const float* w, const float* bias, float* out, int B, int K, int N,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVC_B200_H_ */
