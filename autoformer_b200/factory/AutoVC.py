@@ -60,14 +60,17 @@ class _Plan:
         self.dec_convs = [layers.conv_bn_layer(sd, f"decoder.convolutions.{i}", precision, "relu") for i in range(3)]
         self.lstm2 = layers.lstm_layers(sd, "decoder.lstm2", 2, precision)
         self.linear = ops.ConvGemm(*packing.pack_linear(sd["decoder.linear_projection.linear_layer.weight"],
-                                                        sd["decoder.linear_projection.linear_layer.bias"], precision))
+                                                        sd["decoder.linear_projection.linear_layer.bias"], precision),
+                                   tag="linear")
         self.postnet = layers.Postnet(sd, "postnet", precision)
 
 
 class AutoVC(nn.Module):
     """AutoVC generator (Qian et al. 2019) -- B200 kernels behind the reference API (factory/AutoVC.py:182-211).
 
-    Extra, optional attributes (not in the reference): ``precision`` ("tf32" default | "bf16"),
+    Extra, optional attributes (not in the reference): ``precision`` ("fp32" default: split-bf16
+    three-product tensor-core arithmetic, ~3e-5 from the fp32 reference | "tf32": one TF32 pass, ~1e-3 |
+    "bf16": one bf16 pass, ~1e-2),
     ``persistent_lstm`` (one cooperative launch per LSTM layer instead of one launch per frame),
     ``collect_taps`` (keep fp32 copies of every stage in ``self.taps`` for parity tests)."""
 
@@ -77,7 +80,7 @@ class AutoVC(nn.Module):
         self.decoder = Decoder(dim_neck, dim_emb, dim_pre)
         self.postnet = Postnet()
         self.dim_neck, self.dim_emb, self.dim_pre, self.freq = dim_neck, dim_emb, dim_pre, freq
-        self.precision = "tf32"
+        self.precision = "fp32"
         self.persistent_lstm = False
         self.collect_taps = False
         self.taps = {}

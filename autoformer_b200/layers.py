@@ -31,7 +31,7 @@ def conv_bn_layer(sd, prefix, precision, act):
     """nn.Sequential(ConvNorm(k5,p2), BatchNorm1d) (+act) -> one packed conv (factory/AutoVC.py:26-39)."""
     w, b = packing.fold_bn(sd[f"{prefix}.0.conv.weight"], sd[f"{prefix}.0.conv.bias"], sd[f"{prefix}.1.weight"],
                            sd[f"{prefix}.1.bias"], sd[f"{prefix}.1.running_mean"], sd[f"{prefix}.1.running_var"])
-    return ops.ConvGemm(*packing.pack_conv(w, b, precision), act=act)
+    return ops.ConvGemm(*packing.pack_conv(w, b, precision), act=act, tag="conv")
 
 
 class LstmLayer:
@@ -45,7 +45,8 @@ class LstmLayer:
 
     def packs(self, group):
         if group not in self._packs:
-            ih = ops.ConvGemm(*packing.pack_lstm_ih(self.w_ih, self.b_ih, self.b_hh, self.precision, group))
+            ih = ops.ConvGemm(*packing.pack_lstm_ih(self.w_ih, self.b_ih, self.b_hh, self.precision, group),
+                              tag="inproj")
             hh = packing.pack_lstm_hh(self.w_hh, self.precision, group)
             self._packs[group] = (ih, hh)
         return self._packs[group]
@@ -74,7 +75,7 @@ class BiLstmSmall:
             g = lambda n, d="": sd[f"{prefix}.{n}_l{l}{d}"].detach()
             ih = ops.ConvGemm(*packing.pack_bilstm_ih(g("weight_ih"), g("bias_ih"), g("bias_hh"),
                                                       g("weight_ih", "_reverse"), g("bias_ih", "_reverse"),
-                                                      g("bias_hh", "_reverse"), precision))
+                                                      g("bias_hh", "_reverse"), precision), tag="inproj")
             hh = torch.stack([g("weight_hh"), g("weight_hh", "_reverse")]).float().contiguous()
             self.layers.append((ih, hh))
         self.H = self.layers[0][1].shape[2]

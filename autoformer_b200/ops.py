@@ -13,6 +13,53 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class Profiler:
+    """Optional per-op CUDA-event timing on the launching stream (bench.py's roofline numbers).
+    Disabled by default: the hot path then records nothing."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (family, start_event, end_event, work dict)
+
+    class _Span:
+        def __init__(self, prof, family, work):
+            self.prof, self.family, self.work = prof, family, work
+
+        def __enter__(self):
+            if self.prof.enabled:
+                self.start = torch.cuda.Event(enable_timing=True)
+                self.end = torch.cuda.Event(enable_timing=True)
+                self.start.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.prof.enabled:
+                self.end.record()
+                self.prof.records.append((self.family, self.start, self.end, self.work))
+            return False
+
+    def span(self, family, **work):
+        return Profiler._Span(self, family, work)
+
+    def summary(self):
+        """family -> dict(ms=total, launches=n, flops=sum, bytes=sum); call after a synchronize."""
+        out = {}
+        for family, s, e, work in self.records:
+            d = out.setdefault(family, dict(ms=0.0, calls=0, launches=0, flops=0.0, bytes=0.0))
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            d["launches"] += work.get("launches", 1)
+            d["flops"] += work.get("flops", 0.0)
+            d["bytes"] += work.get("bytes", 0.0)
+        return out
+
+    def reset(self):
+        self.records = []
+
+
+PROFILER = Profiler()
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -34,8 +81,12 @@ class ConvGemm:
     ``w``/``bias``/``meta`` come from ``packing.pack_conv*``; ``tap_t0``/``tap_dt`` per source give the buffer row
     read by tap 0 for output frame 0 (``-pad`` for an unpadded input buffer) and the dilation."""
 
-    def __init__(self, w, bias, meta, tap_t0=None, tap_dt=None, act="none"):
+    def __init__(self, w, bias, meta, tap_t0=None, tap_dt=None, act="none", tag="gemm"):
         self.w, self.bias, self.meta = w, bias, meta
+        self.tag = tag
+        # algorithmic MACs per output row: real channels x taps x real output channels
+        lc = [meta["logical_channels"]] if meta.get("split") else meta["channels"]
+        self.macs_per_row = sum(c * k for c, k in zip(lc, meta["taps"])) * meta["N"]
         n_src = len(meta["taps"])
         self.tap_t0 = list(tap_t0) if tap_t0 is not None else [-(k // 2) for k in meta["taps"]]
         self.tap_dt = list(tap_dt) if tap_dt is not None else [1] * n_src
@@ -101,7 +152,8 @@ class ConvGemm:
             d.residual = residual.data_ptr()
             d.res_ld = residual.stride(-2)
         d.block_n = meta["block_n"]
-        _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
+        with PROFILER.span(self.tag, flops=2.0 * self.macs_per_row * B * T):
+            _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
         return out if out is not None else out2
 
 
@@ -152,7 +204,8 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
     if persistent:
         bar = torch.zeros(4, dtype=torch.int32, device=dev)
         d.grid_barrier = bar.data_ptr()
-    _lib.check(lib.avc_lstm_seq(ctypes.byref(d), _stream()), "avc_lstm_seq")
+    with PROFILER.span("lstm_step", flops=2.0 * 4 * H * H * B * T, launches=1 if persistent else T):
+        _lib.check(lib.avc_lstm_seq(ctypes.byref(d), _stream()), "avc_lstm_seq")
     return hseq
 
 
@@ -171,8 +224,9 @@ def bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=
     if codes is not None:
         assert codes.is_contiguous() and codes.dtype == torch.float32 and codes.shape == (B, T // freq, 2 * H)
         codes_ptr = codes.data_ptr()
-    _lib.check(lib.avc_bilstm_small(xproj.data_ptr(), w_hh.data_ptr(), out_ptr, out_dtype, 1 if round_tf32 else 0,
-                                    codes_ptr, B, T, H, freq, _stream()), "avc_bilstm_small")
+    with PROFILER.span("bilstm_small", flops=2.0 * 2 * 4 * H * H * B * T, bytes=4.0 * B * T * 8 * H):
+        _lib.check(lib.avc_bilstm_small(xproj.data_ptr(), w_hh.data_ptr(), out_ptr, out_dtype, 1 if round_tf32 else 0,
+                                        codes_ptr, B, T, H, freq, _stream()), "avc_bilstm_small")
     return out, codes
 
 
@@ -185,9 +239,10 @@ def concat_bcast(seq, vec, T, div, precision, round_tf32=True):
     C2 = vec.shape[1]
     assert Tin * div == T and vec.shape[0] == B
     out = alloc_act(B, T, C1 + C2, precision, seq.device)
-    _lib.check(lib.avc_concat_bcast(seq.data_ptr(), vec.data_ptr(), out.data_ptr(), B, T, C1, C2, div,
-                                    _dt(precision), 1 if round_tf32 else 0, _stream()),
-               "avc_concat_bcast")
+    with PROFILER.span("concat", bytes=float(seq.numel() * 4 + vec.numel() * 4 + out.numel() * out.element_size())):
+        _lib.check(lib.avc_concat_bcast(seq.data_ptr(), vec.data_ptr(), out.data_ptr(), B, T, C1, C2, div,
+                                        _dt(precision), 1 if round_tf32 else 0, _stream()),
+                   "avc_concat_bcast")
     return out
 
 

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the batched voice-conversion forward path (BASELINE.json metric: converted mel-frames/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a kernels
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU PyTorch path (oracle port)
+
+Workload (BASELINE.json configs[1]): AutoVC(32,256,512,32) conversion forward, batch 512 utterances x 128 frames
+x 80 mel bins per GPU (weak scaling: every rank converts its own batch), random-init weights, synthetic inputs.
+One "step" = one forward over the batch.  `value` times K steps with inputs resident in HBM; `e2e` times the same
+K steps through the public model API starting from pinned HOST buffers (H2D of x/c_org/c_trg and D2H of the three
+outputs inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODEL_ARGS = (32, 256, 512, 32)            # AutoVC "original" hyper-parameters
+FLOP_PER_FRAME = 56_770_560                # conv 23,511,040 + in-proj/Linear 14,352,384 + recurrent 18,907,136
+FAMILY_FLOP_PER_FRAME = {"conv": 23_511_040, "inproj": 14_188_544 + 0, "linear": 163_840, "lstm_step": 18_874_368,
+                         "bilstm_small": 32_768}
+METRIC = "converted mel-frames/sec"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--frames", type=int, default=128)
+    ap.add_argument("--lstm", default="auto", choices=["auto", "persistent", "per-step"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="utterances in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"], tflops_sustained=p["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5),
+                          ("sw_power_cap", 6)):
+            if any(s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.samples[0][1]), samples=len(sm),
+                    power_w_max=max(float(s[2]) for s in self.samples), reasons=reasons)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's arithmetic (torch CPU ATen through the oracle restatement) on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_baseline(state_dict, frames, batch, min_seconds=8.0, max_seconds=40.0):
+    import torch
+    from oracle.autovc import autovc_forward
+    from oracle.seeded import synthetic_mel, synthetic_speaker
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    x, c_org, c_trg = synthetic_mel(batch, frames, 1234), synthetic_speaker(batch, 1234, "org"), \
+        synthetic_speaker(batch, 1234, "trg")
+    run = lambda: autovc_forward(sd, x, c_org, c_trg, MODEL_ARGS[0], MODEL_ARGS[3])
+    run()                                           # warm-up (thread pool, oneDNN primitive cache)
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+        el = time.perf_counter() - t_start
+        if (el >= min_seconds and len(times) >= 3) or el >= max_seconds:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(value=batch * frames / med, unit=UNIT, cores=cores, kind="port",
+                sample=f"oracle AutoVC forward (torch {torch.__version__} CPU fp32, {cores} threads) on "
+                       f"{batch} utterances x {frames} frames, median of {len(times)} runs ({med * 1e3:.0f} ms each)")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is a
+    Python package that cannot travel to the GPU box; its arithmetic is torch CPU ATen, which the oracle calls)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import templates
+    from oracle.autovc import autovc_forward
+    from oracle.seeded import seeded_state_dict, synthetic_mel, synthetic_speaker
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = seeded_state_dict(templates.autovc_template(*MODEL_ARGS), 0)
+    B, T = args.cpu_batch, args.frames
+    x, c_org, c_trg = synthetic_mel(B, T, 1234), synthetic_speaker(B, 1234, "org"), synthetic_speaker(B, 1234, "trg")
+    step = lambda: autovc_forward(sd, x, c_org, c_trg, MODEL_ARGS[0], MODEL_ARGS[3])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = B * T * args.steps / dt
+    sample = (f"oracle AutoVC forward (torch {torch.__version__} CPU fp32, {cores} threads), each step a bounded "
+              f"sample of {B} utterances x {T} frames of the {args.batch} x {args.frames} workload")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"AutoVC(32,256,512,32) conversion forward, {args.batch} utterances x {args.frames} "
+                               f"frames x 80 mel per GPU (BASELINE.json configs[1])",
+                   "sample_batch": B, "frames": T},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from autoformer_b200 import _lib, ops
+    from autoformer_b200.factory.AutoVC import AutoVC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback on the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B, T = args.batch, args.frames
+    torch.manual_seed(1234)
+    model = AutoVC(*MODEL_ARGS)
+    with torch.no_grad():                      # non-trivial BatchNorm statistics so the folding is exercised
+        g = torch.Generator().manual_seed(7)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.5)
+                m.running_var.copy_(torch.rand(m.num_features, generator=g) * 1.5 + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+    state_dict = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(dev).eval()
+    model.precision = args.precision
+
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_h = (torch.rand(B, T, 80, generator=gen) * 6 - 5).pin_memory()
+    spk = lambda: torch.nn.functional.normalize(torch.randn(B, 256, generator=gen), dim=-1).pin_memory()
+    c_org_h, c_trg_h = spk(), spk()
+    x_d, c_org_d, c_trg_d = x_h.to(dev), c_org_h.to(dev), c_trg_h.to(dev)
+    out_h = [torch.empty(B, 1, T, 80).pin_memory(), torch.empty(B, 1, T, 80).pin_memory(),
+             torch.empty(B, 2 * MODEL_ARGS[0] * (T // MODEL_ARGS[3])).pin_memory()]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def device_step():
+        return model(x_d, c_org_d, c_trg_d)
+
+    def e2e_step():
+        xs = x_h.to(dev, non_blocking=True)
+        co = c_org_h.to(dev, non_blocking=True)
+        ct = c_trg_h.to(dev, non_blocking=True)
+        outs = model(xs, co, ct)
+        for h, o in zip(out_h, outs):
+            h.copy_(o, non_blocking=True)
+
+    def timed(step_fn, steps, sampler=None):
+        sync_all()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step_fn()
+        e1.record()
+        sync_all()
+        if sampler:
+            sampler.stop_flag.set()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # choose the LSTM launch mode: measure both once (outside the timed region) unless forced
+    def quick(mode):
+        model.persistent_lstm = mode == "persistent"
+        device_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        device_step()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    if args.lstm == "auto":
+        tp, ts = quick("persistent"), quick("per-step")
+        if world > 1:                                  # all ranks must agree
+            t = torch.tensor([tp, ts], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tp, ts = t.tolist()
+        lstm_mode = "persistent" if tp <= ts else "per-step"
+    else:
+        lstm_mode = args.lstm
+    model.persistent_lstm = lstm_mode == "persistent"
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, launches = timed(device_step, args.steps, sampler)
+    frames_per_step = B * T * world
+    value = frames_per_step * args.steps / (ms_total * 1e-3)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    e2e_value = frames_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = x_h.numel() * 4 + c_org_h.numel() * 4 + c_trg_h.numel() * 4
+    d2h = sum(h.numel() * 4 for h in out_h)
+
+    # per-kernel-family device times (CUDA events on the launching stream) for the roofline entry
+    prof_steps = min(args.steps, 3)
+    ops.PROFILER.reset()
+    ops.PROFILER.enabled = True
+    for _ in range(prof_steps):
+        device_step()
+    torch.cuda.synchronize()
+    ops.PROFILER.enabled = False
+    fam = ops.PROFILER.summary()
+    pk = peaks()
+    # one TF32 / bf16 / split-bf16 MMA pass structure: the tensor-pipe peak is the bf16 figure; a kernel timed
+    # inside a long step is compared with the sustained number
+    kernels = {}
+    for name, d in fam.items():
+        ms = d["ms"] / prof_steps
+        ent = dict(ms_per_step=ms, launches_per_step=d["launches"] // prof_steps)
+        if d["flops"] > 0:
+            ent["tflops"] = d["flops"] / prof_steps / (ms * 1e-3) / 1e12
+            ent["frac_of_bf16_sustained"] = ent["tflops"] / pk["tflops_sustained"]
+        if d["bytes"] > 0:
+            ent["gbs"] = d["bytes"] / prof_steps / (ms * 1e-3) / 1e9
+        kernels[name] = ent
+    tensor_fams = {k: v for k, v in kernels.items() if "tflops" in v and k != "bilstm_small"}
+    dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms_per_step"])
+    dom_e = tensor_fams[dom]
+    kernel_name = {"lstm_step": "lstm_step_kernel", "conv": "conv_gemm_kernel", "inproj": "conv_gemm_kernel",
+                   "linear": "conv_gemm_kernel"}[dom]
+    roofline = {
+        "kernel": f"{kernel_name} ({dom})", "bound": "tensor", "achieved": dom_e["tflops"],
+        "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": dom_e["tflops"] / pk["tflops_sustained"],
+        "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained",
+        "share_of_step": dom_e["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
+        "avg_launch_us": dom_e["ms_per_step"] * 1e3 / max(1, dom_e["launches_per_step"]),
+    }
+
+    # NCCL is used only to gather per-rank records (frames, time, output checksum) -- no data-path collective
+    rec = torch.tensor([float(B * T), ms_total, float(out_h[1].double().sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        allrec = [torch.zeros_like(rec) for _ in range(world)]
+        dist.all_gather(allrec, rec)
+        ranks = [r.tolist() for r in allrec]
+    else:
+        ranks = [rec.tolist()]
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(state_dict, T, args.cpu_batch)
+        act_gb = B * T * (336 + 512 * 10 + 4096 * 2 + 2048 + 1024 * 2 + 320 + 80 * 3) * 4 / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "bf16x3 (split-bf16 three-product MMA, fp32 accumulate; fp32-grade)",
+                      "tf32": "tf32 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "AutoVC(32,256,512,32) conversion forward (encoder+decoder+postnet), "
+                                   f"{B} utterances x {T} frames x 80 mel per GPU (BASELINE.json configs[1])",
+                       "batch_per_gpu": B, "frames": T, "precision": args.precision, "lstm_launch": lstm_mode,
+                       "parallelism": f"utterance-sharded x{world}, no data-path collective",
+                       "l2": f"no explicit flush: each step streams ~{act_gb:.1f} GB of activations/projections, "
+                             "far beyond the 126 MB L2"},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": sampler.summary() if sampler else None,
+            "frac_of_model_roofline": value / world / (pk["tflops_sustained"] * 1e12 / FLOP_PER_FRAME),
+            "kernels": kernels,
+            "ranks": [{"frames_per_step": r[0], "ms": r[1], "checksum": r[2]} for r in ranks],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

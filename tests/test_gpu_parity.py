@@ -1,0 +1,223 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (rel-L2 against the fp32/fp64 oracle):
+  precision "fp32" (split-bf16 three-product MMA)  <= 1e-3 headline, gated here at 2e-4 (measured ~3e-5)
+  precision "tf32" (one TF32 pass)                 <= 2e-3 (measured 0.9e-3 .. 1.0e-3: NOT the default for that reason)
+  precision "bf16"                                 <= 1e-2 on the converted mel (measured 4e-3 .. 8e-3)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import centred_rel_l2, rel_l2, templates
+from oracle.autovc import autovc_forward
+from oracle.layers import lstm_explicit, lstm_stack
+from oracle.seeded import seeded_state_dict, synthetic_mel, synthetic_speaker
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"fp32": 2e-4, "tf32": 2e-3, "bf16": 1.5e-2}
+STAGE_TOL = {"fp32": 3e-4, "tf32": 3e-3, "bf16": 2e-2}
+
+
+def _model(args, sd, precision="fp32", persistent=False):
+    from autoformer_b200.factory.AutoVC import AutoVC
+    m = AutoVC(*args)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    m.precision = precision
+    m.persistent_lstm = persistent
+    return m
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("B,T,c_in,c_out,k,act", [
+    (1, 128, 32, 64, 1, "none"),          # one k-block, one tile
+    (2, 128, 512, 512, 5, "relu"),        # AutoVC conv
+    (3, 64, 336, 512, 5, "relu"),         # ragged channels (336 = 10.5 k-blocks), two utterances per tile
+    (2, 176, 80, 512, 5, "tanh"),         # T = 176 (16-frame tiles), postnet entry
+    (5, 96, 512, 80, 5, "none"),          # N = 80 < tile
+    (130, 1, 256, 2048, 1, "none"),       # plain GEMM, rows = utterances, ragged last tile
+    (1, 1000, 80, 96, 7, "lrelu"),        # long utterance, k = 7
+])
+def test_conv_gemm_matches_conv1d(precision, B, T, c_in, c_out, k, act):
+    from autoformer_b200 import ops, packing
+    torch.manual_seed(B * 1000 + T + c_in)
+    w = torch.randn(c_out, c_in, k) / (c_in * k) ** 0.5
+    b = torch.randn(c_out)
+    x = torch.randn(B, T, c_in)
+    layer = ops.ConvGemm(*packing.pack_conv(w, b, precision), act=act).to("cuda")
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=k // 2).transpose(1, 2)
+    ref = {"none": lambda v: v, "relu": torch.relu, "tanh": torch.tanh,
+           "lrelu": lambda v: F.leaky_relu(v, 0.2)}[act](ref)
+    out = ops.alloc_act(B, T, c_out, precision, "cuda")
+    out2 = torch.full((B * T, c_out), float("nan"), device="cuda")
+    layer(packing.to_act(x, precision).cuda(), B, T, out=out, out2=out2)
+    torch.cuda.synchronize()
+    tol = {"fp32": 5e-5, "tf32": 2e-3, "bf16": 1e-2}[precision]
+    assert rel_l2(out2.view(B, T, c_out), ref) < tol
+    assert rel_l2(packing.act_to_float(out, precision), ref) < tol * (1 if precision == "fp32" else 2)
+
+
+def test_conv_gemm_residual_and_reflect_halo():
+    from autoformer_b200 import ops, packing
+    torch.manual_seed(5)
+    B, T, c, P = 2, 40, 64, 3
+    w, b = torch.randn(c, c, 3) / 14, torch.randn(c)
+    x, res = torch.randn(B, T, c), torch.randn(B * T, c)
+    layer = ops.ConvGemm(*packing.pack_conv(w, b, "fp32"), act="lrelu").to("cuda")
+    out = torch.zeros(B, T + 2 * P, 2 * c, dtype=torch.bfloat16, device="cuda")
+    out2 = torch.empty(B * T, c, device="cuda")
+    layer(packing.to_act(x, "fp32").cuda(), B, T, out=out, out_row0=P, reflect=P, out2=out2, residual=res.cuda())
+    torch.cuda.synchronize()
+    ref = F.leaky_relu(F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=1), 0.2) \
+        + res.double().view(B, T, c).transpose(1, 2)
+    assert rel_l2(out2.view(B, T, c), ref.transpose(1, 2)) < 5e-5
+    padded = F.pad(ref, (P, P), mode="reflect").transpose(1, 2)          # ReflectionPad1d semantics
+    assert rel_l2(packing.act_to_float(out, "fp32"), padded) < 5e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("B,T,I,H,persistent", [(4, 8, 64, 128, False), (130, 16, 320, 512, False),
+                                                (64, 24, 512, 1024, False), (3, 12, 80, 768, False),
+                                                (130, 16, 320, 512, True), (256, 20, 512, 1024, True)])
+def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent):
+    from autoformer_b200 import layers, packing
+    torch.manual_seed(H + T)
+    k = 1.0 / H ** 0.5
+    w_ih, w_hh = (torch.rand(4 * H, I) * 2 - 1) * k * 3, (torch.rand(4 * H, H) * 2 - 1) * k * 3
+    b_ih, b_hh = (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
+    x = torch.randn(B, T, I)
+    ref = lstm_explicit(x.double(), w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
+    layer = layers.LstmLayer(w_ih.cuda(), w_hh.cuda(), b_ih.cuda(), b_hh.cuda(), precision)
+    f32 = torch.full((B, T, H), float("nan"), device="cuda")
+    last = torch.full((B, H), float("nan"), device="cuda")
+    hseq = layer(packing.to_act(x, precision).cuda(), B, T, hseq_f32=f32, h_last=last, persistent=persistent)
+    torch.cuda.synchronize()
+    tol = {"fp32": 5e-5, "tf32": 2e-3, "bf16": 1.5e-2}[precision]
+    assert rel_l2(f32, ref) < tol
+    assert rel_l2(last, ref[:, -1]) < tol
+    assert rel_l2(packing.act_to_float(hseq, precision), ref) < 2 * tol
+
+
+@pytest.mark.parametrize("H,freq,B,T", [(32, 32, 5, 64), (44, 22, 3, 88), (32, 32, 1, 32)])
+def test_bilstm_small_and_code_downsampling(H, freq, B, T):
+    from autoformer_b200 import layers, packing
+    tmpl = {}
+    templates._lstm(tmpl, "lstm", 512, H, 2, bidirectional=True)
+    sd = seeded_state_dict(tmpl, 3)
+    torch.manual_seed(1)
+    x = torch.randn(B, T, 512)
+    ref = lstm_stack({k: v.double() for k, v in sd.items()}, "lstm", x.double(), 2, bidirectional=True, impl="explicit")
+    ref_codes = torch.cat((ref[:, freq - 1::freq, :H], ref[:, ::freq, H:]), dim=-1)     # AutoVC.py:56-66
+    m = layers.BiLstmSmall({k: v.cuda() for k, v in sd.items()}, "lstm", 2, "fp32")
+    out, codes = m(packing.to_act(x, "fp32").cuda(), B, T, freq=freq, want_out=True)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 5e-5 and rel_l2(codes, ref_codes) < 5e-5
+
+
+def test_concat_bcast_upsamples_codes():
+    from autoformer_b200 import ops, packing
+    torch.manual_seed(2)
+    B, T, F_, C1, C2 = 3, 64, 16, 64, 256
+    codes, spk = torch.randn(B, T // F_, C1), torch.randn(B, C2)
+    ref = torch.cat((codes.repeat_interleave(F_, dim=1), spk.unsqueeze(1).expand(-1, T, -1)), dim=-1)   # AutoVC.py:197-204
+    for prec, tol in (("fp32", 2e-5), ("tf32", 5e-4), ("bf16", 5e-3)):
+        out = ops.concat_bcast(codes.cuda(), spk.cuda(), T, F_, prec)
+        assert rel_l2(packing.act_to_float(out, prec), ref) < tol
+
+
+# ------------------------------------------------------------------------------------------------ AutoVC end to end
+@pytest.mark.parametrize("args,B,T,wseed,xseed", [((32, 256, 512, 32), 2, 128, 0, 1234), ((32, 256, 512, 32), 3, 64, 1, 77),
+                                                  ((44, 256, 512, 22), 2, 176, 2, 99)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_autovc_stagewise_parity(args, B, T, wseed, xseed, precision):
+    sd = seeded_state_dict(templates.autovc_template(*args), wseed)
+    x, c_org, c_trg = synthetic_mel(B, T, xseed), synthetic_speaker(B, xseed, "org"), synthetic_speaker(B, xseed, "trg")
+    rt = {}
+    ref = autovc_forward(sd, x, c_org, c_trg, args[0], args[3], taps=rt)
+    m = _model(args, sd, precision)
+    m.collect_taps = True
+    mel, post, codes = m(x.cuda(), c_org.cuda(), c_trg.cuda())
+    torch.cuda.synchronize()
+    assert mel.shape == ref[0].shape and post.shape == ref[1].shape and codes.shape == ref[2].shape
+    assert rel_l2(mel, ref[0]) < TOL[precision]
+    assert rel_l2(post, ref[1]) < TOL[precision]
+    assert rel_l2(codes, ref[2]) < TOL[precision]
+    for k, v in rt.items():
+        assert rel_l2(m.taps[k], v) < STAGE_TOL[precision], k
+    if precision == "fp32":
+        assert centred_rel_l2(post.squeeze(1), ref[1].squeeze(1)) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["autovc_A_b2_t128", "autovc_A_b3_t64", "autovc_R_b2_t176"])
+def test_autovc_matches_reference_golden(name):
+    """Against outputs of the UNMODIFIED reference (tests/golden, made by oracle/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    args = tuple(int(a) for a in g["args"])
+    B, T, xs = int(g["B"]), int(g["T"]), int(g["xseed"])
+    sd = seeded_state_dict(templates.autovc_template(*args), int(g["wseed"]))
+    m = _model(args, sd)
+    x, c_org, c_trg = synthetic_mel(B, T, xs).cuda(), synthetic_speaker(B, xs, "org").cuda(), synthetic_speaker(B, xs, "trg").cuda()
+    mel, post, codes = m(x, c_org, c_trg)
+    assert rel_l2(mel, torch.from_numpy(g["mel"])) < 1e-3
+    assert rel_l2(post, torch.from_numpy(g["mel_postnet"])) < 1e-3
+    assert rel_l2(codes, torch.from_numpy(g["codes"])) < 1e-3
+    # 4-D input with c_trg=None returns only the codes (train.py:90-92)
+    codes2 = m(torch.from_numpy(g["mel"]).cuda(), c_org, None)
+    assert codes2.shape == g["codes_of_mel"].shape
+    assert rel_l2(codes2, torch.from_numpy(g["codes_of_mel"])) < 1e-3
+
+
+def test_negative_control_and_errors():
+    args = (32, 256, 512, 32)
+    sd = seeded_state_dict(templates.autovc_template(*args), 0)
+    m = _model(args, sd)
+    c_org, c_trg = synthetic_speaker(2, 1234, "org"), synthetic_speaker(2, 1234, "trg")
+    ref = autovc_forward(sd, synthetic_mel(2, 128, 1234), c_org, c_trg, 32, 32)
+    wrong = m(synthetic_mel(2, 128, 999).cuda(), c_org.cuda(), c_trg.cuda())
+    assert rel_l2(wrong[1], ref[1]) > 1e-2                     # a path that ignores its input must fail the gate
+    with pytest.raises(IndexError):
+        m(synthetic_mel(1, 100, 1).cuda(), c_org[:1].cuda(), c_trg[:1].cuda())      # T % freq != 0 (AutoVC.py:60-66)
+    with pytest.raises(RuntimeError):
+        m(synthetic_mel(1, 128, 1), c_org[:1], c_trg[:1])                            # CPU tensors: no fallback
+
+
+def test_persistent_lstm_matches_per_step_and_batch_independence():
+    """Size-independent properties at a larger batch: the persistent (grid-barrier) LSTM must reproduce the
+    per-step launches bit for bit, and utterances are independent (eval-mode BN), so a slice of a big batch
+    equals the same utterances converted alone."""
+    args = (32, 256, 512, 32)
+    sd = seeded_state_dict(templates.autovc_template(*args), 4)
+    B, T = 160, 128
+    x, c_org, c_trg = synthetic_mel(B, T, 5).cuda(), synthetic_speaker(B, 5, "org").cuda(), synthetic_speaker(B, 5, "trg").cuda()
+    m = _model(args, sd)
+    a = m(x, c_org, c_trg)
+    m.persistent_lstm = True
+    b = m(x, c_org, c_trg)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    small = m(x[:3], c_org[:3], c_trg[:3])
+    for u, v in zip(small, a):
+        assert rel_l2(u, v[:3]) < 1e-5
+    ref = autovc_forward(sd, x[:4].cpu(), c_org[:4].cpu(), c_trg[:4].cpu(), 32, 32)
+    assert rel_l2(a[1][:4], ref[1]) < 2e-4
+
+
+def test_state_dict_roundtrip_and_repack_on_reload():
+    args = (32, 256, 512, 32)
+    sd0 = seeded_state_dict(templates.autovc_template(*args), 8)
+    sd1 = seeded_state_dict(templates.autovc_template(*args), 9)
+    m = _model(args, sd0)
+    assert set(m.state_dict().keys()) == set(sd0.keys())
+    x, c_org, c_trg = synthetic_mel(1, 64, 3).cuda(), synthetic_speaker(1, 3, "org").cuda(), synthetic_speaker(1, 3, "trg").cuda()
+    y0 = m(x, c_org, c_trg)[1]
+    m.load_state_dict(sd1)                                     # must invalidate the packed weights
+    y1 = m(x, c_org, c_trg)[1]
+    ref1 = autovc_forward(sd1, x.cpu(), c_org.cpu(), c_trg.cpu(), 32, 32)[1]
+    assert rel_l2(y1, ref1) < 2e-4 and rel_l2(y0, ref1) > 1e-2
