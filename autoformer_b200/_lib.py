@@ -11,19 +11,23 @@ ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
 ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU}
 
 EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm", "avc_lstm_seq",
-           "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm"]
+           "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_transpose_pad",
+           "avc_conv_to_mono_tanh"]
+
+
+MAX_SOURCES = 4
 
 
 class GemmDesc(ctypes.Structure):
     """struct avc_gemm_desc"""
     _fields_ = [
-        ("a_ptr", ctypes.c_void_p * 2),
-        ("a_channels", ctypes.c_int * 2),
-        ("a_ld", ctypes.c_longlong * 2),
-        ("a_rows_per_utt", ctypes.c_int * 2),
-        ("a_taps", ctypes.c_int * 2),
-        ("a_tap_t0", ctypes.c_int * 2),
-        ("a_tap_dt", ctypes.c_int * 2),
+        ("a_ptr", ctypes.c_void_p * MAX_SOURCES),
+        ("a_channels", ctypes.c_int * MAX_SOURCES),
+        ("a_ld", ctypes.c_longlong * MAX_SOURCES),
+        ("a_rows_per_utt", ctypes.c_int * MAX_SOURCES),
+        ("a_taps", ctypes.c_int * MAX_SOURCES),
+        ("a_tap_t0", ctypes.c_int * MAX_SOURCES),
+        ("a_tap_dt", ctypes.c_int * MAX_SOURCES),
         ("w_ptr", ctypes.c_void_p),
         ("n_pad", ctypes.c_int),
         ("k_pad", ctypes.c_int),
@@ -33,6 +37,7 @@ class GemmDesc(ctypes.Structure):
         ("N", ctypes.c_int),
         ("bias", ctypes.c_void_p),
         ("act", ctypes.c_int),
+        ("out_phases", ctypes.c_int),
         ("out", ctypes.c_void_p),
         ("out_ld", ctypes.c_longlong),
         ("out_rows_per_utt", ctypes.c_int),
@@ -40,6 +45,8 @@ class GemmDesc(ctypes.Structure):
         ("out_dtype", ctypes.c_int),
         ("out_round_tf32", ctypes.c_int),
         ("out_reflect", ctypes.c_int),
+        ("out_raw", ctypes.c_void_p),
+        ("out_raw_ld", ctypes.c_longlong),
         ("out2", ctypes.c_void_p),
         ("out2_ld", ctypes.c_longlong),
         ("residual", ctypes.c_void_p),
@@ -98,6 +105,12 @@ def load():
     lib.avc_linear_l2norm.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.avc_linear_l2norm.restype = ctypes.c_int
+    lib.avc_transpose_pad.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.avc_transpose_pad.restype = ctypes.c_int
+    lib.avc_conv_to_mono_tanh.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.avc_conv_to_mono_tanh.restype = ctypes.c_int
     _lib = lib
     return lib
 

@@ -1,10 +1,10 @@
 // Implicit-GEMM convolution / dense GEMM on tcgen05 (see include/avc_b200.h: avc_conv_gemm).
 //
-// Tile = 128 output rows x BN output channels.  The 128 rows are `bb` utterances x `tb` consecutive
-// frames (tb * bb = 128, tb = largest power of two <= 128 dividing T), so one 3-D TMA box
-// {128 bytes of channels, tb frames, bb utterances} fetches the A tile of one (tap, channel chunk) k-block,
-// shifted in time by the tap offset; frames outside the utterance are zero-filled by TMA, which IS the
-// convolution's zero padding -- tiles never bleed across utterances.
+// Tile = 128 GEMM rows x BN output columns.  The 128 rows are `bb` utterances x `tb` consecutive frames
+// (tb * bb = 128, the power-of-two split that wastes the fewest rows), so one 3-D TMA box
+// {128 bytes of channels, tb frames, bb utterances} fetches the A tile of one (source, tap, channel chunk)
+// k-block, shifted in time by the tap offset; frames outside the utterance are zero-filled by TMA, which IS
+// the convolution's zero padding -- tiles never bleed across utterances.
 #include <cuda_bf16.h>
 
 #include "../../include/avc_b200.h"
@@ -13,15 +13,17 @@
 
 namespace avc {
 
+constexpr int kMaxSrc = AVC_MAX_SOURCES;
+
 struct alignas(64) GemmParams {
-  CUtensorMap tmap_a[2];
+  CUtensorMap tmap_a[kMaxSrc];
   CUtensorMap tmap_b;
-  // k-block schedule: source s contributes taps[s] * chunks[s] k-blocks, tap-major
-  int kb_src0;           // k-blocks of source 0
-  int num_kb;            // total k-blocks
-  int chunks[2];         // channel chunks per tap
-  int tap_t0[2];
-  int tap_dt[2];
+  // k-block schedule: source s owns k-blocks [kb_end[s-1], kb_end[s]), tap-major, `chunks` channel chunks per tap
+  int kb_end[kMaxSrc];
+  int chunks[kMaxSrc];
+  int tap_t0[kMaxSrc];
+  int tap_dt[kMaxSrc];
+  int num_kb;
   int kc_elems;          // channels per k-block (32 tf32 / 64 bf16)
   // tiling
   int B, T, N;
@@ -30,9 +32,12 @@ struct alignas(64) GemmParams {
   // epilogue
   const float* bias;
   int act;
+  int phases, cs;        // N = phases * cs; output time = phases * t + n / cs
   void* out;
   long long out_ld;
   int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16
+  void* out_raw;
+  long long out_raw_ld;
   float* out2;
   long long out2_ld;
   const float* residual;
@@ -48,21 +53,23 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-__device__ __forceinline__ void store4(const GemmParams& p, long long row, int n, const float (&v)[4]) {
-  if (p.out_mode == 2) {
+// Store four consecutive channels [c, c+4) of one output row in the operand format `mode`.
+__device__ __forceinline__ void store4(void* base, int mode, int round, long long row, long long ld, int c, int cs,
+                                       const float (&v)[4]) {
+  if (mode == 2) {
     float lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) lo[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
-    __nv_bfloat16* base = static_cast<__nv_bfloat16*>(p.out) + row * p.out_ld + n;
-    *reinterpret_cast<uint2*>(base) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-    *reinterpret_cast<uint2*>(base + p.N) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
-  } else if (p.out_mode == 1) {
+    __nv_bfloat16* ptr = static_cast<__nv_bfloat16*>(base) + row * ld + c;
+    *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    *reinterpret_cast<uint2*>(ptr + cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+  } else if (mode == 1) {
     uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
-    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + row * p.out_ld + n) = pk;
+    *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + row * ld + c) = pk;
   } else {
-    float4 o = p.out_round ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
-                           : make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.out_ld + n) = o;
+    float4 o = round ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
+                     : make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(static_cast<float*>(base) + row * ld + c) = o;
   }
 }
 
@@ -86,9 +93,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int n0 = n_tile * BN;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.tmap_a[0]);
     prefetch_tmap(&p.tmap_b);
-    if (p.num_kb > p.kb_src0) prefetch_tmap(&p.tmap_a[1]);
+#pragma unroll
+    for (int i = 0; i < kMaxSrc; ++i)
+      if (i == 0 || p.kb_end[i] > p.kb_end[i - 1]) prefetch_tmap(&p.tmap_a[i]);
   }
   const uint32_t tmem_base = pipe_setup<BN>(s);
 
@@ -96,9 +104,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     if (lane == 0) {
       // ---------------- TMA producer
       RingState rs;
+      int src = 0, base = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int src = kb >= p.kb_src0 ? 1 : 0;
-        const int local = src ? kb - p.kb_src0 : kb;
+        while (kb >= p.kb_end[src]) {
+          base = p.kb_end[src];
+          ++src;
+        }
+        const int local = kb - base;
         const int tap = local / p.chunks[src];
         const int chunk = local - tap * p.chunks[src];
         mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
@@ -132,45 +144,52 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     const int b = b0 + bi;
     const int t = t0 + ti;
     const bool valid = (b < p.B) && (t < p.T);
-    const long long orow = (long long)b * p.out_rows_per_utt + p.out_row0 + t;
-    const long long lrow = (long long)b * p.T + t;
-    // reflected halo rows this thread also writes (ReflectionPad1d of the consumer)
-    long long rrow_l = -1, rrow_r = -1;
-    if (p.out_reflect > 0) {
-      if (t >= 1 && t <= p.out_reflect) rrow_l = orow - 2LL * t;
-      if (t <= p.T - 2 && t >= p.T - 1 - p.out_reflect) rrow_r = orow + 2LL * (p.T - 1 - t);
-    }
+    const int t_out = p.T * p.phases;                       // output frames per utterance
+    const long long obase = (long long)b * p.out_rows_per_utt + p.out_row0;
+    const long long lbase = (long long)b * t_out;
     mbar_wait(s.tmem_full, 0);
     tc_fence_after();
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c32 = 0; c32 < BN / 32; ++c32) {
       uint32_t v[32];
-      tmem_ld_32x32(lane_addr + c * 32, v);
+      tmem_ld_32x32(lane_addr + c32 * 32, v);
       tmem_ld_wait();
-      const int nc = n0 + c * 32;
+      const int nc = n0 + c32 * 32;
       if (valid && nc < p.N) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int n = nc + 4 * j;
           if (n < p.N) {
+            const int phase = p.phases == 1 ? 0 : n / p.cs;
+            const int c = n - phase * p.cs;
+            const int time = t * p.phases + phase;
+            const long long lrow = lbase + time;
             const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             float o[4];
-            o[0] = apply_act(__uint_as_float(v[4 * j + 0]) + bv.x, p.act);
-            o[1] = apply_act(__uint_as_float(v[4 * j + 1]) + bv.y, p.act);
-            o[2] = apply_act(__uint_as_float(v[4 * j + 2]) + bv.z, p.act);
-            o[3] = apply_act(__uint_as_float(v[4 * j + 3]) + bv.w, p.act);
+            o[0] = __uint_as_float(v[4 * j + 0]) + bv.x;
+            o[1] = __uint_as_float(v[4 * j + 1]) + bv.y;
+            o[2] = __uint_as_float(v[4 * j + 2]) + bv.z;
+            o[3] = __uint_as_float(v[4 * j + 3]) + bv.w;
             if (p.residual) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + lrow * p.res_ld + n));
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + lrow * p.res_ld + c));
               o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
             }
+            if (p.out_raw) store4(p.out_raw, p.out_mode, p.out_round, lrow, p.out_raw_ld, c, p.cs, o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = apply_act(o[i], p.act);
             if (p.out) {
-              store4(p, orow, n, o);
-              if (rrow_l >= 0) store4(p, rrow_l, n, o);
-              if (rrow_r >= 0) store4(p, rrow_r, n, o);
+              const long long orow = obase + time;
+              store4(p.out, p.out_mode, p.out_round, orow, p.out_ld, c, p.cs, o);
+              if (p.out_reflect > 0) {   // reflected halo rows (ReflectionPad1d of the consumer)
+                if (time >= 1 && time <= p.out_reflect)
+                  store4(p.out, p.out_mode, p.out_round, orow - 2LL * time, p.out_ld, c, p.cs, o);
+                if (time <= t_out - 2 && time >= t_out - 1 - p.out_reflect)
+                  store4(p.out, p.out_mode, p.out_round, orow + 2LL * (t_out - 1 - time), p.out_ld, c, p.cs, o);
+              }
             }
             if (p.out2)
-              *reinterpret_cast<float4*>(p.out2 + lrow * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(p.out2 + lrow * p.out2_ld + c) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -203,7 +222,7 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   AVC_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->N % 4 == 0, "avc_conv_gemm: bad shape B=%d T=%d N=%d", d->B,
               d->T, d->N);
   AVC_REQUIRE(d->a_taps[0] > 0 && d->a_ptr[0] && d->w_ptr && d->bias, "avc_conv_gemm: missing operand");
-  AVC_REQUIRE(d->out || d->out2, "avc_conv_gemm: no output");
+  AVC_REQUIRE(d->out || d->out2 || d->out_raw, "avc_conv_gemm: no output");
   const int es = d->dtype == AVC_DTYPE_BF16 ? 2 : 4;
   const int kc = kRowBytes / es;
 
@@ -238,18 +257,21 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   p.kc_elems = kc;
 
   int kb_total = 0;
-  for (int s = 0; s < 2; ++s) {
+  bool ended = false;
+  for (int s = 0; s < kMaxSrc; ++s) {
     if (d->a_taps[s] <= 0) {
-      AVC_REQUIRE(s == 1, "avc_conv_gemm: source 0 unused");
+      ended = true;
+      p.kb_end[s] = kb_total;
+      p.chunks[s] = 1;
       continue;
     }
+    AVC_REQUIRE(!ended, "avc_conv_gemm: sources must be used in order (source %d after an unused one)", s);
     AVC_REQUIRE(d->a_ptr[s] != nullptr, "avc_conv_gemm: source %d null", s);
     p.chunks[s] = (d->a_channels[s] + kc - 1) / kc;
     p.tap_t0[s] = d->a_tap_t0[s];
     p.tap_dt[s] = d->a_tap_dt[s];
-    const int kbs = d->a_taps[s] * p.chunks[s];
-    if (s == 0) p.kb_src0 = kbs;
-    kb_total += kbs;
+    kb_total += d->a_taps[s] * p.chunks[s];
+    p.kb_end[s] = kb_total;
     if (!encode_tmap_3d(&p.tmap_a[s], es, d->a_ptr[s], (uint64_t)d->a_channels[s], (uint64_t)d->a_rows_per_utt[s],
                         (uint64_t)d->B, (uint64_t)d->a_ld[s] * es,
                         (uint64_t)d->a_rows_per_utt[s] * (uint64_t)d->a_ld[s] * es, kc, tb, p.bb))
@@ -262,27 +284,36 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
 
   p.bias = d->bias;
   p.act = d->act;
+  p.phases = d->out_phases > 0 ? d->out_phases : 1;
+  AVC_REQUIRE(d->N % p.phases == 0 && (d->N / p.phases) % 4 == 0, "avc_conv_gemm: N=%d not divisible into %d phases",
+              d->N, p.phases);
+  p.cs = d->N / p.phases;
+  const long long t_out = (long long)d->T * p.phases;
   p.out = d->out;
   p.out_ld = d->out_ld;
   p.out_rows_per_utt = d->out_rows_per_utt;
   p.out_row0 = d->out_row0;
   p.out_mode = d->out_dtype;
   AVC_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 2, "avc_conv_gemm: out_dtype %d", d->out_dtype);
-  if (d->out && d->out_dtype == 2) AVC_REQUIRE(d->out_ld >= 2LL * d->N, "avc_conv_gemm: split output needs out_ld >= 2N");
+  const long long min_ld = d->out_dtype == 2 ? 2LL * p.cs : p.cs;
   p.out_round = d->out_round_tf32;
   p.out_reflect = d->out_reflect;
+  p.out_raw = d->out_raw;
+  p.out_raw_ld = d->out_raw_ld;
   p.out2 = d->out2;
   p.out2_ld = d->out2_ld;
   p.residual = d->residual;
   p.res_ld = d->res_ld;
   if (d->out) {
-    AVC_REQUIRE(d->out_ld % 4 == 0 && d->out_rows_per_utt >= d->out_row0 + d->T + d->out_reflect &&
-                    d->out_row0 >= d->out_reflect,
+    AVC_REQUIRE(d->out_ld % 4 == 0 && d->out_ld >= min_ld &&
+                    d->out_rows_per_utt >= d->out_row0 + t_out + d->out_reflect && d->out_row0 >= d->out_reflect,
                 "avc_conv_gemm: bad output geometry");
-    AVC_REQUIRE(d->out_reflect < d->T, "avc_conv_gemm: reflect %d needs T > reflect", d->out_reflect);
+    AVC_REQUIRE(d->out_reflect < t_out, "avc_conv_gemm: reflect %d needs more than that many output frames",
+                d->out_reflect);
   }
-  if (d->out2) AVC_REQUIRE(d->out2_ld % 4 == 0, "avc_conv_gemm: out2_ld");
-  if (d->residual) AVC_REQUIRE(d->res_ld % 4 == 0, "avc_conv_gemm: res_ld");
+  if (d->out_raw) AVC_REQUIRE(d->out_raw_ld % 4 == 0 && d->out_raw_ld >= min_ld, "avc_conv_gemm: out_raw_ld");
+  if (d->out2) AVC_REQUIRE(d->out2_ld % 4 == 0 && d->out2_ld >= p.cs, "avc_conv_gemm: out2_ld");
+  if (d->residual) AVC_REQUIRE(d->res_ld % 4 == 0 && d->res_ld >= p.cs, "avc_conv_gemm: res_ld");
 
   const long long grid = (long long)p.tiles_t * tiles_b * p.n_tiles;
   AVC_REQUIRE(grid > 0 && grid < (1LL << 31), "avc_conv_gemm: grid %lld", grid);

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) concat_bcast_kernel(const float* __restri
     const long long b = r / T;
     const int t = static_cast<int>(r - b * T);
     float4 v;
-    if (c < C1)
+    if (c < C1)   // C2 == 0: pure conversion of seq
       v = __ldg(reinterpret_cast<const float4*>(seq + (b * Tin + t / div) * C1 + c));
     else
       v = __ldg(reinterpret_cast<const float4*>(vec + b * C2 + (c - C1)));
@@ -197,14 +197,93 @@ __global__ void __launch_bounds__(256) linear_l2norm_kernel(const float* __restr
   for (int n = threadIdx.x; n < N; n += blockDim.x, ++cnt) out[(long long)b * N + n] = e_val[cnt] * inv;
 }
 
+// ---------------------------------------------------------------------------------------------
+// (B, C, L) fp32 channels-first -> channels-last operand format with reflected halo rows
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store1(void* out, int mode, int round, long long row, int ld, int c, int C, float v) {
+  if (mode == 2) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16* p = static_cast<__nv_bfloat16*>(out) + row * ld + c;
+    p[0] = hi;
+    p[C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  } else if (mode == 1) {
+    static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
+  } else {
+    static_cast<float*>(out)[row * ld + c] = round ? round_tf32(v) : v;
+  }
+}
+
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ in, void* __restrict__ out, int C,
+                                                            int L, int pad, int mode, int round) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {          // coalesced along L
+    const int c = c0 + i, l = l0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && l < L) ? __ldg(in + ((long long)b * C + c) * L + l) : 0.0f;
+  }
+  __syncthreads();
+  const int ld = mode == 2 ? 2 * C : C;
+  const long long base = (long long)b * (L + 2 * pad) + pad;
+  for (int i = threadIdx.y; i < 32; i += 8) {          // coalesced along C
+    const int l = l0 + i, c = c0 + threadIdx.x;
+    if (l < L && c < C) {
+      const float v = tile[threadIdx.x][i];
+      store1(out, mode, round, base + l, ld, c, C, v);
+      if (l >= 1 && l <= pad) store1(out, mode, round, base - l, ld, c, C, v);
+      if (l <= L - 2 && l >= L - 1 - pad) store1(out, mode, round, base + 2LL * (L - 1) - l, ld, c, C, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MelGAN output layer: reflect-pad + K-tap conv to one channel + tanh.  One thread per output sample; the
+// (256 + K - 1) x C input window of a CTA is staged in shared memory (row stride C+1: conflict free).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMonoTile = 256;
+__global__ void __launch_bounds__(kMonoTile) conv_to_mono_tanh_kernel(const float* __restrict__ x,
+                                                                      const float* __restrict__ w, float bias,
+                                                                      float* __restrict__ out, int L, int C, int K) {
+  extern __shared__ float sm[];
+  const int half = K / 2;
+  const int rows = kMonoTile + K - 1;
+  float* xs = sm;                       // [rows][C + 1]
+  float* ws = sm + rows * (C + 1);      // [K][C]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kMonoTile;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) ws[i] = w[i];
+  const int c4 = C / 4;
+  for (int i = threadIdx.x; i < rows * c4; i += blockDim.x) {
+    const int r = i / c4, c = (i - r * c4) * 4;
+    int src = t0 + r - half;
+    if (src < 0) src = -src;                         // ReflectionPad1d: edge sample not repeated
+    if (src >= L) src = 2 * (L - 1) - src;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src >= 0 && src < L) v = __ldg(reinterpret_cast<const float4*>(x + ((long long)b * L + src) * C + c));
+    float* d = xs + r * (C + 1) + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = bias;
+  for (int k = 0; k < K; ++k) {
+    const float* xr = xs + (threadIdx.x + k) * (C + 1);
+    const float* wr = ws + k * C;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) acc = fmaf(xr[c], wr[c], acc);
+  }
+  out[(long long)b * L + t] = tanh_fast(acc);
+}
+
 }  // namespace avc
 
 extern "C" int avc_concat_bcast(const float* seq, const float* vec, void* out, int B, int T, int C1, int C2, int div,
                                 int out_dtype, int out_round_tf32, void* stream_v) {
   using namespace avc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  AVC_REQUIRE(seq && vec && out, "avc_concat_bcast: null buffer");
-  AVC_REQUIRE(B > 0 && T > 0 && C1 > 0 && C2 > 0 && C1 % 4 == 0 && C2 % 4 == 0 && div > 0 && T % div == 0,
+  AVC_REQUIRE(seq && out && (vec || C2 == 0), "avc_concat_bcast: null buffer");
+  AVC_REQUIRE(B > 0 && T > 0 && C1 > 0 && C2 >= 0 && C1 % 4 == 0 && C2 % 4 == 0 && div > 0 && T % div == 0,
               "avc_concat_bcast: bad shape B=%d T=%d C1=%d C2=%d div=%d", B, T, C1, C2, div);
   const long long rows = (long long)B * T;
   const long long total = rows * ((C1 + C2) / 4);
@@ -255,6 +334,37 @@ extern "C" int avc_linear_l2norm(const float* h, const float* w, const float* bi
   AVC_REQUIRE(h && w && bias && out, "avc_linear_l2norm: null buffer");
   AVC_REQUIRE(B > 0 && K > 0 && K % 4 == 0 && N > 0 && N <= 1024, "avc_linear_l2norm: bad shape B=%d K=%d N=%d", B, K, N);
   linear_l2norm_kernel<<<B, 256, (K + 8) * sizeof(float), stream>>>(h, w, bias, out, K, N);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_transpose_pad(const float* in, void* out, int B, int C, int L, int pad, int out_dtype,
+                                 int out_round_tf32, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(in && out, "avc_transpose_pad: null buffer");
+  AVC_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && L > pad && pad >= 0 && B < 65536, "avc_transpose_pad: bad shape B=%d C=%d L=%d pad=%d",
+              B, C, L, pad);
+  AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "avc_transpose_pad: out_dtype %d", out_dtype);
+  dim3 grid((L + 31) / 32, (C + 31) / 32, B);
+  transpose_pad_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, C, L, pad, out_dtype, out_round_tf32);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_conv_to_mono_tanh(const float* x, const float* w, float bias, float* out, int B, int L, int C, int K,
+                                     void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(x && w && out, "avc_conv_to_mono_tanh: null buffer");
+  AVC_REQUIRE(B > 0 && B < 65536 && L > K / 2 && C > 0 && C <= 64 && C % 4 == 0 && K % 2 == 1 && K <= 15,
+              "avc_conv_to_mono_tanh: bad shape B=%d L=%d C=%d K=%d", B, L, C, K);
+  const size_t smem = ((size_t)(kMonoTile + K - 1) * (C + 1) + (size_t)K * C) * sizeof(float);
+  AVC_CHECK_CUDA(cudaFuncSetAttribute(conv_to_mono_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((L + kMonoTile - 1) / kMonoTile, B);
+  conv_to_mono_tanh_kernel<<<grid, kMonoTile, smem, stream>>>(x, w, bias, out, L, C, K);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

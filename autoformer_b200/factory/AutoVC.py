@@ -98,8 +98,7 @@ class AutoVC(nn.Module):
             self._warned_train = True
         if x.dim() == 4:
             x = x.squeeze(1)                                    # AutoVC.py:46
-        if not x.is_cuda:
-            raise RuntimeError("autoformer_b200.AutoVC needs CUDA tensors (there is no CPU fallback)")
+        ops._require_cuda(x)
         x = x.contiguous().float()
         c_org = c_org.contiguous().float()
         B, T, n_mel = x.shape

@@ -1,0 +1,42 @@
+"""Drop-in ``factory.LstmDV.LstmDV`` (the d-vector speaker embedder) on libavc_b200.so.
+
+Same constructor defaults, ``forward(x)`` contract and state_dict keys as the reference
+(factory/LstmDV.py:4-24): 3 x LSTM(80 -> 768), last time step, Linear(768 -> 256), L2 normalisation.
+Each LSTM layer is one dense input-projection GEMM plus the tensor-core recurrence; only h_T of the top
+layer leaves the recurrence kernel (``h_last``), and the Linear + normalisation is one fused kernel.
+"""
+import torch
+import torch.nn as nn
+
+from .. import layers, ops
+
+
+class LstmDV(nn.Module):
+    def __init__(self, num_layers=3, dim_input=80, dim_cell=768, dim_emb=256):
+        super().__init__()
+        self.lstm = nn.LSTM(input_size=dim_input, hidden_size=dim_cell, num_layers=num_layers, batch_first=True)
+        self.embedding = nn.Linear(dim_cell, dim_emb)
+        self.num_layers, self.dim_cell = num_layers, dim_cell
+        self.precision = "fp32"
+        self.persistent_lstm = False
+        self._cache = layers.PlanCache()
+
+    def _plan(self):
+        def build():
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            return dict(lstm=layers.lstm_layers(sd, "lstm", self.num_layers, self.precision),
+                        w=sd["embedding.weight"].float().contiguous(), b=sd["embedding.bias"].float().contiguous())
+        return self._cache.get(self, (self.precision,), build)
+
+    @torch.no_grad()
+    def forward(self, x):
+        ops._require_cuda(x)
+        plan = self._plan()
+        x = x.contiguous().float()
+        B, T, _ = x.shape
+        h = ops.to_act(x, self.precision)
+        h_last = torch.empty(B, self.dim_cell, dtype=torch.float32, device=x.device)
+        for i, layer in enumerate(plan["lstm"]):
+            last = i == self.num_layers - 1
+            h = layer(h, B, T, h_last=h_last if last else None, persistent=self.persistent_lstm)
+        return ops.linear_l2norm(h_last, plan["w"], plan["b"])        # LstmDV.py:21-24

@@ -1,0 +1,150 @@
+"""Drop-in MelGAN ``Generator(input_size, ngf, n_residual_layers)`` on libavc_b200.so (melgan/modules.py:72-130).
+
+The module tree only HOLDS parameters under the reference's state_dict names (``model.{i}.weight_g`` ...);
+``forward`` folds weight norm once and runs every layer as a tcgen05 implicit GEMM on channels-last buffers:
+
+  ReflectionPad1d(3) + transpose    -> avc_transpose_pad (halo rows written once)
+  WNConv1d k7                       -> 7-tap conv, LeakyReLU fused (its only consumer applies it)
+  LeakyReLU + WNConvTranspose1d(r)  -> 3-tap conv producing r output phases per input frame (poly-phase), whose
+                                       epilogue writes both x (for the shortcut) and LeakyReLU(x) with the reflected
+                                       halo rows the next dilated conv needs
+  ResnetBlock                       -> [k3 dilated conv + LeakyReLU] then ONE GEMM over the K-concatenated pair
+                                       (block output, shortcut input) x [W_k1 | W_shortcut]
+  LeakyReLU + ReflectionPad1d(3) + WNConv1d(32 -> 1, k7) + Tanh -> avc_conv_to_mono_tanh
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.utils import weight_norm
+
+from .. import layers, ops, packing
+
+
+def WNConv1d(*args, **kwargs):
+    return weight_norm(nn.Conv1d(*args, **kwargs))
+
+
+def WNConvTranspose1d(*args, **kwargs):
+    return weight_norm(nn.ConvTranspose1d(*args, **kwargs))
+
+
+class ResnetBlock(nn.Module):
+    """Parameter container (melgan/modules.py:72-85)."""
+
+    def __init__(self, dim, dilation=1):
+        super().__init__()
+        self.block = nn.Sequential(nn.LeakyReLU(0.2), nn.ReflectionPad1d(dilation),
+                                   WNConv1d(dim, dim, kernel_size=3, dilation=dilation), nn.LeakyReLU(0.2),
+                                   WNConv1d(dim, dim, kernel_size=1))
+        self.shortcut = WNConv1d(dim, dim, kernel_size=1)
+        self.dilation = dilation
+
+
+class _Plan:
+    def __init__(self, gen, precision):
+        sd = {k: v.detach() for k, v in gen.state_dict().items()}
+        W = lambda p: packing.fold_weight_norm(sd[p + ".weight_g"], sd[p + ".weight_v"])
+        b = lambda p: sd[p + ".bias"].float()
+        self.precision = precision
+        self.stem = ops.ConvGemm(*packing.pack_conv(W("model.1"), b("model.1"), precision), tap_t0=[0], act="lrelu",
+                                 tag="melgan_conv")
+        self.stages = []
+        idx = 2
+        for r in gen.ratios:
+            wt = W(f"model.{idx + 1}")                                   # (C_in, C_out, 2r)
+            c_out = wt.shape[1]
+            w3 = packing.conv_transpose_as_conv(wt, r, r // 2 + r % 2)
+            up = ops.ConvGemm(*packing.pack_conv(w3, b(f"model.{idx + 1}").repeat(r), precision), tap_t0=[-1],
+                              act="lrelu", tag="melgan_up")
+            blocks = []
+            for j in range(gen.n_residual_layers):
+                p = f"model.{idx + 2 + j}"
+                d = 3 ** j
+                c3 = ops.ConvGemm(*packing.pack_conv(W(p + ".block.2"), b(p + ".block.2"), precision), tap_t0=[0],
+                                  tap_dt=[d], act="lrelu", tag="melgan_conv")
+                k1 = ops.ConvGemm(*packing.pack_conv_sources([W(p + ".block.4"), W(p + ".shortcut")],
+                                                             b(p + ".block.4") + b(p + ".shortcut"), precision),
+                                  tap_t0=[0, 0], act="lrelu", tag="melgan_conv")
+                blocks.append((d, c3, k1))
+            self.stages.append((r, c_out, up, blocks))
+            idx += 2 + gen.n_residual_layers
+        wf = W(f"model.{idx + 2}")                                        # (1, ngf, 7)
+        self.w_out = wf[0].t().contiguous().float()                      # [K][C]
+        self.b_out = float(b(f"model.{idx + 2}")[0])
+
+
+class Generator(nn.Module):
+    def __init__(self, input_size, ngf, n_residual_layers):
+        super().__init__()
+        ratios = [8, 8, 2, 2]
+        self.ratios, self.n_residual_layers = ratios, n_residual_layers
+        self.hop_length = int(np.prod(ratios))
+        mult = int(2 ** len(ratios))
+        model = [nn.ReflectionPad1d(3), WNConv1d(input_size, mult * ngf, kernel_size=7, padding=0)]
+        for r in ratios:
+            model += [nn.LeakyReLU(0.2),
+                      WNConvTranspose1d(mult * ngf, mult * ngf // 2, kernel_size=r * 2, stride=r,
+                                        padding=r // 2 + r % 2, output_padding=r % 2)]
+            for j in range(n_residual_layers):
+                model += [ResnetBlock(mult * ngf // 2, dilation=3 ** j)]
+            mult //= 2
+        model += [nn.LeakyReLU(0.2), nn.ReflectionPad1d(3), WNConv1d(ngf, 1, kernel_size=7, padding=0), nn.Tanh()]
+        self.model = nn.Sequential(*model)
+        self.precision = "fp32"
+        self.collect_taps = False
+        self.taps = {}
+        self._cache = layers.PlanCache()
+
+    def _plan(self):
+        return self._cache.get(self, (self.precision,), lambda: _Plan(self, self.precision))
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x (B, input_size, T) log-mel -> waveform (B, 1, hop_length * T)   (melgan/modules.py:129-130)."""
+        ops._require_cuda(x)
+        plan = self._plan()
+        prec = plan.precision
+        x = x.contiguous().float()
+        B, _, T = x.shape
+        dev = x.device
+        taps = self.taps if self.collect_taps else None
+        if taps is not None:
+            taps.clear()
+        m0 = ops.transpose_pad(x, 3, prec)                                # model.0 + layout change
+        cur = ops.alloc_act(B, T, plan.stem.meta["N"], prec, dev)
+        plan.stem(m0, B, T, out=cur)                                      # model.1 (+ model.2's LeakyReLU)
+        L = T
+        final = None
+        n_stage = len(plan.stages)
+        for si, (r, C, up, blocks) in enumerate(plan.stages):
+            Lr = r * L
+            d0 = blocks[0][0]
+            x_raw = ops.alloc_act(B, Lr, C, prec, dev)
+            xa = ops.alloc_act(B, Lr + 2 * d0, C, prec, dev)
+            up(cur, B, L, out=xa, out_row0=d0, reflect=d0, out_raw=x_raw, phases=r)     # ConvTranspose1d
+            if taps is not None:
+                taps[f"up{si}"] = packing.act_to_float(x_raw, prec)
+            for j, (d, c3, k1) in enumerate(blocks):
+                h1 = ops.alloc_act(B, Lr, C, prec, dev)
+                c3(xa, B, Lr, out=h1)                                     # block.0-3
+                if j + 1 < len(blocks):
+                    dn = blocks[j + 1][0]
+                    y_raw = ops.alloc_act(B, Lr, C, prec, dev)
+                    ya = ops.alloc_act(B, Lr + 2 * dn, C, prec, dev)
+                    k1([h1, x_raw], B, Lr, out=ya, out_row0=dn, reflect=dn, out_raw=y_raw)   # block.4 + shortcut
+                    x_raw, xa = y_raw, ya
+                elif si + 1 < n_stage:
+                    cur = ops.alloc_act(B, Lr, C, prec, dev)
+                    raw = ops.alloc_act(B, Lr, C, prec, dev) if taps is not None else None
+                    k1([h1, x_raw], B, Lr, out=cur, out_raw=raw)
+                    if taps is not None:
+                        taps[f"stage{si}"] = packing.act_to_float(raw, prec)
+                else:
+                    final = torch.empty(B * Lr, C, dtype=torch.float32, device=dev)
+                    raw = ops.alloc_act(B, Lr, C, prec, dev) if taps is not None else None
+                    k1([h1, x_raw], B, Lr, out2=final, out_raw=raw)
+                    if taps is not None:
+                        taps[f"stage{si}"] = packing.act_to_float(raw, prec)
+            L = Lr
+        wav = ops.conv_to_mono_tanh(final.view(B, L, -1), plan.w_out, plan.b_out)      # model.22-25
+        return wav.unsqueeze(1)

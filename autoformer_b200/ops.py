@@ -85,11 +85,19 @@ class ConvGemm:
         self.w, self.bias, self.meta = w, bias, meta
         self.tag = tag
         # algorithmic MACs per output row: real channels x taps x real output channels
-        lc = [meta["logical_channels"]] if meta.get("split") else meta["channels"]
-        self.macs_per_row = sum(c * k for c, k in zip(lc, meta["taps"])) * meta["N"]
+        if meta.get("split"):
+            self.macs_per_row = sum(c * k for c, k in zip(meta["logical_channels"], meta["logical_taps"])) * meta["N"]
+        else:
+            self.macs_per_row = sum(c * k for c, k in zip(meta["channels"], meta["taps"])) * meta["N"]
         n_src = len(meta["taps"])
-        self.tap_t0 = list(tap_t0) if tap_t0 is not None else [-(k // 2) for k in meta["taps"]]
-        self.tap_dt = list(tap_dt) if tap_dt is not None else [1] * n_src
+        # tap geometry is given per LOGICAL source; split precision duplicates it for the two physical sources
+        rep = 2 if meta.get("split") else 1
+        if tap_t0 is not None:
+            self.tap_t0 = [v for v in tap_t0 for _ in range(rep)]
+        else:
+            self.tap_t0 = [-(k // 2) for k in meta["taps"]]
+        self.tap_dt = [v for v in tap_dt for _ in range(rep)] if tap_dt is not None else [1] * n_src
+        assert len(self.tap_t0) == n_src and len(self.tap_dt) == n_src
         self.act = _lib.ACTS[act]
         self.precision = meta["precision"]
 
@@ -98,19 +106,25 @@ class ConvGemm:
         self.bias = self.bias.to(device)
         return self
 
-    def __call__(self, srcs, B, T, out=None, out_row0=0, out_dtype=None, round_tf32=True, reflect=0, out2=None,
-                 residual=None):
-        """srcs: list of channels-last activation tensors [B][rows][C_s] (one per packed source).
-        out: [B][rows_out][N] (operand dtype) written at rows out_row0 + t, or None; out2: fp32 [B*T][N] exact."""
+    def __call__(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
+                 out_raw=None, phases=1):
+        """srcs: channels-last activation tensors [B][rows][C_s], one per logical source.
+        out: act(v) [B][rows_out][Cs'] (operand format) at rows out_row0 + time (+ `reflect` mirrored halo rows);
+        out_raw: v before the activation [B][phases*T][Cs'] (operand format); out2: act(v) as exact fp32
+        [B*phases*T][Cs]; residual fp32 [B*phases*T][Cs] is added before the activation.  Cs = N / phases."""
         lib = _lib.load()
         meta = self.meta
         if not isinstance(srcs, (list, tuple)):
             srcs = [srcs]
         _require_cuda(self.w, *srcs)
         split = bool(meta.get("split"))
-        if split:      # one buffer [hi | lo]: source 0 = all 2C channels, source 1 = the hi half
-            assert len(srcs) == 1 and srcs[0].shape[2] == 2 * meta["logical_channels"], srcs[0].shape
-            srcs = [srcs[0], srcs[0][:, :, :meta["logical_channels"]]]
+        if split:      # one buffer [hi | lo] per logical source: all 2C channels, then the hi half
+            assert len(srcs) == len(meta["logical_channels"])
+            phys = []
+            for a, c in zip(srcs, meta["logical_channels"]):
+                assert a.shape[2] == 2 * c, (a.shape, c)
+                phys += [a, a[:, :, :c]]
+            srcs = phys
         assert len(srcs) == len(meta["taps"])
         d = _lib.GemmDesc()
         want = TORCH_DTYPE[self.precision]
@@ -131,9 +145,11 @@ class ConvGemm:
         d.B, d.T, d.N = B, T, meta["N"]
         d.bias = self.bias.data_ptr()
         d.act = self.act
+        d.out_phases = phases
+        cs = meta["N"] // phases
         if out is not None:
             assert out.is_cuda and out.dim() == 3 and out.shape[0] == B and out.stride(2) == 1
-            assert out.shape[2] >= packing.act_channels(meta["N"], self.precision)
+            assert out.shape[2] >= packing.act_channels(cs, self.precision)
             assert out.stride(0) == out.shape[1] * out.stride(1)
             d.out = out.data_ptr()
             d.out_ld = out.stride(1)
@@ -143,6 +159,14 @@ class ConvGemm:
             assert out.dtype in (torch.float32, torch.bfloat16)
             d.out_round_tf32 = 1 if (round_tf32 and out.dtype == torch.float32) else 0
             d.out_reflect = reflect
+        if out_raw is not None:
+            assert out_raw.is_cuda and out_raw.dtype == TORCH_DTYPE[self.precision] and out_raw.stride(-1) == 1
+            assert out_raw.shape[-1] >= packing.act_channels(cs, self.precision)
+            assert out is None or out.dtype == out_raw.dtype
+            d.out_raw = out_raw.data_ptr()
+            d.out_raw_ld = out_raw.stride(-2)
+            d.out_dtype = (2 if split else 1) if out_raw.dtype == torch.bfloat16 else 0
+            d.out_round_tf32 = 1 if (round_tf32 and out_raw.dtype == torch.float32) else 0
         if out2 is not None:
             assert out2.is_cuda and out2.dtype == torch.float32 and out2.stride(-1) == 1
             d.out2 = out2.data_ptr()
@@ -154,7 +178,7 @@ class ConvGemm:
         d.block_n = meta["block_n"]
         with PROFILER.span(self.tag, flops=2.0 * self.macs_per_row * B * T):
             _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
-        return out if out is not None else out2
+        return out if out is not None else (out2 if out2 is not None else out_raw)
 
 
 def choose_gate_group(B, H, persistent=False, n_sm=148):
@@ -239,7 +263,7 @@ def concat_bcast(seq, vec, T, div, precision, round_tf32=True):
     C2 = vec.shape[1]
     assert Tin * div == T and vec.shape[0] == B
     out = alloc_act(B, T, C1 + C2, precision, seq.device)
-    with PROFILER.span("concat", bytes=float(seq.numel() * 4 + vec.numel() * 4 + out.numel() * out.element_size())):
+    with PROFILER.span("concat", bytes=float(seq.numel() * 4 + out.numel() * out.element_size())):
         _lib.check(lib.avc_concat_bcast(seq.data_ptr(), vec.data_ptr(), out.data_ptr(), B, T, C1, C2, div,
                                         _dt(precision), 1 if round_tf32 else 0, _stream()),
                    "avc_concat_bcast")
@@ -255,4 +279,36 @@ def linear_l2norm(h, w, bias):
     out = torch.empty(B, N, dtype=torch.float32, device=h.device)
     _lib.check(lib.avc_linear_l2norm(h.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, K, N, _stream()),
                "avc_linear_l2norm")
+    return out
+
+
+def to_act(x, precision, round_tf32=True):
+    """fp32 [B][T][C] -> operand format of `precision` (a concat_bcast launch with no broadcast part)."""
+    return concat_bcast(x, None, x.shape[1], 1, precision, round_tf32)
+
+
+def transpose_pad(x, pad, precision, round_tf32=True):
+    """(B, C, L) fp32 -> channels-last [B][L + 2 pad][C'] operand format with reflected halo rows."""
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    B, C, L = x.shape
+    out = alloc_act(B, L + 2 * pad, C, precision, x.device)
+    with PROFILER.span("transpose_pad", bytes=float(x.numel() * 4 + out.numel() * out.element_size())):
+        _lib.check(lib.avc_transpose_pad(x.data_ptr(), out.data_ptr(), B, C, L, pad, _dt(precision),
+                                         1 if round_tf32 else 0, _stream()), "avc_transpose_pad")
+    return out
+
+
+def conv_to_mono_tanh(x, w, bias):
+    """x [B][L][C] fp32, w [K][C] fp32 -> tanh(conv) [B][L] with reflect padding K//2."""
+    lib = _lib.load()
+    _require_cuda(x, w)
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous()
+    B, L, C = x.shape
+    K = w.shape[0]
+    out = torch.empty(B, L, dtype=torch.float32, device=x.device)
+    with PROFILER.span("mono_conv", bytes=float(x.numel() * 4 + out.numel() * 4), flops=2.0 * K * C * B * L):
+        _lib.check(lib.avc_conv_to_mono_tanh(x.data_ptr(), w.data_ptr(), float(bias), out.data_ptr(), B, L, C, K,
+                                             _stream()), "avc_conv_to_mono_tanh")
     return out

@@ -93,11 +93,16 @@ def pack_conv_sources(weights, bias, precision, block_n=None):
     kc = KC[precision]
     n = weights[0].shape[0]
     if precision == "fp32":
-        # a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: source 0 = [a_hi|a_lo] x [w_hi|w_hi], source 1 = a_hi x w_lo
-        assert len(weights) == 1, "split precision uses both source slots for one logical source"
-        hi, lo = split_bf16(weights[0])
-        w_p, b_p, meta = pack_conv_sources([torch.cat([hi, hi], dim=1).float(), lo.float()], bias, "bf16", block_n)
-        meta.update(precision="fp32", split=True, logical_channels=weights[0].shape[1])
+        # a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: each logical source becomes two physical ones over the same
+        # buffer: [a_hi|a_lo] x [w_hi|w_hi] (2C channels) and a_hi x w_lo (the first C channels)
+        assert len(weights) <= 2, "at most two logical sources in split precision (four physical sources)"
+        phys = []
+        for w in weights:
+            hi, lo = split_bf16(w)
+            phys += [torch.cat([hi, hi], dim=1).float(), lo.float()]
+        w_p, b_p, meta = pack_conv_sources(phys, bias, "bf16", block_n)
+        meta.update(precision="fp32", split=True, logical_channels=[w.shape[1] for w in weights],
+                    logical_taps=[w.shape[2] for w in weights])
         return w_p, b_p, meta
     bn_tile = block_n or choose_block_n(n)
     n_pad = _ceil_to(n, bn_tile)

@@ -47,43 +47,54 @@ long long avc_launch_count(void);
 /*
  * Implicit-GEMM convolution / dense GEMM on the tcgen05 tensor cores (TMA-fed, TMEM accumulators).
  *
- *   out[b, t, n] = act( bias[n] + sum_s sum_k sum_c  W[n, (s,k,c)] * A_s[b, tap_t0_s + t + k*tap_dt_s, c] ) (+ residual)
+ *   v[b, t, n]   = bias[n] + sum_s sum_k sum_c  W[n, (s,k,c)] * A_s[b, tap_t0_s + t + k*tap_dt_s, c]  (+ residual)
+ *   out_raw      = v                 (operand format, no halo)              -- optional
+ *   out, out2    = act(v)            (operand format with halo / exact fp32) -- optional
  *
  * Replaces: nn.Conv1d + nn.BatchNorm1d(eval) + relu/tanh  (factory/AutoVC.py:26-41,50-51,79-94,104-108,
  * 127-179; factory/Norm.py:21-37), nn.Linear (factory/Norm.py:40-50, factory/AutoVC.py:98,112),
  * the LSTM input projections W_ih x + b_ih + b_hh of nn.LSTM (factory/AutoVC.py:43,77,96;
- * factory/LstmDV.py:12), and the MelGAN Conv1d / ConvTranspose1d layers (melgan/modules.py:72-130).
- * BatchNorm is folded by the caller: scale into W, shift into bias.
+ * factory/LstmDV.py:12), and the MelGAN WNConv1d / WNConvTranspose1d / ResnetBlock layers
+ * (melgan/modules.py:72-130).  BatchNorm and weight norm are folded by the caller.
  *
  * Rows of A outside [0, a_rows_per_utt) read as zero (the convolution's zero padding).
  * Weights are packed [n_pad][k_pad], K contiguous, k_pad = sum_s taps_s * ceil(C_s / KC) * KC with
  * KC = 32 (tf32) or 64 (bf16) channels per k-block, zero filled; n_pad is a multiple of block_n.
+ *
+ * Poly-phase output (ConvTranspose1d with stride r as a 3-tap convolution, melgan/modules.py:101-112):
+ * with out_phases = r the N = r*Cs output columns of GEMM row t are the r consecutive output samples
+ * time = r*t + phase, each with Cs channels; all output row indices below are in `time` units and the output
+ * index space is B x (r*T).
  */
+#define AVC_MAX_SOURCES 4
 typedef struct avc_gemm_desc {
-  const void* a_ptr[2];      /* up to two activation sources (K-concatenated) */
-  int a_channels[2];         /* C_s */
-  long long a_ld[2];         /* elements between consecutive rows (>= C_s, 16-byte multiple) */
-  int a_rows_per_utt[2];     /* rows per utterance in the buffer (frames + halo rows) */
-  int a_taps[2];             /* taps of source s; 0 = source unused */
-  int a_tap_t0[2];           /* buffer row that tap 0 reads for output frame 0 (negative => zero pad) */
-  int a_tap_dt[2];           /* row step between taps (dilation) */
+  const void* a_ptr[AVC_MAX_SOURCES];   /* activation sources, K-concatenated in order */
+  int a_channels[AVC_MAX_SOURCES];      /* C_s */
+  long long a_ld[AVC_MAX_SOURCES];      /* elements between consecutive rows (>= C_s, 16-byte multiple) */
+  int a_rows_per_utt[AVC_MAX_SOURCES];  /* rows per utterance in the buffer (frames + halo rows) */
+  int a_taps[AVC_MAX_SOURCES];          /* taps of source s; 0 = source unused (sources are used in order) */
+  int a_tap_t0[AVC_MAX_SOURCES];        /* buffer row that tap 0 reads for output frame 0 (negative => zero pad) */
+  int a_tap_dt[AVC_MAX_SOURCES];        /* row step between taps (dilation) */
   const void* w_ptr;         /* packed weights */
   int n_pad, k_pad;
-  int dtype;                 /* AVC_DTYPE_* of A and W */
-  int B, T;                  /* output index space: B utterances x T frames */
-  int N;                     /* real output channels (multiple of 4) */
+  int dtype;                 /* AVC_DTYPE_TF32 or AVC_DTYPE_BF16 (operand type of A and W) */
+  int B, T;                  /* GEMM row space: B utterances x T frames */
+  int N;                     /* real output columns (multiple of 4) */
   const float* bias;         /* [n_pad] fp32 */
   int act;                   /* AVC_ACT_* */
-  void* out;                 /* [B][out_rows_per_utt][out_ld], written at row out_row0 + t */
+  int out_phases;            /* r >= 1 (0 is read as 1): N = r * Cs, see above */
+  void* out;                 /* act(v): [B][out_rows_per_utt][out_ld], written at row out_row0 + time */
   long long out_ld;
   int out_rows_per_utt, out_row0;
-  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column n, lo at column N + n (out_ld >= 2N) */
+  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column c, lo at column Cs + c (out_ld >= 2Cs) */
   int out_round_tf32;        /* round fp32 outputs to TF32 (rna) so the next GEMM reads them exactly */
   int out_reflect;           /* also write `out_reflect` reflected halo rows each side (ReflectionPad1d,
                                 melgan/modules.py:77,96,121); needs out_row0 >= out_reflect */
-  float* out2;               /* optional exact fp32 copy, rows b*T+t, ld out2_ld (may be NULL) */
+  void* out_raw;             /* v before the activation, same dtype as out, rows b*(r*T)+time, ld out_raw_ld (may be NULL) */
+  long long out_raw_ld;
+  float* out2;               /* act(v) as exact fp32, rows b*(r*T)+time, ld out2_ld (may be NULL) */
   long long out2_ld;
-  const float* residual;     /* optional fp32 [B*T][res_ld], added after the activation */
+  const float* residual;     /* optional fp32, rows b*(r*T)+time, ld res_ld, added BEFORE the activation */
   long long res_ld;
   int block_n;               /* 64 / 128 / 256; 0 = choose */
 } avc_gemm_desc;
@@ -131,7 +142,7 @@ int avc_bilstm_small(const float* xproj, const float* w_hh, void* out, int out_d
  * Replaces the speaker-code concat of Encoder.forward (factory/AutoVC.py:46-48; div = 1) and the code
  * up-sampling + target-speaker concat of AutoVC.forward (factory/AutoVC.py:197-204; div = freq).
  *   seq [B][T/div][C1] fp32, vec [B][C2] fp32, out [B][T][C1+C2] in out_dtype (2: [B][T][2(C1+C2)] split bf16).
- *   C1, C2 multiples of 4.
+ *   C1, C2 multiples of 4; C2 = 0 (vec NULL) turns it into a pure fp32 -> operand-format conversion.
  */
 int avc_concat_bcast(const float* seq, const float* vec, void* out, int B, int T, int C1, int C2, int div,
                      int out_dtype, int out_round_tf32, void* stream);
@@ -141,6 +152,22 @@ int avc_concat_bcast(const float* seq, const float* vec, void* out, int B, int T
  */
 int avc_linear_l2norm(const float* h, const float* w, const float* bias, float* out, int B, int K, int N,
                       void* stream);
+
+/*
+ * in [B][C][L] fp32 (channels-first, the reference's (B, 80, T) mel layout) -> out [B][L + 2*pad][C'] channels-last in
+ * out_dtype (C' = C, or 2C for split bf16), with `pad` reflected rows each side (nn.ReflectionPad1d(3) in front of the
+ * MelGAN stem, melgan/modules.py:96; `mel.transpose` at conversion.ipynb cell 14).  C multiple of 4, L > pad.
+ */
+int avc_transpose_pad(const float* in, void* out, int B, int C, int L, int pad, int out_dtype, int out_round_tf32,
+                      void* stream);
+
+/*
+ * MelGAN output layer: out[b, t] = tanh( bias + sum_k sum_c w[k][c] * x[b, reflect(t + k - K/2), c] )
+ * (ReflectionPad1d(3) + WNConv1d(32 -> 1, k7) + Tanh, melgan/modules.py:120-124; the preceding LeakyReLU is applied
+ * by the producer).  x [B][L][C] fp32, w [K][C] fp32 (weight norm folded), out [B][L] fp32.  K odd <= 15, C <= 64.
+ */
+int avc_conv_to_mono_tanh(const float* x, const float* w, float bias, float* out, int B, int L, int C, int K,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -198,6 +198,49 @@ def autovc_taps():
                 print(f"    {k:12s} rel_l2={rel_l2(m.taps[k], rt[k]):.3e} centred={centred_rel_l2(m.taps[k], rt[k]):.3e}")
 
 
+@case
+def melgan():
+    import warnings
+    warnings.filterwarnings("ignore")
+    import torch
+    from autoformer_b200.melgan.modules import Generator
+    from oracle import rel_l2, templates
+    from oracle.melgan import melgan_forward
+    from oracle.seeded import seeded_state_dict, synthetic_mel
+    sd = seeded_state_dict(templates.melgan_template(), 4)
+    for prec in ("fp32", "tf32", "bf16"):
+        for B, T in ((1, 40), (2, 17)):
+            mel = synthetic_mel(B, T, 6).transpose(1, 2).contiguous()
+            rt = {}
+            ref = melgan_forward(sd, mel, taps=rt, dtype=torch.float64)
+            g = Generator(80, 32, 3)
+            g.load_state_dict(sd)
+            g = g.cuda().eval()
+            g.precision = prec
+            g.collect_taps = True
+            wav = g(mel.cuda())
+            torch.cuda.synchronize()
+            print(f"  melgan {prec} B={B} T={T}: wav rel_l2={rel_l2(wav, ref):.3e}", {k: f"{rel_l2(g.taps[k], rt[k].transpose(1, 2)):.1e}" for k in g.taps})
+
+
+@case
+def lstmdv():
+    import torch
+    from autoformer_b200.factory.LstmDV import LstmDV
+    from oracle import rel_l2, templates
+    from oracle.lstmdv import lstmdv_forward
+    from oracle.seeded import seeded_state_dict, synthetic_mel
+    sd = seeded_state_dict(templates.lstmdv_template(), 3, lstm_gain=1.5)
+    x = synthetic_mel(2, 100, 5)
+    ref = lstmdv_forward(sd, x, dtype=torch.float64)
+    for prec in ("fp32", "tf32", "bf16"):
+        m = LstmDV()
+        m.load_state_dict(sd)
+        m = m.cuda().eval()
+        m.precision = prec
+        print(f"  lstmdv {prec}: rel_l2={rel_l2(m(x.cuda()), ref):.3e}")
+
+
 def main():
     names = sys.argv[1:] or list(CASES)
     if len(names) == 1 and os.environ.get("AVC_PROBE_CHILD"):

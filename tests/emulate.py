@@ -44,3 +44,141 @@ def emulate_lstm_seq(xproj, w_hh_packed, B, T, H, G):
         h = torch.sigmoid(zo) * torch.tanh(c)
         out[:, t] = h
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU stand-ins for the C-ABI entry points, so the drop-in models' HOST logic (weight packing, halo buffers,
+# poly-phase outputs, gate interleave, buffer formats) can be exercised without a GPU.  Test-only: installed by
+# the `cpu_kernels` fixture through monkeypatching; the product package never imports this file.
+# ---------------------------------------------------------------------------------------------------------
+import torch.nn.functional as F  # noqa: E402
+
+from autoformer_b200 import ops, packing  # noqa: E402
+
+_ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(v, 0.2)}
+
+
+def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
+                       out_raw=None, phases=1):
+    meta = self.meta
+    prec = self.precision
+    if not isinstance(srcs, (list, tuple)):
+        srcs = [srcs]
+    if meta.get("split"):
+        phys = []
+        for a, c in zip(srcs, meta["logical_channels"]):
+            assert a.shape[2] == 2 * c
+            phys += [a, a[:, :, :c]]
+        srcs = phys
+    for a, c in zip(srcs, meta["channels"]):
+        assert a.shape[2] == c and a.dtype == packing.TORCH_DTYPE[prec]
+    v = emulate_conv_gemm(self.w, self.bias, meta, srcs, B, T, self.tap_t0, self.tap_dt)
+    n = meta["N"]
+    cs = n // phases
+    tl = T * phases
+    v = v.reshape(B, tl, cs)
+    if residual is not None:
+        v = v + residual.reshape(B, tl, -1)[..., :cs].double()
+    ac = packing.act_channels(cs, prec)
+    if out_raw is not None:
+        out_raw.view(B, tl, -1)[..., :ac] = packing.to_act(v.float(), prec)
+    a = _ACT[self.act](v)
+    if out is not None:
+        assert out.shape[1] >= out_row0 + tl + reflect and out_row0 >= reflect
+        full = a
+        if reflect:
+            full = F.pad(a.transpose(1, 2), (reflect, reflect), mode="reflect").transpose(1, 2)
+        out[:, out_row0 - reflect:out_row0 + tl + reflect, :ac] = packing.to_act(full.float(), prec)
+    if out2 is not None:
+        out2.view(B, tl, -1)[..., :cs] = a.float()
+    return out if out is not None else (out2 if out2 is not None else out_raw)
+
+
+def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False):
+    if precision == "fp32":
+        w = w_hh[:, :H].double() + w_hh[:, 2 * H:].double()
+    else:
+        w = w_hh.double()
+    xp = xproj.double().view(B, T, 4 * H)
+    h = torch.zeros(B, H, dtype=torch.float64)
+    c = torch.zeros(B, H, dtype=torch.float64)
+    outs = torch.zeros(B, T, H, dtype=torch.float64)
+    u = torch.arange(H)
+    base = (u // group) * 4 * group + u % group
+    for t in range(T):
+        hq = packing.act_to_float(packing.to_act(h.float(), precision), precision).double()   # operand rounding of h
+        z = xp[:, t] + hq @ w.t()
+        zi, zf, zg, zo = (z[:, base + g * group] for g in range(4))
+        c = torch.sigmoid(zf) * c + torch.sigmoid(zi) * torch.tanh(zg)
+        h = torch.sigmoid(zo) * torch.tanh(c)
+        outs[:, t] = h
+    if hseq is None:
+        hseq = torch.empty(B, T, packing.act_channels(H, precision), dtype=packing.TORCH_DTYPE[precision])
+    hseq.copy_(packing.to_act(outs.float(), precision))
+    if hseq_f32 is not None:
+        hseq_f32.copy_(outs.float())
+    if h_last is not None:
+        h_last.copy_(outs[:, -1].float())
+    return hseq
+
+
+def _emu_bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=True, split=False):
+    xp = xproj.double().view(B, T, 8 * H)
+    res = torch.zeros(B, T, 2 * H, dtype=torch.float64)
+    for d in range(2):
+        w = w_hh[d].double()
+        h = torch.zeros(B, H, dtype=torch.float64)
+        c = torch.zeros(B, H, dtype=torch.float64)
+        steps = range(T - 1, -1, -1) if d else range(T)
+        for t in steps:
+            z = xp[:, t, d * 4 * H:(d + 1) * 4 * H] + h @ w.t()
+            zi, zf, zg, zo = z.split(H, dim=1)
+            c = torch.sigmoid(zf) * c + torch.sigmoid(zi) * torch.tanh(zg)
+            h = torch.sigmoid(zo) * torch.tanh(c)
+            res[:, t, d * H:(d + 1) * H] = h
+    if out is not None:
+        if split:
+            out.copy_(packing.to_act(res.float(), "fp32"))
+        elif out.dtype == torch.bfloat16:
+            out.copy_(res.to(torch.bfloat16))
+        else:
+            out.copy_(packing.round_tf32(res.float()) if round_tf32 else res.float())
+    if codes is not None:
+        codes.copy_(torch.cat((res[:, freq - 1::freq, :H], res[:, ::freq, H:]), dim=-1).float())
+    return out, codes
+
+
+def _emu_concat_bcast(seq, vec, T, div, precision, round_tf32=True):
+    parts = [seq.repeat_interleave(div, dim=1)]
+    if vec is not None:
+        parts.append(vec.unsqueeze(1).expand(-1, T, -1))
+    return packing.to_act(torch.cat(parts, dim=-1), precision)
+
+
+def _emu_linear_l2norm(h, w, bias):
+    e = h.double() @ w.double().t() + bias.double()
+    return (e / e.norm(dim=-1, keepdim=True)).float()
+
+
+def _emu_transpose_pad(x, pad, precision, round_tf32=True):
+    y = F.pad(x, (pad, pad), mode="reflect") if pad else x
+    return packing.to_act(y.transpose(1, 2).contiguous(), precision)
+
+
+def _emu_conv_to_mono_tanh(x, w, bias):
+    K = w.shape[0]
+    xp = F.pad(x.double().transpose(1, 2), (K // 2, K // 2), mode="reflect")
+    y = F.conv1d(xp, w.double().t().unsqueeze(0)) + bias
+    return torch.tanh(y).squeeze(1).float()
+
+
+def install_cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops, "_require_cuda", lambda *a: None)
+    monkeypatch.setattr(ops.ConvGemm, "__call__", _emu_convgemm_call)
+    monkeypatch.setattr(ops, "lstm_seq", _emu_lstm_seq)
+    monkeypatch.setattr(ops, "bilstm_small", _emu_bilstm_small)
+    monkeypatch.setattr(ops, "concat_bcast", _emu_concat_bcast)
+    monkeypatch.setattr(ops, "to_act", lambda x, precision, round_tf32=True: _emu_concat_bcast(x, None, x.shape[1], 1, precision))
+    monkeypatch.setattr(ops, "linear_l2norm", _emu_linear_l2norm)
+    monkeypatch.setattr(ops, "transpose_pad", _emu_transpose_pad)
+    monkeypatch.setattr(ops, "conv_to_mono_tanh", _emu_conv_to_mono_tanh)

@@ -221,3 +221,84 @@ def test_state_dict_roundtrip_and_repack_on_reload():
     y1 = m(x, c_org, c_trg)[1]
     ref1 = autovc_forward(sd1, x.cpu(), c_org.cpu(), c_trg.cpu(), 32, 32)[1]
     assert rel_l2(y1, ref1) < 2e-4 and rel_l2(y0, ref1) > 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ LstmDV / MelGAN / pipeline
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 2e-2)])
+def test_lstmdv_parity_and_golden(precision, tol):
+    from autoformer_b200.factory.LstmDV import LstmDV
+    from oracle.lstmdv import lstmdv_forward
+    g = np.load(os.path.join(GOLDEN, "lstmdv_b2_t100.npz"))
+    sd = seeded_state_dict(templates.lstmdv_template(), int(g["wseed"]), lstm_gain=float(g["lstm_gain"]))
+    x = synthetic_mel(int(g["B"]), int(g["T"]), int(g["xseed"]))
+    m = LstmDV()
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    m.precision = precision
+    e = m(x.cuda())
+    assert rel_l2(e, torch.from_numpy(g["emb"])) < tol                 # the unmodified reference's output
+    assert rel_l2(e, lstmdv_forward(sd, x)) < tol
+    assert torch.allclose(e.norm(dim=-1), torch.ones(2, device="cuda"), atol=1e-4)
+    m.persistent_lstm = True
+    assert torch.equal(m(x.cuda()), e)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 5e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("name", ["melgan_b1_t40", "melgan_b2_t17"])
+def test_melgan_parity_and_golden(precision, tol, name):
+    import warnings
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    from autoformer_b200.melgan.modules import Generator
+    from oracle.melgan import melgan_forward
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, T = int(g["B"]), int(g["T"])
+    sd = seeded_state_dict(templates.melgan_template(), int(g["wseed"]))
+    mel = synthetic_mel(B, T, int(g["xseed"])).transpose(1, 2).contiguous()
+    rt = {}
+    ref = melgan_forward(sd, mel, taps=rt)
+    gen = Generator(80, 32, 3)
+    gen.load_state_dict(sd)
+    gen = gen.cuda().eval()
+    gen.precision = precision
+    gen.collect_taps = True
+    wav = gen(mel.cuda())
+    assert wav.shape == (B, 1, 256 * T)
+    for k in ("up0", "stage0", "up1", "stage1", "up2", "stage2", "up3", "stage3"):
+        assert rel_l2(gen.taps[k], rt[k].transpose(1, 2)) < tol, k
+    assert rel_l2(wav, ref) < tol
+    assert rel_l2(wav, torch.from_numpy(g["wav"])) < tol               # the unmodified reference's waveform
+    if precision == "fp32":
+        # random-init MelGAN output is dominated by a constant offset: gate the centred signal too
+        c, r = wav.cpu().double(), ref.double()
+        assert ((c - r.mean()) - (r - r.mean())).norm() / (r - r.mean()).norm() < 1e-3
+
+
+def test_full_pipeline_embed_convert_vocode():
+    """BASELINE config 4 at test size: LstmDV(src), LstmDV(tgt) -> AutoVC with pad/convert/trim -> MelGAN."""
+    import warnings
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    from autoformer_b200 import pipeline
+    from autoformer_b200.factory.AutoVC import AutoVC
+    from autoformer_b200.factory.LstmDV import LstmDV
+    from autoformer_b200.melgan.modules import Generator
+    from oracle.lstmdv import lstmdv_forward
+    from oracle.melgan import melgan_forward
+    args = (32, 256, 512, 32)
+    B, T = 2, 100                                       # 100 is not a multiple of 32: pad to 128, trim back
+    sd_dv = seeded_state_dict(templates.lstmdv_template(), 3, lstm_gain=1.5)
+    sd_vc = seeded_state_dict(templates.autovc_template(*args), 0)
+    sd_g = seeded_state_dict(templates.melgan_template(), 4)
+    src, trg = synthetic_mel(B, T, 11), synthetic_mel(B, 80, 12)
+    # oracle pipeline (same recipe, CPU)
+    e_org, e_trg = lstmdv_forward(sd_dv, src), lstmdv_forward(sd_dv, trg)
+    xpad = torch.nn.functional.pad(src, (0, 0, 0, 28))
+    ref_mel = autovc_forward(sd_vc, xpad, e_org, e_trg, 32, 32)[1].squeeze(1)[:, :T]
+    ref_wav = melgan_forward(sd_g, ref_mel.transpose(1, 2)).squeeze(1)
+    dv, vc, gen = LstmDV(), AutoVC(*args), Generator(80, 32, 3)
+    dv.load_state_dict(sd_dv), vc.load_state_dict(sd_vc), gen.load_state_dict(sd_g)
+    dv, vc, gen = dv.cuda().eval(), vc.cuda().eval(), gen.cuda().eval()
+    mel, wav, eo, et = pipeline.convert_and_vocode(dv, vc, gen, src.cuda(), trg.cuda())
+    assert mel.shape == (B, T, 80) and wav.shape == (B, 256 * T)
+    assert rel_l2(eo, e_org) < 1e-4 and rel_l2(et, e_trg) < 1e-4
+    assert rel_l2(mel, ref_mel) < 1e-3
+    assert rel_l2(wav, ref_wav) < 1e-3
