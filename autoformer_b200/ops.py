@@ -258,13 +258,17 @@ def concat_bcast(seq, vec, T, div, precision, round_tf32=True):
     """[seq[b, t // div, :] || vec[b, :]] -> [B][T][C1+C2] in the operand dtype of `precision`."""
     lib = _lib.load()
     _require_cuda(seq, vec)
-    assert seq.dtype == torch.float32 and vec.dtype == torch.float32 and seq.is_contiguous() and vec.is_contiguous()
+    assert seq.dtype == torch.float32 and seq.is_contiguous()
     B, Tin, C1 = seq.shape
-    C2 = vec.shape[1]
-    assert Tin * div == T and vec.shape[0] == B
+    C2 = 0
+    if vec is not None:
+        assert vec.dtype == torch.float32 and vec.is_contiguous() and vec.shape[0] == B
+        C2 = vec.shape[1]
+    assert Tin * div == T
     out = alloc_act(B, T, C1 + C2, precision, seq.device)
+    vec_ptr = vec.data_ptr() if vec is not None else None
     with PROFILER.span("concat", bytes=float(seq.numel() * 4 + out.numel() * out.element_size())):
-        _lib.check(lib.avc_concat_bcast(seq.data_ptr(), vec.data_ptr(), out.data_ptr(), B, T, C1, C2, div,
+        _lib.check(lib.avc_concat_bcast(seq.data_ptr(), vec_ptr, out.data_ptr(), B, T, C1, C2, div,
                                         _dt(precision), 1 if round_tf32 else 0, _stream()),
                    "avc_concat_bcast")
     return out

@@ -75,8 +75,9 @@ def test_conv_gemm_residual_and_reflect_halo():
     out2 = torch.empty(B * T, c, device="cuda")
     layer(packing.to_act(x, "fp32").cuda(), B, T, out=out, out_row0=P, reflect=P, out2=out2, residual=res.cuda())
     torch.cuda.synchronize()
-    ref = F.leaky_relu(F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=1), 0.2) \
-        + res.double().view(B, T, c).transpose(1, 2)
+    # the residual is added BEFORE the activation (include/avc_b200.h)
+    ref = F.leaky_relu(F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=1)
+                       + res.double().view(B, T, c).transpose(1, 2), 0.2)
     assert rel_l2(out2.view(B, T, c), ref.transpose(1, 2)) < 5e-5
     padded = F.pad(ref, (P, P), mode="reflect").transpose(1, 2)          # ReflectionPad1d semantics
     assert rel_l2(packing.act_to_float(out, "fp32"), padded) < 5e-5
