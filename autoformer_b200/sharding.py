@@ -1,0 +1,86 @@
+"""Utterance-sharded data parallelism for the conversion path (BASELINE config 5).
+
+In eval mode every utterance is independent, so the path shards by utterance with NO data-path collective:
+weights are replicated, each rank converts its own batches, and ``torch.distributed`` (NCCL over NVLink on the GPU
+box, gloo in the CPU tests) is used only to gather fixed-size per-rank records (frames, time, checksum) and, on
+request, the outputs.  Utterances are bucketed by EXACT length: zero padding changes the result because the
+backward LSTM and LstmDV's last step see the padding, so batches never mix lengths.
+"""
+from collections import defaultdict
+
+import torch
+import torch.distributed as dist
+
+
+def bucket_by_length(lengths):
+    """lengths[i] = frames of utterance i -> {T: [utterance ids]} (ids ascending)."""
+    buckets = defaultdict(list)
+    for i, t in enumerate(lengths):
+        buckets[int(t)].append(i)
+    return dict(sorted(buckets.items()))
+
+
+def make_batches(buckets, max_batch=512):
+    """Split every bucket into batches of at most ``max_batch`` utterances: [(T, [ids])]."""
+    batches = []
+    for t, ids in buckets.items():
+        for s in range(0, len(ids), max_batch):
+            batches.append((t, ids[s:s + max_batch]))
+    return batches
+
+
+def assign_batches(batches, world_size):
+    """Greedy longest-processing-time assignment by frame count.  Deterministic, identical on every rank.
+
+    Returns a list (one entry per rank) of batch lists."""
+    order = sorted(range(len(batches)), key=lambda i: (-batches[i][0] * len(batches[i][1]), i))
+    load = [0] * world_size
+    out = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        out[r].append(batches[i])
+        load[r] += batches[i][0] * len(batches[i][1])
+    return out
+
+
+def plan(lengths, world_size, max_batch=512):
+    return assign_batches(make_batches(bucket_by_length(lengths), max_batch), world_size)
+
+
+def gather_records(record, device=None):
+    """All-gather one fixed-size float64 record per rank; returns a (world, len) tensor on every rank."""
+    rec = torch.as_tensor(record, dtype=torch.float64, device=device)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rec.unsqueeze(0)
+    out = [torch.zeros_like(rec) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, rec)
+    return torch.stack(out)
+
+
+def gather_outputs(local, total_count, ids, dst=0):
+    """Gather per-utterance outputs of equal shape to rank ``dst``: local (n_local, ...) with global ids ``ids``.
+
+    Chunked all_gather of padded blocks (ranks may hold different counts).  Returns the (total_count, ...) tensor on
+    ``dst`` and None elsewhere.  Outside any timed region in bench.py."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        full = local.new_zeros((total_count,) + tuple(local.shape[1:]))
+        full[torch.as_tensor(ids, device=local.device, dtype=torch.long)] = local
+        return full
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = gather_records([float(len(ids))], device=local.device).long().flatten()
+    cap = int(counts.max().item())
+    pad_local = local.new_zeros((cap,) + tuple(local.shape[1:]))
+    pad_local[:len(ids)] = local
+    pad_ids = torch.full((cap,), -1, dtype=torch.long, device=local.device)
+    pad_ids[:len(ids)] = torch.as_tensor(ids, dtype=torch.long, device=local.device)
+    all_vals = [torch.zeros_like(pad_local) for _ in range(world)]
+    all_ids = [torch.zeros_like(pad_ids) for _ in range(world)]
+    dist.all_gather(all_vals, pad_local)
+    dist.all_gather(all_ids, pad_ids)
+    if rank != dst:
+        return None
+    full = local.new_zeros((total_count,) + tuple(local.shape[1:]))
+    for v, i in zip(all_vals, all_ids):
+        keep = i >= 0
+        full[i[keep]] = v[keep]
+    return full

@@ -24,8 +24,6 @@ if ROOT not in sys.path:
 
 MODEL_ARGS = (32, 256, 512, 32)            # AutoVC "original" hyper-parameters
 FLOP_PER_FRAME = 56_770_560                # conv 23,511,040 + in-proj/Linear 14,352,384 + recurrent 18,907,136
-FAMILY_FLOP_PER_FRAME = {"conv": 23_511_040, "inproj": 14_188_544 + 0, "linear": 163_840, "lstm_step": 18_874_368,
-                         "bilstm_small": 32_768}
 METRIC = "converted mel-frames/sec"
 UNIT = "frames/s"
 
@@ -42,6 +40,10 @@ def parse_args():
     ap.add_argument("--lstm", default="auto", choices=["auto", "persistent", "per-step"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=16, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--workload", default="batch", choices=["batch", "sweep"],
+                    help="batch: BASELINE config 2 (default); sweep: config 5, utterances of 128..1024 frames "
+                         "bucketed by exact length and sharded over the ranks (strong scaling)")
+    ap.add_argument("--utterances", type=int, default=65536)
     return ap.parse_args()
 
 
@@ -355,10 +357,92 @@ def run_native(args):
     return 0
 
 
+def run_sweep(args):
+    """BASELINE config 5: N utterances with T uniform in {128,160,...,1024}, bucketed by exact T, batches of <= 512,
+    greedily assigned to ranks by frame count; no data-path collective; NCCL gathers the per-rank records."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from autoformer_b200 import _lib, sharding
+    from autoformer_b200.factory.AutoVC import AutoVC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234)
+    model = AutoVC(*MODEL_ARGS).to(dev).eval()
+    model.precision = args.precision
+    model.persistent_lstm = args.lstm != "per-step"
+    rng = random.Random(1234)
+    lengths = [rng.choice(range(128, 1025, 32)) for _ in range(args.utterances)]
+    mine = sharding.plan(lengths, world, args.batch)[rank]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool = {}
+
+    def inputs(T, n):
+        if T not in pool:      # synthetic data: one resident batch per length, reused for every batch of that length
+            x = torch.rand(args.batch, T, 80, generator=gen, device=dev) * 6 - 5
+            c = torch.nn.functional.normalize(torch.randn(2, args.batch, 256, generator=gen, device=dev), dim=-1)
+            pool[T] = (x, c[0].contiguous(), c[1].contiguous())
+        x, co, ct = pool[T]
+        return x[:n], co[:n], ct[:n]
+
+    def one_pass():
+        acc = torch.zeros((), device=dev, dtype=torch.float64)
+        for T, ids in mine:
+            x, co, ct = inputs(T, len(ids))
+            acc += model(x, co, ct)[1].double().sum()
+        return acc
+
+    for T in sorted({t for t, _ in mine})[:3]:          # warm-up: a few buckets (weights packed, kernels loaded)
+        model(*inputs(T, min(args.batch, 64)))
+    for T, ids in mine:                                  # allocate every resident input before timing
+        inputs(T, len(ids))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    chk = one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    frames = float(sum(t * len(i) for t, i in mine))
+    recs = sharding.gather_records([frames, ms, float(chk)], device=dev)
+    if rank == 0:
+        total = float(recs[:, 0].sum())
+        ms_max = float(recs[:, 1].max())
+        pk = peaks()
+        line = {"metric": METRIC, "value": total / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": 1,
+                "warmup": 3, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"AutoVC(32,256,512,32) conversion of {args.utterances} utterances x 128..1024 "
+                                       "frames (BASELINE.json configs[4]), bucketed by exact length, batches <= "
+                                       f"{args.batch}, sharded by frames over {world} ranks",
+                           "frames_total": total, "batches": sum(1 for _ in sharding.make_batches(
+                               sharding.bucket_by_length(lengths), args.batch))},
+                "frac_of_model_roofline": total / (ms_max * 1e-3) / world / (pk["tflops_sustained"] * 1e12 / FLOP_PER_FRAME),
+                "gpu_launches": _lib.launch_count() - n0,
+                "ranks": [{"frames": r[0], "ms": r[1], "checksum": r[2]} for r in recs.tolist()]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "sweep":
+        return run_sweep(args)
     return run_native(args)
 
 

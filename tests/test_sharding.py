@@ -1,0 +1,76 @@
+"""Host logic of the utterance-sharded multi-GPU path, incl. a real world_size-2 gloo run on CPU."""
+import os
+import random
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from autoformer_b200 import sharding
+
+
+def _lengths(n, seed=0):
+    rng = random.Random(seed)
+    return [rng.choice(range(128, 1025, 32)) for _ in range(n)]
+
+
+def test_buckets_are_exact_length_and_cover_everything():
+    lens = _lengths(5000)
+    b = sharding.bucket_by_length(lens)
+    assert all(t % 32 == 0 for t in b) and sum(len(v) for v in b.values()) == 5000
+    for t, ids in b.items():
+        assert all(lens[i] == t for i in ids)
+    batches = sharding.make_batches(b, 512)
+    assert all(1 <= len(ids) <= 512 for _, ids in batches)
+    assert sorted(i for _, ids in batches for i in ids) == list(range(5000))
+    assert sharding.make_batches({}, 512) == []                         # empty input
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_assignment_is_balanced_and_deterministic(world):
+    lens = _lengths(65536 // 8, seed=1)
+    plan_a = sharding.plan(lens, world)
+    plan_b = sharding.plan(lens, world)
+    assert plan_a == plan_b
+    seen = sorted(i for r in plan_a for _, ids in r for i in ids)
+    assert seen == list(range(len(lens)))                               # every utterance exactly once
+    load = [sum(t * len(ids) for t, ids in r) for r in plan_a]
+    assert max(load) - min(load) <= 1024 * 512                          # within one largest batch
+    assert max(load) <= sum(load) / world * 1.15
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lens = _lengths(300, seed=2)
+    mine = sharding.plan(lens, world, max_batch=16)[rank]
+    ids = [i for _, b in mine for i in b]
+    frames = float(sum(t * len(b) for t, b in mine))
+    # stand-in for the conversion: output row = [id, length]
+    local = torch.tensor([[float(i), float(lens[i])] for i in ids]).reshape(-1, 2)
+    recs = sharding.gather_records([frames, float(len(ids)), float(local.sum())])
+    full = sharding.gather_outputs(local, len(lens), ids, dst=0)
+    if rank == 0:
+        q.put((recs.tolist(), full.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + random.randint(0, 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    recs, full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lens = _lengths(300, seed=2)
+    assert len(recs) == 2 and sum(r[1] for r in recs) == 300
+    assert sum(r[0] for r in recs) == float(sum(lens))
+    assert [int(v[0]) for v in full] == list(range(300))                # every utterance landed at its own index
+    assert [int(v[1]) for v in full] == lens
