@@ -7,12 +7,13 @@ LIB_PATH = os.path.join(_HERE, "libavc_b200.so")
 
 DTYPE_TF32 = 0
 DTYPE_BF16 = 1
-ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU = 0, 1, 2, 3
-ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU}
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU, ACT_GELU = 0, 1, 2, 3, 4
+ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU, "gelu": ACT_GELU}
 
 EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm", "avc_lstm_seq",
            "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_transpose_pad",
-           "avc_conv_to_mono_tanh"]
+           "avc_conv_to_mono_tanh", "avc_gn_stats", "avc_gn_pool_residual", "avc_gn_apply", "avc_patchify",
+           "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes"]
 
 
 MAX_SOURCES = 4
@@ -51,6 +52,7 @@ class GemmDesc(ctypes.Structure):
         ("out2_ld", ctypes.c_longlong),
         ("residual", ctypes.c_void_p),
         ("res_ld", ctypes.c_longlong),
+        ("res_after_act", ctypes.c_int),
         ("block_n", ctypes.c_int),
     ]
 
@@ -111,6 +113,17 @@ def load():
     lib.avc_conv_to_mono_tanh.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.avc_conv_to_mono_tanh.restype = ctypes.c_int
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lib.avc_gn_stats.argtypes = [vp, vp, ci, ctypes.c_longlong, ctypes.c_float, vp]
+    lib.avc_gn_pool_residual.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.avc_gn_apply.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.avc_patchify.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.avc_ln_transpose.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp, ci, ci, ci, vp]
+    lib.avc_meta_decoder_input.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+    lib.avc_gather_codes.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    for fn in (lib.avc_gn_stats, lib.avc_gn_pool_residual, lib.avc_gn_apply, lib.avc_patchify, lib.avc_ln_transpose,
+               lib.avc_meta_decoder_input, lib.avc_gather_codes):
+        fn.restype = ctypes.c_int
     _lib = lib
     return lib
 

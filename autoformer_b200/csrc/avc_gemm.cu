@@ -42,6 +42,7 @@ struct alignas(64) GemmParams {
   long long out2_ld;
   const float* residual;
   long long res_ld;
+  int res_after;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -49,6 +50,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case AVC_ACT_RELU: return fmaxf(v, 0.0f);
     case AVC_ACT_TANH: return tanh_fast(v);
     case AVC_ACT_LRELU: return v > 0.0f ? v : 0.2f * v;
+    case AVC_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
     default: return v;
   }
 }
@@ -171,13 +173,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             o[1] = __uint_as_float(v[4 * j + 1]) + bv.y;
             o[2] = __uint_as_float(v[4 * j + 2]) + bv.z;
             o[3] = __uint_as_float(v[4 * j + 3]) + bv.w;
-            if (p.residual) {
-              const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + lrow * p.res_ld + c));
-              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-            }
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.residual) rv = __ldg(reinterpret_cast<const float4*>(p.residual + lrow * p.res_ld + c));
+            if (!p.res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
             if (p.out_raw) store4(p.out_raw, p.out_mode, p.out_round, lrow, p.out_raw_ld, c, p.cs, o);
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = apply_act(o[i], p.act);
+            if (p.res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
             if (p.out) {
               const long long orow = obase + time;
               store4(p.out, p.out_mode, p.out_round, orow, p.out_ld, c, p.cs, o);
@@ -304,6 +306,7 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   p.out2_ld = d->out2_ld;
   p.residual = d->residual;
   p.res_ld = d->res_ld;
+  p.res_after = d->res_after_act;
   if (d->out) {
     AVC_REQUIRE(d->out_ld % 4 == 0 && d->out_ld >= min_ld &&
                     d->out_rows_per_utt >= d->out_row0 + t_out + d->out_reflect && d->out_row0 >= d->out_reflect,

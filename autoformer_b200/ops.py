@@ -107,7 +107,7 @@ class ConvGemm:
         return self
 
     def __call__(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                 out_raw=None, phases=1):
+                 out_raw=None, phases=1, res_after=False):
         """srcs: channels-last activation tensors [B][rows][C_s], one per logical source.
         out: act(v) [B][rows_out][Cs'] (operand format) at rows out_row0 + time (+ `reflect` mirrored halo rows);
         out_raw: v before the activation [B][phases*T][Cs'] (operand format); out2: act(v) as exact fp32
@@ -175,6 +175,7 @@ class ConvGemm:
             assert residual.is_cuda and residual.dtype == torch.float32 and residual.stride(-1) == 1
             d.residual = residual.data_ptr()
             d.res_ld = residual.stride(-2)
+            d.res_after_act = 1 if res_after else 0
         d.block_n = meta["block_n"]
         with PROFILER.span(self.tag, flops=2.0 * self.macs_per_row * B * T):
             _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
@@ -316,3 +317,98 @@ def conv_to_mono_tanh(x, w, bias):
         _lib.check(lib.avc_conv_to_mono_tanh(x.data_ptr(), w.data_ptr(), float(bias), out.data_ptr(), B, L, C, K,
                                              _stream()), "avc_conv_to_mono_tanh")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ Meta glue
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def gn_stats(x, B, eps=1e-5):
+    """x fp32, B samples of equal size -> [B][2] (mean, rstd) of GroupNorm(1, C)."""
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n = x.numel() // B
+    stats = torch.empty(B, 2, dtype=torch.float32, device=x.device)
+    with PROFILER.span("gn_stats", bytes=4.0 * x.numel()):
+        _lib.check(lib.avc_gn_stats(x.data_ptr(), stats.data_ptr(), B, n, eps, _stream()), "avc_gn_stats")
+    return stats
+
+
+def gn_pool_residual(x, stats, gamma, precision, want_f32=True, want_op=True):
+    """x [B][L][C] fp32 -> (x1 fp32, x1 operand format), x1 = x + pool3(GN(x)) - GN(x)."""
+    lib = _lib.load()
+    _require_cuda(x)
+    B, L, C = x.shape
+    out_f32 = torch.empty_like(x) if want_f32 else None
+    out_op = alloc_act(B, L, C, precision, x.device) if want_op else None
+    with PROFILER.span("gn_pool", bytes=4.0 * x.numel() * 2):
+        _lib.check(lib.avc_gn_pool_residual(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), _ptr(out_f32),
+                                            _ptr(out_op), _dt(precision), 1, B, L, C, _stream()),
+                   "avc_gn_pool_residual")
+    return out_f32, out_op
+
+
+def gn_apply(x, stats, gamma, beta, precision):
+    lib = _lib.load()
+    _require_cuda(x)
+    B, L, C = x.shape
+    out = alloc_act(B, L, C, precision, x.device)
+    with PROFILER.span("gn_apply", bytes=4.0 * x.numel() * 2):
+        _lib.check(lib.avc_gn_apply(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+                                    _dt(precision), 1, B, L, C, _stream()), "avc_gn_apply")
+    return out
+
+
+def patchify(a, stats, gamma, beta, p, precision):
+    """a [B][S][S] fp32 channels-last -> tokens [B][(S/p)^2][p*p] operand format (after GroupNorm if stats given)."""
+    lib = _lib.load()
+    _require_cuda(a)
+    B, S, S2 = a.shape
+    assert S == S2 and a.is_contiguous() and a.dtype == torch.float32
+    out = alloc_act(B, (S // p) ** 2, p * p, precision, a.device)
+    with PROFILER.span("patchify", bytes=4.0 * a.numel() * 2):
+        _lib.check(lib.avc_patchify(a.data_ptr(), _ptr(stats), _ptr(gamma), _ptr(beta), out.data_ptr(), _dt(precision),
+                                    1, B, S, p, _stream()), "avc_patchify")
+    return out
+
+
+def ln_transpose(x, gamma, beta, ln_axis, precision, want_op=True, want_f32=False):
+    """x [B][R][C] fp32 -> (out_op [B][C][R8] operand format, out_f32 [B][C][R8] raw), R8 = R rounded up to 8
+    (pad columns are zero).  ln_axis 0 none / 1 per row over C / 2 per column over R."""
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, R, C = x.shape
+    r8 = (R + 7) // 8 * 8
+    out_op = alloc_act(B, C, r8, precision, x.device) if want_op else None
+    out_f32 = torch.empty(B, C, r8, dtype=torch.float32, device=x.device) if want_f32 else None
+    scratch = torch.empty(2 * B * max(R, C), dtype=torch.float32, device=x.device) if ln_axis else None
+    with PROFILER.span("ln_transpose", bytes=4.0 * x.numel() * 2):
+        _lib.check(lib.avc_ln_transpose(x.data_ptr(), _ptr(gamma), _ptr(beta), ln_axis, _ptr(out_op), _dt(precision), 1,
+                                        _ptr(out_f32), _ptr(scratch), B, R, C, _stream()), "avc_ln_transpose")
+    return out_op, out_f32
+
+
+def meta_decoder_input(codes, c_trg, T, freq, precision):
+    """codes [B][T/freq][2H] fp32, c_trg [B][E] -> [B][2H+E][T] operand format (channels = time)."""
+    lib = _lib.load()
+    _require_cuda(codes, c_trg)
+    B, _, H2 = codes.shape
+    E = c_trg.shape[1]
+    out = alloc_act(B, H2 + E, T, precision, codes.device)
+    with PROFILER.span("concat", bytes=float(out.numel() * out.element_size())):
+        _lib.check(lib.avc_meta_decoder_input(codes.data_ptr(), c_trg.data_ptr(), out.data_ptr(), _dt(precision), 1, B,
+                                              T, freq, H2, E, _stream()), "avc_meta_decoder_input")
+    return out
+
+
+def gather_codes(out, H, freq):
+    """out [B][T][2H] fp32 -> codes [B][T/freq][2H]: [out[jF+F-1, :H] || out[jF, H:]]."""
+    lib = _lib.load()
+    _require_cuda(out)
+    B, T, _ = out.shape
+    codes = torch.empty(B, T // freq, 2 * H, dtype=torch.float32, device=out.device)
+    _lib.check(lib.avc_gather_codes(out.data_ptr(), codes.data_ptr(), B, T, H, freq, _stream()), "avc_gather_codes")
+    return codes

@@ -38,6 +38,7 @@ extern "C" {
 #define AVC_ACT_RELU 1
 #define AVC_ACT_TANH 2
 #define AVC_ACT_LRELU 3 /* slope 0.2, melgan/modules.py:75,100,120 */
+#define AVC_ACT_GELU 4  /* exact erf GELU, nn.GELU() default, factory/MLPMixer.py:19 */
 
 int avc_version(void);
 const char* avc_last_error(void);
@@ -94,8 +95,9 @@ typedef struct avc_gemm_desc {
   long long out_raw_ld;
   float* out2;               /* act(v) as exact fp32, rows b*(r*T)+time, ld out2_ld (may be NULL) */
   long long out2_ld;
-  const float* residual;     /* optional fp32, rows b*(r*T)+time, ld res_ld, added BEFORE the activation */
+  const float* residual;     /* optional fp32, rows b*(r*T)+time, ld res_ld, added before the activation ... */
   long long res_ld;
+  int res_after_act;         /* ... or after it when non-zero (x + relu(bn(conv(..))), factory/MetaPool.py:68,75) */
   int block_n;               /* 64 / 128 / 256; 0 = choose */
 } avc_gemm_desc;
 
@@ -168,6 +170,49 @@ int avc_transpose_pad(const float* in, void* out, int B, int C, int L, int pad, 
  */
 int avc_conv_to_mono_tanh(const float* x, const float* w, float bias, float* out, int B, int L, int C, int K,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MetaPool / MetaConv glue (factory/MetaPool.py, factory/MetaConv.py, factory/MLPMixer.py).  All inputs are fp32
+ * channels-last; `out_dtype` selects the operand format of the output (0 fp32, 1 bf16, 2 split bf16).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* GroupNorm(1, C) statistics (factory/Norm.py:53-60): stats[b] = {mean, 1/sqrt(biased var + eps)} over the n
+ * contiguous fp32 elements of sample b. */
+int avc_gn_stats(const float* x, float* stats, int B, long long n, float eps, void* stream);
+
+/* MetaPool token mixer + residual (factory/MetaPool.py:7-15,68):
+ *   y = x + (AvgPool1d(3,1,1,count_include_pad=False)(GN(x)) - GN(x)) = x + rstd_b * gamma_c * (pool_t(x) - x)
+ * x [B][L][C] fp32 -> out_f32 [B][L][C] and/or out_op (operand format). */
+int avc_gn_pool_residual(const float* x, const float* stats, const float* gamma, float* out_f32, void* out_op,
+                         int out_dtype, int out_round_tf32, int B, int L, int C, void* stream);
+
+/* GroupNorm apply: out = (x - mean_b) * rstd_b * gamma_c + beta_c -> operand format (MetaConv token mixer input,
+ * factory/MetaConv.py:66). */
+int avc_gn_apply(const float* x, const float* stats, const float* gamma, const float* beta, void* out_op,
+                 int out_dtype, int out_round_tf32, int B, int L, int C, void* stream);
+
+/* einops "b c (h p1) (w p2) -> b (h w) (p1 p2 c)" (factory/MLPMixer.py:76-78) of the S x S image whose rows are the
+ * CHANNELS and whose columns are the LENGTH axis of a [B][L=S][C=S] channels-last tensor, optionally after
+ * GroupNorm(1, S) (stats/gamma/beta may be NULL): tokens [B][(S/p)^2][p*p] in operand format. */
+int avc_patchify(const float* a, const float* stats, const float* gamma, const float* beta, void* out_op, int out_dtype,
+                 int out_round_tf32, int B, int S, int p, void* stream);
+
+/* Transpose with optional LayerNorm (factory/MLPMixer.py:27-33): x [B][R][C] fp32 -> out_op [B][C][R] (operand
+ * format) and/or out_f32 [B][C][R] (the un-normalised values).  ln_axis: 0 none, 1 normalise every ROW over its C
+ * entries (gamma/beta indexed by column), 2 normalise every COLUMN over its R entries (gamma/beta indexed by row);
+ * biased variance, eps 1e-5.  `scratch` holds 2*B*max(R,C) floats. */
+int avc_ln_transpose(const float* x, const float* gamma, const float* beta, int ln_axis, void* out_op, int out_dtype,
+                     int out_round_tf32, float* out_f32, float* scratch, int B, int R, int C, void* stream);
+
+/* Meta decoder input (factory/MetaPool.py:262-271 feeding Decoder.forward:160-162, which reads the (B, T, 2H+E)
+ * tensor as channels = T, length = 2H+E): out[b][f][t] = f < 2H ? codes[b][t / freq][f] : c_trg[b][f - 2H],
+ * channels-last [B][2H+E][T] in operand format.  T multiple of 4. */
+int avc_meta_decoder_input(const float* codes, const float* c_trg, void* out_op, int out_dtype, int out_round_tf32,
+                           int B, int T, int freq, int H2, int E, void* stream);
+
+/* Content-code down-sampling of the Meta encoders (factory/MetaPool.py:122-133):
+ * codes[b][j] = [ out[b][j*freq + freq-1][0:H] || out[b][j*freq][H:2H] ],  out [B][T][2H] fp32. */
+int avc_gather_codes(const float* out, float* codes, int B, int T, int H, int freq, void* stream);
 
 #ifdef __cplusplus
 }

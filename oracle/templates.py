@@ -94,3 +94,65 @@ def melgan_template(input_size=80, ngf=32, n_residual_layers=3):
         mult //= 2
     _wn(sd, f"model.{idx + 2}", (1, ngf, 7), 1)
     return sd
+
+
+def _mixer(sd, prefix, image, patch, out_dim):
+    """factory/MLPMixer.py:58-92 with channels=1, dim=image, depth=1."""
+    np_ = (image // patch) ** 2
+    dim = image
+    sd[f"{prefix}.1.weight"] = _z(dim, patch * patch)
+    sd[f"{prefix}.1.bias"] = _z(dim)
+    sd[f"{prefix}.2.0.fn.0.weight"] = _z(4 * np_, np_, 1)
+    sd[f"{prefix}.2.0.fn.0.bias"] = _z(4 * np_)
+    sd[f"{prefix}.2.0.fn.3.weight"] = _z(np_, 4 * np_, 1)
+    sd[f"{prefix}.2.0.fn.3.bias"] = _z(np_)
+    sd[f"{prefix}.2.0.norm.weight"] = _z(dim)
+    sd[f"{prefix}.2.0.norm.bias"] = _z(dim)
+    sd[f"{prefix}.2.1.fn.0.weight"] = _z(4 * dim, dim)
+    sd[f"{prefix}.2.1.fn.0.bias"] = _z(4 * dim)
+    sd[f"{prefix}.2.1.fn.3.weight"] = _z(dim, 4 * dim)
+    sd[f"{prefix}.2.1.fn.3.bias"] = _z(dim)
+    sd[f"{prefix}.2.1.norm.weight"] = _z(dim)
+    sd[f"{prefix}.2.1.norm.bias"] = _z(dim)
+    sd[f"{prefix}.3.weight"] = _z(out_dim, np_, 5)
+    sd[f"{prefix}.3.bias"] = _z(out_dim)
+
+
+def _conv_bn_seq(sd, prefix, c_out, c_in):
+    sd[f"{prefix}.0.conv.weight"] = _z(c_out, c_in, 5)
+    sd[f"{prefix}.0.conv.bias"] = _z(c_out)
+    _bn(sd, f"{prefix}.1", c_out)
+
+
+def _meta_block(sd, prefix, kind, dim, crop, out_neck=88, patch=8):
+    """factory/MetaPool.py:18-64 / factory/MetaConv.py:8-63."""
+    sd[f"{prefix}.norm1.weight"] = _z(dim)
+    sd[f"{prefix}.norm1.bias"] = _z(dim)
+    if kind == "conv":
+        _conv_bn_seq(sd, f"{prefix}.token_mixer", 512, 512)
+    sd[f"{prefix}.norm2.weight"] = _z(crop)
+    sd[f"{prefix}.norm2.bias"] = _z(crop)
+    _conv_bn_seq(sd, f"{prefix}.conv_1", crop, 512)
+    _mixer(sd, f"{prefix}.mlp", crop, patch, out_neck)
+    _conv_bn_seq(sd, f"{prefix}.conv_2", 512, out_neck)
+
+
+def meta_template(kind, dim_neck, dim, dim_pre, freq):
+    """MetaPool / MetaConv (factory/MetaPool.py:249-254): kind = "pool" | "conv"."""
+    sd = {}
+    sd["encoder.embding.proj.weight"] = _z(512, 336, 5)
+    sd["encoder.embding.proj.bias"] = _z(512)
+    for i in range(3):
+        _meta_block(sd, f"encoder.metablock.{i}", kind, dim_pre, 176)
+    _conv_bn_seq(sd, "encoder.output_conv", 176, 512)
+    _mixer(sd, "encoder.mlp", 176, 16, 2 * dim_neck)
+    sd["decoder.embding.proj.weight"] = _z(512, 176, 5)
+    sd["decoder.embding.proj.bias"] = _z(512)
+    _meta_block(sd, "decoder.metablock.0", kind, dim_pre, 344)
+    _conv_bn_seq(sd, "decoder.output_conv_1", 344, 512)
+    _mixer(sd, "decoder.mlp", 344, 8, 88)
+    _conv_bn_seq(sd, "decoder.output_conv_2", 176, 344)
+    sd["decoder.linear_projection.linear_layer.weight"] = _z(80, 88)
+    sd["decoder.linear_projection.linear_layer.bias"] = _z(80)
+    _postnet(sd)
+    return sd

@@ -55,11 +55,12 @@ import torch.nn.functional as F  # noqa: E402
 
 from autoformer_b200 import ops, packing  # noqa: E402
 
-_ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(v, 0.2)}
+_ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(v, 0.2),
+        4: lambda v: 0.5 * v * (1.0 + torch.erf(v / 2 ** 0.5))}
 
 
 def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                       out_raw=None, phases=1):
+                       out_raw=None, phases=1, res_after=False):
     meta = self.meta
     prec = self.precision
     if not isinstance(srcs, (list, tuple)):
@@ -77,12 +78,15 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
     cs = n // phases
     tl = T * phases
     v = v.reshape(B, tl, cs)
-    if residual is not None:
-        v = v + residual.reshape(B, tl, -1)[..., :cs].double()
+    res = residual.reshape(B, tl, -1)[..., :cs].double() if residual is not None else 0.0
+    if not res_after:
+        v = v + res
     ac = packing.act_channels(cs, prec)
     if out_raw is not None:
         out_raw.view(B, tl, -1)[..., :ac] = packing.to_act(v.float(), prec)
     a = _ACT[self.act](v)
+    if res_after:
+        a = a + res
     if out is not None:
         assert out.shape[1] >= out_row0 + tl + reflect and out_row0 >= reflect
         full = a
@@ -172,7 +176,73 @@ def _emu_conv_to_mono_tanh(x, w, bias):
     return torch.tanh(y).squeeze(1).float()
 
 
+def _emu_gn_stats(x, B, eps=1e-5):
+    v = x.double().reshape(B, -1)
+    mean = v.mean(dim=1)
+    var = v.var(dim=1, unbiased=False)
+    return torch.stack([mean, 1.0 / torch.sqrt(var + eps)], dim=1).float()
+
+
+def _emu_gn_pool_residual(x, stats, gamma, precision, want_f32=True, want_op=True):
+    xd = x.double()
+    pool = F.avg_pool1d(xd.transpose(1, 2), 3, stride=1, padding=1, count_include_pad=False).transpose(1, 2)
+    y = xd + stats[:, 1].double().view(-1, 1, 1) * gamma.double().view(1, 1, -1) * (pool - xd)
+    return (y.float() if want_f32 else None), (packing.to_act(y.float(), precision) if want_op else None)
+
+
+def _emu_gn_apply(x, stats, gamma, beta, precision):
+    y = (x.double() - stats[:, 0].double().view(-1, 1, 1)) * stats[:, 1].double().view(-1, 1, 1) \
+        * gamma.double().view(1, 1, -1) + beta.double().view(1, 1, -1)
+    return packing.to_act(y.float(), precision)
+
+
+def _emu_patchify(a, stats, gamma, beta, p, precision):
+    B, S, _ = a.shape
+    img = a.double().transpose(1, 2)                       # [B][h = channel][w = length]
+    if stats is not None:
+        img = (img - stats[:, 0].double().view(-1, 1, 1)) * stats[:, 1].double().view(-1, 1, 1) \
+            * gamma.double().view(1, -1, 1) + beta.double().view(1, -1, 1)
+    n = S // p
+    tok = img.reshape(B, n, p, n, p).permute(0, 1, 3, 2, 4).reshape(B, n * n, p * p)
+    return packing.to_act(tok.float(), precision)
+
+
+def _emu_ln_transpose(x, gamma, beta, ln_axis, precision, want_op=True, want_f32=False):
+    B, R, C = x.shape
+    xd = x.double()
+    y = xd
+    if ln_axis == 1:
+        y = (xd - xd.mean(-1, keepdim=True)) / torch.sqrt(xd.var(-1, unbiased=False, keepdim=True) + 1e-5) \
+            * gamma.double() + beta.double()
+    elif ln_axis == 2:
+        y = (xd - xd.mean(1, keepdim=True)) / torch.sqrt(xd.var(1, unbiased=False, keepdim=True) + 1e-5) \
+            * gamma.double().view(1, -1, 1) + beta.double().view(1, -1, 1)
+    r8 = (R + 7) // 8 * 8
+    yt = torch.zeros(B, C, r8, dtype=torch.float64)
+    yt[:, :, :R] = y.transpose(1, 2)
+    xt = torch.zeros(B, C, r8, dtype=torch.float64)
+    xt[:, :, :R] = xd.transpose(1, 2)
+    return (packing.to_act(yt.float(), precision) if want_op else None), (xt.float() if want_f32 else None)
+
+
+def _emu_meta_decoder_input(codes, c_trg, T, freq, precision):
+    up = codes.repeat_interleave(freq, dim=1)                                       # [B][T][2H]
+    full = torch.cat((up, c_trg.unsqueeze(1).expand(-1, T, -1)), dim=-1)            # [B][T][2H+E]
+    return packing.to_act(full.transpose(1, 2).contiguous(), precision)
+
+
+def _emu_gather_codes(out, H, freq):
+    return torch.cat((out[:, freq - 1::freq, :H], out[:, ::freq, H:]), dim=-1).contiguous()
+
+
 def install_cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops, "gn_stats", _emu_gn_stats)
+    monkeypatch.setattr(ops, "gn_pool_residual", _emu_gn_pool_residual)
+    monkeypatch.setattr(ops, "gn_apply", _emu_gn_apply)
+    monkeypatch.setattr(ops, "patchify", _emu_patchify)
+    monkeypatch.setattr(ops, "ln_transpose", _emu_ln_transpose)
+    monkeypatch.setattr(ops, "meta_decoder_input", _emu_meta_decoder_input)
+    monkeypatch.setattr(ops, "gather_codes", _emu_gather_codes)
     monkeypatch.setattr(ops, "_require_cuda", lambda *a: None)
     monkeypatch.setattr(ops.ConvGemm, "__call__", _emu_convgemm_call)
     monkeypatch.setattr(ops, "lstm_seq", _emu_lstm_seq)

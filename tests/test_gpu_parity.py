@@ -303,3 +303,82 @@ def test_full_pipeline_embed_convert_vocode():
     assert rel_l2(eo, e_org) < 1e-4 and rel_l2(et, e_trg) < 1e-4
     assert rel_l2(mel, ref_mel) < 1e-3
     assert rel_l2(wav, ref_wav) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ MetaPool / MetaConv
+def test_meta_glue_kernels_match_cpu_standins():
+    """GroupNorm stats/apply, pooling mixer, patchify, LayerNorm+transpose, decoder input, code gather."""
+    from autoformer_b200 import ops, packing
+    from tests import emulate as E
+    torch.manual_seed(3)
+    B, L, C = 3, 176, 512
+    x = torch.randn(B, L, C) * 1.7 + 0.3
+    g, be = torch.rand(C) + 0.5, torch.randn(C) * 0.2
+    st = ops.gn_stats(x.cuda(), B)
+    st_ref = E._emu_gn_stats(x, B)
+    assert rel_l2(st, st_ref) < 1e-5
+    f32, op = ops.gn_pool_residual(x.cuda(), st, g.cuda(), "fp32")
+    rf, ro = E._emu_gn_pool_residual(x, st_ref, g, "fp32")
+    assert rel_l2(f32, rf) < 1e-5 and rel_l2(packing.act_to_float(op, "fp32"), rf) < 2e-5
+    ap = ops.gn_apply(x.cuda(), st, g.cuda(), be.cuda(), "fp32")
+    assert rel_l2(packing.act_to_float(ap, "fp32"), packing.act_to_float(E._emu_gn_apply(x, st_ref, g, be, "fp32"), "fp32")) < 2e-5
+    for S, p in ((176, 8), (176, 16), (344, 8)):
+        a = torch.randn(2, S, S)
+        gs, bs = torch.rand(S) + 0.5, torch.randn(S) * 0.2
+        st2 = ops.gn_stats(a.cuda(), 2)
+        for stats in (None, st2):
+            tk = ops.patchify(a.cuda(), stats, gs.cuda() if stats is not None else None,
+                              bs.cuda() if stats is not None else None, p, "fp32")
+            ref = E._emu_patchify(a, stats.cpu() if stats is not None else None, gs, bs, p, "fp32")
+            assert tk.shape == ref.shape
+            assert rel_l2(packing.act_to_float(tk, "fp32"), packing.act_to_float(ref, "fp32")) < 2e-5
+    for R, C2, ax in ((484, 176, 1), (176, 488, 2), (1849, 344, 1), (344, 1856, 2), (344, 88, 0), (88, 176, 0)):
+        z = torch.randn(2, R, C2)
+        n = C2 if ax == 1 else R
+        gz, bz = torch.rand(n) + 0.5, torch.randn(n) * 0.2
+        o, f = ops.ln_transpose(z.cuda(), gz.cuda() if ax else None, bz.cuda() if ax else None, ax, "fp32", want_f32=True)
+        ro_, rf_ = E._emu_ln_transpose(z, gz, bz, ax, "fp32", want_f32=True)
+        assert o.shape == ro_.shape and f.shape == rf_.shape
+        assert rel_l2(packing.act_to_float(o, "fp32"), packing.act_to_float(ro_, "fp32")) < 3e-5, (R, C2, ax)
+        assert torch.equal(f.cpu(), rf_)
+    codes, spk = torch.randn(2, 8, 88), torch.randn(2, 256)
+    di = ops.meta_decoder_input(codes.cuda(), spk.cuda(), 176, 22, "fp32")
+    assert rel_l2(packing.act_to_float(di, "fp32"), packing.act_to_float(E._emu_meta_decoder_input(codes, spk, 176, 22, "fp32"), "fp32")) < 1e-6
+    out = torch.randn(2, 176, 88)
+    assert torch.equal(ops.gather_codes(out.cuda(), 44, 22).cpu(), E._emu_gather_codes(out, 44, 22))
+
+
+@pytest.mark.parametrize("kind,name", [("pool", "metapool_b1_t176"), ("conv", "metaconv_b1_t176")])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_meta_parity_and_golden(kind, name, precision, tol):
+    """BASELINE config 3 at test size: MetaPool / MetaConv (44,256,512,22), T=176, fp32-grade vs bf16 tolerance."""
+    from autoformer_b200.factory.MetaConv import MetaConv
+    from autoformer_b200.factory.MetaPool import MetaPool
+    from oracle.meta import meta_forward
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    args = tuple(int(a) for a in g["args"])
+    xs = int(g["xseed"])
+    sd = seeded_state_dict(templates.meta_template(kind, *args), int(g["wseed"]))
+    B = 2
+    x, c_org, c_trg = synthetic_mel(B, 176, xs + 1), synthetic_speaker(B, xs + 1, "org"), synthetic_speaker(B, xs + 1, "trg")
+    rt = {}
+    ref = meta_forward(sd, x, c_org, c_trg, args[0], args[3], kind, taps=rt)
+    m = (MetaPool if kind == "pool" else MetaConv)(*args)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    m.precision = precision
+    m.collect_taps = True
+    mel, post, codes = m(x.cuda(), c_org.cuda(), c_trg.cuda())
+    cl = lambda t: t.transpose(1, 2)
+    for i in range(3):
+        assert rel_l2(m.taps[f"encoder.metablock.{i}"], cl(rt[f"encoder.metablock.{i}"])) < tol, i
+    assert rel_l2(m.taps["decoder.metablock.0"], cl(rt["decoder.metablock.0"])) < tol
+    assert rel_l2(codes, ref[2]) < tol and rel_l2(mel, ref[0]) < tol and rel_l2(post, ref[1]) < tol
+    if precision == "fp32":
+        # the unmodified reference's own outputs (B=1 fixture)
+        x1, co1, ct1 = synthetic_mel(1, 176, xs), synthetic_speaker(1, xs, "org"), synthetic_speaker(1, xs, "trg")
+        mel1, post1, codes1 = m(x1.cuda(), co1.cuda(), ct1.cuda())
+        assert rel_l2(mel1, torch.from_numpy(g["mel"])) < 1e-3
+        assert rel_l2(post1, torch.from_numpy(g["mel_postnet"])) < 1e-3
+        assert rel_l2(codes1, torch.from_numpy(g["codes"])) < 1e-3
+        assert rel_l2(m(torch.from_numpy(g["mel"]).cuda(), co1.cuda(), None), torch.from_numpy(g["codes_of_mel"])) < 1e-3

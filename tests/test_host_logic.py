@@ -80,3 +80,33 @@ def test_melgan_host_logic(cpu_kernels, precision, tol, B, T):
     for k in ("up0", "stage0", "up1", "stage1", "up2", "stage2", "up3", "stage3"):
         assert rel_l2(g.taps[k], rt[k].transpose(1, 2)) < tol, k
     assert rel_l2(wav, ref) < tol
+
+
+@pytest.mark.parametrize("kind", ["pool", "conv"])
+def test_meta_host_logic(cpu_kernels, kind):
+    """MetaPool / MetaConv wiring (GroupNorm, pooling mixer, patchify, LN+transpose, padded token GEMMs, the
+    channels=time decoder) against the oracle, stage by stage."""
+    from autoformer_b200.factory.MetaConv import MetaConv
+    from autoformer_b200.factory.MetaPool import MetaPool
+    from oracle.meta import meta_forward
+    args = (44, 256, 512, 22)
+    sd = seeded_state_dict(templates.meta_template(kind, *args), 6)
+    x, c_org, c_trg = synthetic_mel(1, 176, 8), synthetic_speaker(1, 8, "org"), synthetic_speaker(1, 8, "trg")
+    rt = {}
+    ref = meta_forward(sd, x, c_org, c_trg, 44, 22, kind, taps=rt)
+    m = (MetaPool if kind == "pool" else MetaConv)(*args)
+    m.load_state_dict(sd)
+    m.eval()
+    m.collect_taps = True
+    mel, post, codes = m(x, c_org, c_trg)
+    cl = lambda t: t.transpose(1, 2)                       # oracle taps are channels-first
+    assert rel_l2(m.taps["enc_embed"], cl(rt["enc_embed"])) < 1e-4
+    for i in range(3):
+        assert rel_l2(m.taps[f"encoder.metablock.{i}"], cl(rt[f"encoder.metablock.{i}"])) < 1e-4, i
+    assert rel_l2(m.taps["enc_out"], rt["enc_out"]) < 1e-4
+    assert rel_l2(m.taps["decoder.metablock.0"], cl(rt["decoder.metablock.0"])) < 1e-4
+    assert rel_l2(m.taps["dec_conv2"], cl(rt["dec_conv2"])) < 1e-4
+    assert rel_l2(codes, ref[2]) < 1e-4 and rel_l2(mel, ref[0]) < 1e-4 and rel_l2(post, ref[1]) < 1e-4
+    assert rel_l2(m(x, c_org, None), ref[2]) < 1e-4
+    with pytest.raises(RuntimeError):
+        m(synthetic_mel(1, 128, 8), c_org, c_trg)          # the reference's hard-wired T = 176
