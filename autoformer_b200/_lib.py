@@ -54,6 +54,8 @@ class GemmDesc(ctypes.Structure):
         ("res_ld", ctypes.c_longlong),
         ("res_after_act", ctypes.c_int),
         ("block_n", ctypes.c_int),
+        ("cta_group", ctypes.c_int),
+        ("debug_clk", ctypes.c_void_p),
     ]
 
 

@@ -6,6 +6,7 @@
 // k-block, shifted in time by the tap offset; frames outside the utterance are zero-filled by TMA, which IS
 // the convolution's zero padding -- tiles never bleed across utterances.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "../../include/avc_b200.h"
 #include "avc_host.h"
@@ -43,16 +44,16 @@ struct alignas(64) GemmParams {
   const float* residual;
   long long res_ld;
   int res_after;
+  long long* debug_clk;  // optional: 4 clock64 stamps per CTA (entry, setup done, accumulator ready, epilogue done)
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case AVC_ACT_RELU: return fmaxf(v, 0.0f);
-    case AVC_ACT_TANH: return tanh_fast(v);
-    case AVC_ACT_LRELU: return v > 0.0f ? v : 0.2f * v;
-    case AVC_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
-    default: return v;
-  }
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if (ACT == AVC_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == AVC_ACT_TANH) return tanh_fast(v);
+  if (ACT == AVC_ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
+  if (ACT == AVC_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  return v;
 }
 
 // Store four consecutive channels [c, c+4) of one output row in the operand format `mode`.
@@ -75,18 +76,106 @@ __device__ __forceinline__ void store4(void* base, int mode, int round, long lon
   }
 }
 
-template <int BN, bool BF16>
+// Epilogue of one 128 x BN accumulator tile, run by the kEpiWarps epilogue warps of a CTA.
+// tcgen05.ld hands thread i the 32 columns of accumulator ROW i; storing that directly would write 8..16-byte
+// fragments of 32 different rows per instruction.  Each 32x32 chunk is therefore transposed through a padded
+// shared-memory tile: afterwards 8 consecutive lanes own 32 consecutive channels of ONE row, so every global
+// load/store of the epilogue (bias, residual, outputs) is a full 64..128-byte row segment.
+// Epilogue warp e (0..7) may touch TMEM lanes [32*(e%4), +32) (hardware rule: warp_id % 4); the two warps of a lane
+// quarter take alternate 32-column chunks.
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSmem& s, uint32_t tmem_base, int ew, int lane,
+                                              int b0, int t0, int n0) {
+  const int q = (ew + 2) & 3;            // == warp_id % 4
+  const int half = ew >> 2;              // which of the two warps of this quarter
+  float* stg = s.staging + ew * (32 * kStagingLd);
+  const int cl = (lane & 7) * 4;         // this lane's 4 columns inside a 32-column chunk
+  const int rsub = lane >> 3;            // this lane's row inside a group of 4 rows
+  const int tb = 1 << p.tb_log2;
+  const int t_out = p.T * p.phases;      // output frames per utterance
+  // the 8 rows this lane stores (one per 4-row group) are the same for every chunk: precompute their row indices
+  long long lrow[8], orow[8];
+  int time0[8];
+  unsigned valid = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = q * 32 + 4 * i + rsub;
+    const int b = b0 + (m >> p.tb_log2);
+    const int t = t0 + (m & (tb - 1));
+    if (b < p.B && t < p.T) valid |= 1u << i;
+    time0[i] = t * p.phases;
+    lrow[i] = (long long)b * t_out + time0[i];
+    orow[i] = (long long)b * p.out_rows_per_utt + p.out_row0 + time0[i];
+  }
+  const bool has_res = p.residual != nullptr, res_after = p.res_after != 0;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+  for (int c32 = half; c32 < BN / 32; c32 += kEpiWarps / 4) {
+    uint32_t v[32];
+    tmem_ld_32x32(lane_addr + c32 * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stg + lane * kStagingLd + 4 * j) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                      __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    const int n = n0 + c32 * 32 + cl;
+    if (n < p.N) {
+      const int phase = p.phases == 1 ? 0 : n / p.cs;
+      const int c = n - phase * p.cs;
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (valid & (1u << i)) {
+          const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
+          const long long lr = lrow[i] + phase;
+          float o[4] = {a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w};
+          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res) {
+            rv = __ldg(reinterpret_cast<const float4*>(p.residual + lr * p.res_ld + c));
+            if (!res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
+          }
+          if (p.out_raw) store4(p.out_raw, p.out_mode, p.out_round, lr, p.out_raw_ld, c, p.cs, o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
+          if (has_res && res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
+          if (p.out) {
+            const long long orw = orow[i] + phase;
+            store4(p.out, p.out_mode, p.out_round, orw, p.out_ld, c, p.cs, o);
+            if (p.out_reflect > 0) {   // reflected halo rows (ReflectionPad1d of the consumer)
+              const int time = time0[i] + phase;
+              if (time >= 1 && time <= p.out_reflect)
+                store4(p.out, p.out_mode, p.out_round, orw - 2LL * time, p.out_ld, c, p.cs, o);
+              if (time <= t_out - 2 && time >= t_out - 1 - p.out_reflect)
+                store4(p.out, p.out_mode, p.out_round, orw + 2LL * (t_out - 1 - time), p.out_ld, c, p.cs, o);
+            }
+          }
+          if (p.out2) *reinterpret_cast<float4*>(p.out2 + lr * p.out2_ld + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+    __syncwarp();   // the staging tile is overwritten by the next chunk
+  }
+}
+
+template <int BN, bool BF16, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = PipeCfg<BN>;
+  using C = PipeCfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
-  const PipeSmem s = carve_smem<BN>(smem_raw);
+  const PipeSmem s = carve_smem<BN, CTAS>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const long long clk_entry = p.debug_clk ? clock64() : 0;
+  // CTA pair: rank 0 (leader) issues the MMAs of the 256-row tile; each CTA owns one 128-row m-tile of it
+  const int cta_rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
 
-  // tile coordinates: n fastest so CTAs sharing an A tile are co-scheduled (A stays in L2)
-  const int tile = blockIdx.x;
+  // tile coordinates: n fastest so CTAs sharing an A tile are co-scheduled (A stays in L2); with CTA pairs the two
+  // CTAs of a cluster (consecutive blockIdx) take consecutive m-tiles of the same n-tile
+  const int tile = blockIdx.x / CTAS;
   const int n_tile = tile % p.n_tiles;
-  const int m_tile = tile / p.n_tiles;
+  const int m_tile = (tile / p.n_tiles) * CTAS + cta_rank;
   const int tt = m_tile % p.tiles_t;
   const int bt = m_tile / p.tiles_t;
   const int tb = 1 << p.tb_log2;
@@ -100,11 +189,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int i = 0; i < kMaxSrc; ++i)
       if (i == 0 || p.kb_end[i] > p.kb_end[i - 1]) prefetch_tmap(&p.tmap_a[i]);
   }
-  const uint32_t tmem_base = pipe_setup<BN>(s);
+  const uint32_t tmem_base = pipe_setup<BN, CTAS>(s);
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer
+      // ---------------- TMA producer (both CTAs of a pair: own A rows, own half of the B rows)
       RingState rs;
       int src = 0, base = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -117,101 +206,99 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int chunk = local - tap * p.chunks[src];
         mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
         uint8_t* a_dst = s.base + rs.stage * C::kStageBytes;
-        mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
-        tma_load_3d(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
-                    t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
-        tma_load_2d(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems, n0);
+        if (CTAS == 2) {
+          // all bytes of the pair are credited to the leader's full barrier
+          if (leader) mbar_arrive_expect_tx(&s.full[rs.stage], 2 * C::kStageBytes);
+          tma_load_3d_2sm(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
+                          t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
+          tma_load_2d_2sm(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems,
+                          n0 + cta_rank * (BN / 2));
+        } else {
+          mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
+          tma_load_3d(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
+                      t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
+          tma_load_2d(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems, n0);
+        }
         rs.advance<C::kStages>();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader CTA only)
       RingState rs;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&s.full[rs.stage], rs.phase);
         tc_fence_after();
-        issue_kblock<BN, BF16>(s, rs.stage, tmem_base, kb == 0);
-        umma_commit(&s.empty[rs.stage]);   // frees the smem slot once these MMAs have read it
+        issue_kblock<BN, BF16, CTAS>(s, rs.stage, tmem_base, kb == 0);
+        // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+        if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
         rs.advance<C::kStages>();
       }
-      umma_commit(s.tmem_full);
+      if (CTAS == 2) umma_commit_2sm(s.tmem_full, 0x3); else umma_commit(s.tmem_full);
     }
   } else {
-    // ---------------- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int bi = m >> p.tb_log2;
-    const int ti = m & (tb - 1);
-    const int b = b0 + bi;
-    const int t = t0 + ti;
-    const bool valid = (b < p.B) && (t < p.T);
-    const int t_out = p.T * p.phases;                       // output frames per utterance
-    const long long obase = (long long)b * p.out_rows_per_utt + p.out_row0;
-    const long long lbase = (long long)b * t_out;
+    // ---------------- epilogue warps
+    const long long clk_setup = p.debug_clk ? clock64() : 0;
     mbar_wait(s.tmem_full, 0);
     tc_fence_after();
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-    for (int c32 = 0; c32 < BN / 32; ++c32) {
-      uint32_t v[32];
-      tmem_ld_32x32(lane_addr + c32 * 32, v);
-      tmem_ld_wait();
-      const int nc = n0 + c32 * 32;
-      if (valid && nc < p.N) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int n = nc + 4 * j;
-          if (n < p.N) {
-            const int phase = p.phases == 1 ? 0 : n / p.cs;
-            const int c = n - phase * p.cs;
-            const int time = t * p.phases + phase;
-            const long long lrow = lbase + time;
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            float o[4];
-            o[0] = __uint_as_float(v[4 * j + 0]) + bv.x;
-            o[1] = __uint_as_float(v[4 * j + 1]) + bv.y;
-            o[2] = __uint_as_float(v[4 * j + 2]) + bv.z;
-            o[3] = __uint_as_float(v[4 * j + 3]) + bv.w;
-            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.residual) rv = __ldg(reinterpret_cast<const float4*>(p.residual + lrow * p.res_ld + c));
-            if (!p.res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
-            if (p.out_raw) store4(p.out_raw, p.out_mode, p.out_round, lrow, p.out_raw_ld, c, p.cs, o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = apply_act(o[i], p.act);
-            if (p.res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
-            if (p.out) {
-              const long long orow = obase + time;
-              store4(p.out, p.out_mode, p.out_round, orow, p.out_ld, c, p.cs, o);
-              if (p.out_reflect > 0) {   // reflected halo rows (ReflectionPad1d of the consumer)
-                if (time >= 1 && time <= p.out_reflect)
-                  store4(p.out, p.out_mode, p.out_round, orow - 2LL * time, p.out_ld, c, p.cs, o);
-                if (time <= t_out - 2 && time >= t_out - 1 - p.out_reflect)
-                  store4(p.out, p.out_mode, p.out_round, orow + 2LL * (t_out - 1 - time), p.out_ld, c, p.cs, o);
-              }
-            }
-            if (p.out2)
-              *reinterpret_cast<float4*>(p.out2 + lrow * p.out2_ld + c) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
+    const long long clk_acc = p.debug_clk ? clock64() : 0;
+    switch (p.act) {   // the activation is resolved once per tile, not once per element
+      case AVC_ACT_RELU: epilogue_tile<BN, AVC_ACT_RELU>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
+      case AVC_ACT_TANH: epilogue_tile<BN, AVC_ACT_TANH>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
+      case AVC_ACT_LRELU: epilogue_tile<BN, AVC_ACT_LRELU>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
+      case AVC_ACT_GELU: epilogue_tile<BN, AVC_ACT_GELU>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
+      default: epilogue_tile<BN, AVC_ACT_NONE>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
+    }
+    if (p.debug_clk && threadIdx.x == 64) {
+      long long* d = p.debug_clk + 4LL * blockIdx.x;
+      d[0] = clk_entry; d[1] = clk_setup; d[2] = clk_acc; d[3] = clock64();
     }
   }
-  pipe_teardown<BN>(tmem_base);
+  pipe_teardown<BN, CTAS>(tmem_base);
+}
+
+template <int BN, bool BF16, int CTAS>
+static int launch_impl(const GemmParams& p, long long m_tiles, cudaStream_t stream) {
+  auto kern = conv_gemm_kernel<BN, BF16, CTAS>;
+  using C = PipeCfg<BN, CTAS>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  const long long pairs_m = (m_tiles + CTAS - 1) / CTAS;          // a phantom second m-tile is masked in the epilogue
+  const long long grid = pairs_m * p.n_tiles * CTAS;
+  AVC_REQUIRE(grid > 0 && grid < (1LL << 31), "avc_conv_gemm: grid %lld", grid);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTAS > 1 ? 1 : 0;
+  AVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  count_launch();
+  return 0;
 }
 
 template <int BN, bool BF16>
-static int launch(const GemmParams& p, int grid, cudaStream_t stream) {
-  auto kern = conv_gemm_kernel<BN, BF16>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<BN>::kSmemBytes));
-    configured = true;
+static int launch(const GemmParams& p, long long m_tiles, int ctas, cudaStream_t stream) {
+  return ctas == 2 ? launch_impl<BN, BF16, 2>(p, m_tiles, stream) : launch_impl<BN, BF16, 1>(p, m_tiles, stream);
+}
+
+// CTA pairs by default; AVC_CTA_GROUP=1 forces the single-CTA kernel (A/B testing).
+static int default_cta_group() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("AVC_CTA_GROUP");
+    v = (e && e[0] == '1') ? 1 : 2;
   }
-  kern<<<grid, kNumThreads, PipeCfg<BN>::kSmemBytes, stream>>>(p);
-  AVC_CHECK_CUDA(cudaGetLastError());
-  count_launch();
-  return 0;
+  return v;
 }
 
 }  // namespace avc
@@ -281,7 +368,12 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   }
   p.num_kb = kb_total;
   AVC_REQUIRE(kb_total * kc == d->k_pad, "avc_conv_gemm: k_pad %d != %d k-blocks x %d", d->k_pad, kb_total, kc);
-  if (!encode_tmap_2d(&p.tmap_b, es, d->w_ptr, (uint64_t)d->k_pad, (uint64_t)d->n_pad, (uint64_t)d->k_pad * es, kc, bn))
+  const long long m_tiles = (long long)p.tiles_t * tiles_b;
+  int ctas = d->cta_group == 1 || d->cta_group == 2 ? d->cta_group : default_cta_group();
+  if (m_tiles < 2) ctas = 1;
+  // each CTA of a pair stages bn / 2 rows of the weight tile
+  if (!encode_tmap_2d(&p.tmap_b, es, d->w_ptr, (uint64_t)d->k_pad, (uint64_t)d->n_pad, (uint64_t)d->k_pad * es, kc,
+                      bn / ctas))
     return -3;
 
   p.bias = d->bias;
@@ -307,6 +399,7 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   p.residual = d->residual;
   p.res_ld = d->res_ld;
   p.res_after = d->res_after_act;
+  p.debug_clk = d->debug_clk;
   if (d->out) {
     AVC_REQUIRE(d->out_ld % 4 == 0 && d->out_ld >= min_ld &&
                     d->out_rows_per_utt >= d->out_row0 + t_out + d->out_reflect && d->out_row0 >= d->out_reflect,
@@ -318,12 +411,10 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   if (d->out2) AVC_REQUIRE(d->out2_ld % 4 == 0 && d->out2_ld >= p.cs, "avc_conv_gemm: out2_ld");
   if (d->residual) AVC_REQUIRE(d->res_ld % 4 == 0 && d->res_ld >= p.cs, "avc_conv_gemm: res_ld");
 
-  const long long grid = (long long)p.tiles_t * tiles_b * p.n_tiles;
-  AVC_REQUIRE(grid > 0 && grid < (1LL << 31), "avc_conv_gemm: grid %lld", grid);
   const bool bf16 = d->dtype == AVC_DTYPE_BF16;
   switch (bn) {
-    case 64: return bf16 ? launch<64, true>(p, (int)grid, stream) : launch<64, false>(p, (int)grid, stream);
-    case 128: return bf16 ? launch<128, true>(p, (int)grid, stream) : launch<128, false>(p, (int)grid, stream);
-    default: return bf16 ? launch<256, true>(p, (int)grid, stream) : launch<256, false>(p, (int)grid, stream);
+    case 64: return bf16 ? launch<64, true>(p, m_tiles, ctas, stream) : launch<64, false>(p, m_tiles, ctas, stream);
+    case 128: return bf16 ? launch<128, true>(p, m_tiles, ctas, stream) : launch<128, false>(p, m_tiles, ctas, stream);
+    default: return bf16 ? launch<256, true>(p, m_tiles, ctas, stream) : launch<256, false>(p, m_tiles, ctas, stream);
   }
 }

@@ -107,8 +107,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
       }
       __syncwarp();
     } else {
-      // ---------------- cell epilogue: thread owns utterance b, G hidden units of this tile
+      // ---------------- cell epilogue: thread owns utterance b; the two epilogue warps of a TMEM lane quarter
+      // (warp_id % 4) take alternate groups of 8 hidden units of this tile
       const int q = warp & 3;
+      const int half = (warp - 2) >> 2;
       const int b = b0 + q * 32 + lane;
       const bool valid = b < p.B;
       const int u0 = n_tile * G;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
       }
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int j = 0; j < G / 8; ++j) {
+      for (int j = half; j < G / 8; j += kEpiWarps / 4) {
         uint32_t acc[4][8];
         if (has_mma) {
 #pragma unroll

@@ -12,15 +12,22 @@ namespace avc {
 constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;                 // one swizzle row = one k-block of one row
 constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
-constexpr int kNumThreads = 192;               // 6 warps
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kEpiWarps = 8;                   // two epilogue warps per TMEM lane quarter (= per SM sub-partition)
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;   // TMA warp + MMA warp + epilogue warps
+constexpr int kSmemBudget = 186 * 1024;
+constexpr int kStagingLd = 36;                  // floats per staged row: 32 + 4 pad keeps 16-byte accesses conflict free
+constexpr int kStagingBytes = kEpiWarps * 32 * kStagingLd * 4;   // one 32 x 32 transpose tile per epilogue warp
 
-template <int BN>
+// CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (cta_group::2) owns a 256 x BN tile; each CTA stages its
+// own 128 A rows and BN/2 of the B rows, and the leader CTA's MMA thread issues for both.
+template <int BN, int CTAS = 1>
 struct PipeCfg {
-  static constexpr int kBTileBytes = BN * kRowBytes;
+  static constexpr int kBTileBytes = BN / CTAS * kRowBytes;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
-  static constexpr int kBarOffset = kStages * kStageBytes;
+  // per-epilogue-warp staging tile used to transpose 32 rows x 32 columns so that global stores are coalesced
+  static constexpr int kStagingOffset = kStages * kStageBytes;
+  static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
   // full[kStages], empty[kStages], tmem_full, then the TMEM base address word
   static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024 /* alignment slack */;
   static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
@@ -28,18 +35,20 @@ struct PipeCfg {
 
 struct PipeSmem {
   uint8_t* base;        // 1024-byte aligned
+  float* staging;
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tmem_full;
   uint32_t* tmem_ptr;
 };
 
-template <int BN>
+template <int BN, int CTAS = 1>
 __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
-  using C = PipeCfg<BN>;
+  using C = PipeCfg<BN, CTAS>;
   PipeSmem s;
   const uint32_t addr = smem_u32(raw);
   s.base = raw + ((1024u - (addr & 1023u)) & 1023u);
+  s.staging = reinterpret_cast<float*>(s.base + C::kStagingOffset);
   s.full = reinterpret_cast<uint64_t*>(s.base + C::kBarOffset);
   s.empty = s.full + C::kStages;
   s.tmem_full = s.empty + C::kStages;
@@ -48,9 +57,9 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
 }
 
 // Barrier init (thread 0) + TMEM allocation (warp 1) + CTA sync.  Returns the TMEM base address.
-template <int BN>
+template <int BN, int CTAS = 1>
 __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
-  using C = PipeCfg<BN>;
+  using C = PipeCfg<BN, CTAS>;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -61,22 +70,37 @@ __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(s.tmem_ptr, C::kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc_2sm(s.tmem_ptr, C::kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(s.tmem_ptr, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2)
+    cluster_sync_all();   // the peer's TMA credits bytes to the leader's barriers: inits must be visible cluster-wide
+  else
+    __syncthreads();
   tc_fence_after();
   return *reinterpret_cast<volatile uint32_t*>(s.tmem_ptr);
 }
 
-template <int BN>
+template <int BN, int CTAS = 1>
 __device__ __forceinline__ void pipe_teardown(uint32_t tmem_base) {
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2)
+    cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or multicast arrivals are pending
+  else
+    __syncthreads();
   if ((threadIdx.x >> 5) == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, PipeCfg<BN>::kTmemCols);
+    if (CTAS == 2)
+      tmem_dealloc_2sm(tmem_base, PipeCfg<BN, CTAS>::kTmemCols);
+    else
+      tmem_dealloc(tmem_base, PipeCfg<BN, CTAS>::kTmemCols);
   }
 }
 
@@ -92,11 +116,11 @@ struct RingState {
   }
 };
 
-// MMA issue for one k-block that has landed in `stage`: 4 x (128 x BN x 32 bytes of K).
-template <int BN, bool BF16>
+// MMA issue for one k-block that has landed in `stage`: 4 x ((128 * CTAS) x BN x 32 bytes of K).
+template <int BN, bool BF16, int CTAS = 1>
 __device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, uint32_t tmem_acc, bool first) {
-  using C = PipeCfg<BN>;
-  constexpr uint32_t idesc = umma_idesc(kBlockM, BN, !BF16);
+  using C = PipeCfg<BN, CTAS>;
+  constexpr uint32_t idesc = umma_idesc(kBlockM * CTAS, BN, !BF16);
   const uint32_t a_addr = smem_u32(s.base + stage * C::kStageBytes);
   const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
@@ -104,10 +128,17 @@ __device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, 
     const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
     const uint64_t bdesc = umma_desc_sw128(b_addr + k * 32);
     const uint32_t acc = (first && k == 0) ? 0u : 1u;
-    if (BF16)
-      umma_bf16(tmem_acc, adesc, bdesc, idesc, acc);
-    else
-      umma_tf32(tmem_acc, adesc, bdesc, idesc, acc);
+    if (CTAS == 2) {
+      if (BF16)
+        umma_bf16_2sm(tmem_acc, adesc, bdesc, idesc, acc);
+      else
+        umma_tf32_2sm(tmem_acc, adesc, bdesc, idesc, acc);
+    } else {
+      if (BF16)
+        umma_bf16(tmem_acc, adesc, bdesc, idesc, acc);
+      else
+        umma_tf32(tmem_acc, adesc, bdesc, idesc, acc);
+    }
   }
 }
 

@@ -177,6 +177,10 @@ class ConvGemm:
             d.res_ld = residual.stride(-2)
             d.res_after_act = 1 if res_after else 0
         d.block_n = meta["block_n"]
+        d.cta_group = getattr(self, "cta_group", 0)
+        dbg = getattr(self, "debug_clk", None)
+        if dbg is not None:
+            d.debug_clk = dbg.data_ptr()
         with PROFILER.span(self.tag, flops=2.0 * self.macs_per_row * B * T):
             _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
         return out if out is not None else (out2 if out2 is not None else out_raw)

@@ -99,6 +99,9 @@ typedef struct avc_gemm_desc {
   long long res_ld;
   int res_after_act;         /* ... or after it when non-zero (x + relu(bn(conv(..))), factory/MetaPool.py:68,75) */
   int block_n;               /* 64 / 128 / 256; 0 = choose */
+  int cta_group;             /* 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles), 1 = single CTA, 0 = default (2) */
+  long long* debug_clk;      /* optional device buffer, 4 x int64 per CTA: clock64 at entry / setup done / accumulator
+                                ready / epilogue done (profiling aid; NULL in production) */
 } avc_gemm_desc;
 
 int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
