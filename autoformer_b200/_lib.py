@@ -75,6 +75,7 @@ class LstmDesc(ctypes.Structure):
         ("gate_group", ctypes.c_int),
         ("persistent", ctypes.c_int),
         ("grid_barrier", ctypes.c_void_p),
+        ("debug_clk", ctypes.c_void_p),
     ]
 
 

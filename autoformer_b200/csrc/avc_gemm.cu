@@ -163,7 +163,7 @@ template <int BN, bool BF16, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = PipeCfg<BN, CTAS>;
   extern __shared__ uint8_t smem_raw[];
-  const PipeSmem s = carve_smem<BN, CTAS>(smem_raw);
+  const PipeSmem s = carve_smem<C>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const long long clk_entry = p.debug_clk ? clock64() : 0;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int i = 0; i < kMaxSrc; ++i)
       if (i == 0 || p.kb_end[i] > p.kb_end[i - 1]) prefetch_tmap(&p.tmap_a[i]);
   }
-  const uint32_t tmem_base = pipe_setup<BN, CTAS>(s);
+  const uint32_t tmem_base = pipe_setup<C>(s);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       d[0] = clk_entry; d[1] = clk_setup; d[2] = clk_acc; d[3] = clock64();
     }
   }
-  pipe_teardown<BN, CTAS>(tmem_base);
+  pipe_teardown<C>(tmem_base);
 }
 
 template <int BN, bool BF16, int CTAS>

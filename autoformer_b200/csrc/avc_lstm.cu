@@ -7,10 +7,19 @@
 // h_{t-1} is read by TMA straight out of the output sequence [B][T][H] (a 3-D box {128 B, 1 frame,
 // 128 utterances} at frame t-1), so there is no separate recurrent-state buffer.
 //
+// The step is bound by streaming the operands from L2 into shared memory (W_hh is re-read every frame), so the
+// kernel minimises bytes per MMA:
+//   * CTA pairs (cta_group::2): a pair owns 256 utterances x 4G gate columns and each CTA stages only half of the
+//     W_hh tile;
+//   * split-bf16 ("fp32") mode loads {h_hi, h_lo, W_hi, W_lo} of a 64-channel chunk ONCE per stage and issues the
+//     three products hi*hi, lo*hi, hi*lo from them (4 tiles instead of the 6 a K-concatenated GEMM would load);
+//   * the epilogue L2-prefetches the next frame's xproj rows so the cell update does not wait on HBM.
+//
 // Two launch modes share the kernel:
 //   per-step    t_end = t_begin + 1, one launch per frame (stream order is the time dependency)
 //   persistent  one cooperative launch for all frames; a grid-wide barrier separates frames
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "../../include/avc_b200.h"
 #include "avc_host.h"
@@ -19,17 +28,18 @@
 namespace avc {
 
 struct alignas(64) LstmParams {
-  CUtensorMap tmap_h;   // hseq as (H, T, B), box {kc, 1, 128}
-  CUtensorMap tmap_w;   // w_hh as (H, 4H), box {kc, BN}
+  CUtensorMap tmap_h[2];   // hseq as (H, T, B), box {kc, 1, 128}; [1] = the lo half in split mode
+  CUtensorMap tmap_w[2];   // w_hh as (H, 4H), box {kc, BN / CTAS}; [1] = the lo half in split mode
+  CUtensorMap tmap_x;      // xproj as (4H, T, B) fp32, box {32, 1, 128}
   const float* xproj;
   void* hseq;
   float* hseq_f32;
   float* h_last;
   float* c_state;
   unsigned int* grid_barrier;
+  long long* debug_clk;   // optional: 6 clock64 stamps per (frame, CTA)
   int B, T, H;
   int num_kb, kc_elems;
-  int a_wrap;           // A channel coordinate = (kb * kc) % a_wrap  (split bf16: [h_hi|h_lo] then h_hi again)
   int n_tiles;
   int t_begin, t_end;
 };
@@ -54,56 +64,141 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target
   __syncthreads();
 }
 
-// MODE: 0 = tf32, 1 = bf16, 2 = split bf16 (three bf16 products per fp32 product)
-template <int BN, int MODE>
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// MODE: 0 = tf32, 1 = bf16, 2 = split bf16 (three bf16 products per fp32 product, operands staged once)
+template <int BN, int MODE, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_constant__ LstmParams p) {
-  using C = PipeCfg<BN>;
+  constexpr int PARTS = MODE == 2 ? 2 : 1;
+  constexpr int kXSlabs = BN / 32;                         // xproj tile = BN/32 swizzled slabs of 128 rows x 128 B
+  constexpr int kXBytes = kXSlabs * kATileBytes;
+  using C = PipeCfg<BN, CTAS, PARTS, false, kXBytes>;
   constexpr int G = BN / 4;
   constexpr bool BF16 = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
-  const PipeSmem s = carve_smem<BN>(smem_raw);
+  const PipeSmem s = carve_smem<C>(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_tile = blockIdx.x / p.n_tiles;
+  const int cta_rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CTAS;                       // one (pair of) CTA(s) per (m, n) tile
+  const int n_tile = unit % p.n_tiles;
+  const int m_tile = (unit / p.n_tiles) * CTAS + cta_rank;
   const int b0 = m_tile * kBlockM;
   const int n0 = n_tile * BN;
+  const int nb0 = n0 + cta_rank * (BN / CTAS);              // first W_hh row staged by this CTA
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&p.tmap_h);
-    prefetch_tmap(&p.tmap_w);
+    prefetch_tmap(&p.tmap_h[0]);
+    prefetch_tmap(&p.tmap_w[0]);
+    prefetch_tmap(&p.tmap_x);
+    if (PARTS == 2) {
+      prefetch_tmap(&p.tmap_h[1]);
+      prefetch_tmap(&p.tmap_w[1]);
+    }
   }
-  const uint32_t tmem_base = pipe_setup<BN>(s);
+  const uint32_t tmem_base = pipe_setup<C>(s);
 
   RingState rs;              // producer and MMA issuer each keep their own copy (same sequence)
   uint32_t acc_phase = 0;    // epilogue: parity of tmem_full
   unsigned int sync_count = 0;
+  int pre_issued = 0;        // producer: stages of the current frame whose W tiles are already in flight
+  // cell warps: the running cell state lives in registers across frames; the xproj tile of each frame is fetched by
+  // the producer thread with TMA into 128-byte-swizzled shared memory (a thread-per-row read of a swizzled slab is
+  // bank-conflict free) while the MMAs of that frame run, so the cell warps issue no global loads.
+  constexpr int NJ = (G / 8 + kEpiWarps / 4 - 1) / (kEpiWarps / 4);   // 8-unit groups per cell thread
+  float4 cq[NJ][2];
+  uint32_t x_phase = 0;
 
   for (int t = p.t_begin; t < p.t_end; ++t) {
     const bool has_mma = t > 0;   // h_{-1} = 0: the first frame has no recurrent term
+    long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64();                       // frame start (after the grid barrier)
     if (warp == 0) {
-      if (lane == 0 && has_mma) {
-        fence_proxy_async_all();   // h_{t-1} was written with generic stores (other CTAs / previous launch)
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
-          uint8_t* a_dst = s.base + rs.stage * C::kStageBytes;
-          mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
-          tma_load_3d(a_dst, &p.tmap_h, &s.full[rs.stage], (kb * p.kc_elems) % p.a_wrap, t - 1, b0);
-          tma_load_2d(a_dst + kATileBytes, &p.tmap_w, &s.full[rs.stage], kb * p.kc_elems, n0);
-          rs.advance<C::kStages>();
+      if (lane == 0) {
+        // One stage = {h tile(s), W_hh tile(s)} of a 64/32-channel chunk.  The W_hh tiles do not depend on the previous
+        // frame, so the first `pre` stages of frame t+1 get their W loads (and the full barrier's byte count) BEFORE
+        // the grid barrier, while the cell epilogue of frame t is still running; only the h loads wait for it.
+        auto issue = [&](int kb, int frame, bool want_w, bool want_h, uint32_t stage) {
+          uint8_t* st = s.base + stage * C::kStageBytes;
+          uint8_t* wst = st + PARTS * kATileBytes;
+          const int kc0 = kb * p.kc_elems;
+          if (want_w) {
+            if (CTAS == 2) {
+              if (leader) mbar_arrive_expect_tx(&s.full[stage], 2 * C::kStageBytes);
+              tma_load_2d_2sm(wst, &p.tmap_w[0], &s.full[stage], kc0, nb0);
+              if (PARTS == 2) tma_load_2d_2sm(wst + C::kBTileBytes, &p.tmap_w[1], &s.full[stage], kc0, nb0);
+            } else {
+              mbar_arrive_expect_tx(&s.full[stage], C::kStageBytes);
+              tma_load_2d(wst, &p.tmap_w[0], &s.full[stage], kc0, nb0);
+              if (PARTS == 2) tma_load_2d(wst + C::kBTileBytes, &p.tmap_w[1], &s.full[stage], kc0, nb0);
+            }
+          }
+          if (want_h) {
+            if (CTAS == 2) {
+              tma_load_3d_2sm(st, &p.tmap_h[0], &s.full[stage], kc0, frame - 1, b0);
+              if (PARTS == 2) tma_load_3d_2sm(st + kATileBytes, &p.tmap_h[1], &s.full[stage], kc0, frame - 1, b0);
+            } else {
+              tma_load_3d(st, &p.tmap_h[0], &s.full[stage], kc0, frame - 1, b0);
+              if (PARTS == 2) tma_load_3d(st + kATileBytes, &p.tmap_h[1], &s.full[stage], kc0, frame - 1, b0);
+            }
+          }
+        };
+        auto issue_x = [&]() {     // this frame's xproj tile (independent of h): consumed by the cell warps
+          mbar_arrive_expect_tx(s.extra_bar, kXBytes);
+#pragma unroll
+          for (int cc = 0; cc < kXSlabs; ++cc)
+            tma_load_3d(s.extra + cc * kATileBytes, &p.tmap_x, s.extra_bar, n0 + cc * 32, t, b0);
+        };
+        if (!has_mma) issue_x();
+        if (has_mma) {
+          fence_proxy_async_all();   // h_{t-1} was written with generic stores (other CTAs / previous launch)
+          RingState hs = rs;         // stages whose W tiles were pre-issued: add the h tiles
+          for (int kb = 0; kb < pre_issued; ++kb) {
+            issue(kb, t, false, true, hs.stage);
+            hs.advance<C::kStages>();
+          }
+          for (int kb = 0; kb < pre_issued; ++kb) rs.advance<C::kStages>();
+          issue_x();                 // after the h tiles of the first stages: those are on the critical path
+          for (int kb = pre_issued; kb < p.num_kb; ++kb) {
+            mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
+            issue(kb, t, true, true, rs.stage);
+            rs.advance<C::kStages>();
+          }
+          pre_issued = 0;
+        }
+        if (t + 1 < p.t_end) {     // persistent mode: W tiles of the next frame's first stages
+          RingState ws = rs;
+          const int pre = p.num_kb < C::kStages ? p.num_kb : C::kStages;
+          for (int kb = 0; kb < pre; ++kb) {
+            mbar_wait(&s.empty[ws.stage], ws.phase ^ 1u);
+            issue(kb, t + 1, true, false, ws.stage);
+            ws.advance<C::kStages>();
+          }
+          pre_issued = pre;
         }
       }
       __syncwarp();
     } else if (warp == 1) {
-      if (lane == 0 && has_mma) {
+      if (lane == 0 && has_mma && leader) {
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&s.full[rs.stage], rs.phase);
+          if (dbg && kb == 0) dbg[1] = clock64();                          // first stage landed
           tc_fence_after();
-          issue_kblock<BN, BF16>(s, rs.stage, tmem_base, kb == 0);
-          umma_commit(&s.empty[rs.stage]);
+          const uint32_t a_hi = smem_u32(s.base + rs.stage * C::kStageBytes);
+          const uint32_t w_hi = a_hi + PARTS * kATileBytes;
+          issue_pair<BN, BF16, CTAS>(a_hi, w_hi, tmem_base, kb == 0);
+          if (PARTS == 2) {
+            issue_pair<BN, BF16, CTAS>(a_hi + kATileBytes, w_hi, tmem_base, false);            // h_lo * W_hi
+            issue_pair<BN, BF16, CTAS>(a_hi, w_hi + C::kBTileBytes, tmem_base, false);         // h_hi * W_lo
+          }
+          if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
           rs.advance<C::kStages>();
         }
-        umma_commit(s.tmem_full);
+        if (CTAS == 2) umma_commit_2sm(s.tmem_full, 0x3); else umma_commit(s.tmem_full);
+        if (dbg) dbg[2] = clock64();                                       // all MMAs issued
       }
       __syncwarp();
     } else {
@@ -115,16 +210,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
       const bool valid = b < p.B;
       const int u0 = n_tile * G;
       const long long row = (long long)b * p.T + t;
-      const float* xp = p.xproj + row * (4LL * p.H) + n0;
       float* cp = p.c_state + (long long)b * p.H + u0;
+      if (t == p.t_begin) {      // first frame of this launch
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          const int j = half + jj * (kEpiWarps / 4);
+          cq[jj][0] = cq[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && has_mma && j < G / 8) {      // per-step launches carry c through global memory
+            cq[jj][0] = *reinterpret_cast<const float4*>(cp + j * 8);
+            cq[jj][1] = *reinterpret_cast<const float4*>(cp + j * 8 + 4);
+          }
+        }
+      }
+      if (dbg && threadIdx.x == 64) dbg[3] = clock64();                    // xproj / c preloads issued
       if (has_mma) {
         mbar_wait(s.tmem_full, acc_phase);
         acc_phase ^= 1u;
         tc_fence_after();
       }
+      mbar_wait(s.extra_bar, x_phase);                                     // xproj tile of this frame has landed
+      x_phase ^= 1u;
+      if (dbg && threadIdx.x == 64) dbg[4] = clock64();                    // accumulator ready
+      const int xr = q * 32 + lane;                                        // this thread's row in the xproj tile
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int j = half; j < G / 8; j += kEpiWarps / 4) {
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        const int j = half + jj * (kEpiWarps / 4);
+        if (j >= G / 8) break;
         uint32_t acc[4][8];
         if (has_mma) {
 #pragma unroll
@@ -140,8 +252,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           float z[4][8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(xp + g * G + j * 8));
-            const float4 x1 = __ldg(reinterpret_cast<const float4*>(xp + g * G + j * 8 + 4));
+            // column g*G + j*8 of the tile: slab (col / 32), 16-byte chunk (col % 32) / 4, swizzled by row % 8
+            const int col = g * G + j * 8;
+            const uint8_t* slab = s.extra + (col >> 5) * kATileBytes + xr * 128;
+            const int ch = (col & 31) >> 2;
+            const float4 x0 = *reinterpret_cast<const float4*>(slab + ((ch ^ (xr & 7)) << 4));
+            const float4 x1 = *reinterpret_cast<const float4*>(slab + (((ch + 1) ^ (xr & 7)) << 4));
             z[g][0] = __uint_as_float(acc[g][0]) + x0.x;
             z[g][1] = __uint_as_float(acc[g][1]) + x0.y;
             z[g][2] = __uint_as_float(acc[g][2]) + x0.z;
@@ -151,16 +267,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
             z[g][6] = __uint_as_float(acc[g][6]) + x1.z;
             z[g][7] = __uint_as_float(acc[g][7]) + x1.w;
           }
-          float cprev[8];
-          if (has_mma) {
-            const float4 c0 = *reinterpret_cast<const float4*>(cp + j * 8);
-            const float4 c1 = *reinterpret_cast<const float4*>(cp + j * 8 + 4);
-            cprev[0] = c0.x; cprev[1] = c0.y; cprev[2] = c0.z; cprev[3] = c0.w;
-            cprev[4] = c1.x; cprev[5] = c1.y; cprev[6] = c1.z; cprev[7] = c1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cprev[e] = 0.0f;
-          }
+          const float4 c0 = cq[jj][0], c1 = cq[jj][1];
+          const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           float cn[8], hn[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -171,8 +279,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
             cn[e] = fg * cprev[e] + ig * gg;
             hn[e] = og * tanh_fast(cn[e]);
           }
-          *reinterpret_cast<float4*>(cp + j * 8) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-          *reinterpret_cast<float4*>(cp + j * 8 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          cq[jj][0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          cq[jj][1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          if (t + 1 == p.t_end) {       // a later launch (per-step mode) resumes from global memory
+            *reinterpret_cast<float4*>(cp + j * 8) = cq[jj][0];
+            *reinterpret_cast<float4*>(cp + j * 8 + 4) = cq[jj][1];
+          }
           const long long hoff = row * p.H + u0 + j * 8;
           if (MODE == 2) {
             float lo[8];
@@ -207,6 +319,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
         }
       }
       fence_proxy_async_all();   // order the h stores before later async-proxy (TMA) reads
+      if (dbg && threadIdx.x == 64) dbg[5] = clock64();                    // cell update done
     }
     if (t + 1 < p.t_end) {
       // the next frame's MMAs overwrite the accumulator and read h_t from every CTA: grid-wide barrier
@@ -216,42 +329,76 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
       tc_fence_after();
     }
   }
-  pipe_teardown<BN>(tmem_base);
+  pipe_teardown<C>(tmem_base);
 }
 
-template <int BN, int MODE>
-static int run(LstmParams p, const avc_lstm_desc* d, cudaStream_t stream) {
-  auto kern = lstm_step_kernel<BN, MODE>;
+template <int BN, int MODE, int CTAS>
+static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t stream) {
+  auto kern = lstm_step_kernel<BN, MODE, CTAS>;
+  using C = PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes>;
   static bool configured = false;
   if (!configured) {
-    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<BN>::kSmemBytes));
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
-  const int m_tiles = (d->B + kBlockM - 1) / kBlockM;
-  const int grid = m_tiles * p.n_tiles;
+  const int grid = (m_tiles + CTAS - 1) / CTAS * CTAS * p.n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CTAS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   if (d->persistent) {
     AVC_REQUIRE(d->grid_barrier != nullptr, "avc_lstm_seq: persistent mode needs grid_barrier scratch");
-    int per_sm = 0;
-    AVC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNumThreads, PipeCfg<BN>::kSmemBytes));
-    AVC_REQUIRE(per_sm * num_sms() >= grid, "avc_lstm_seq: persistent grid %d does not fit (%d x %d resident)", grid,
-                per_sm, num_sms());
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (d->persistent) {
+    int resident = 0;
+    if (CTAS > 1) {
+      int clusters = 0;
+      AVC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg));
+      resident = clusters * CTAS;
+    } else {
+      int per_sm = 0;
+      AVC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNumThreads, C::kSmemBytes));
+      resident = per_sm * num_sms();
+    }
+    AVC_REQUIRE(resident >= grid, "avc_lstm_seq: persistent grid %d does not fit (%d CTAs resident)", grid, resident);
     AVC_CHECK_CUDA(cudaMemsetAsync(d->grid_barrier, 0, sizeof(unsigned int), stream));
     p.t_begin = 0;
     p.t_end = d->T;
-    void* args[] = {&p};
-    AVC_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kNumThreads), args,
-                                               PipeCfg<BN>::kSmemBytes, stream));
+    AVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
   } else {
     for (int t = 0; t < d->T; ++t) {
       p.t_begin = t;
       p.t_end = t + 1;
-      kern<<<grid, kNumThreads, PipeCfg<BN>::kSmemBytes, stream>>>(p);
+      AVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     }
-    AVC_CHECK_CUDA(cudaGetLastError());
     count_launch(d->T);
   }
   return 0;
+}
+
+static int lstm_cta_group() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("AVC_LSTM_CTA_GROUP");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
 }
 
 }  // namespace avc
@@ -261,8 +408,7 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(d != nullptr, "avc_lstm_seq: null descriptor");
   AVC_REQUIRE(d->dtype >= AVC_DTYPE_TF32 && d->dtype <= AVC_DTYPE_BF16X3, "avc_lstm_seq: bad dtype %d", d->dtype);
-  AVC_REQUIRE(d->gate_group == 16 || d->gate_group == 32 || d->gate_group == 64, "avc_lstm_seq: gate_group %d",
-              d->gate_group);
+  AVC_REQUIRE(d->gate_group == 16 || d->gate_group == 32, "avc_lstm_seq: gate_group %d (16 or 32)", d->gate_group);
   AVC_REQUIRE(d->B > 0 && d->T > 0 && d->H > 0 && d->H % d->gate_group == 0, "avc_lstm_seq: bad shape B=%d T=%d H=%d",
               d->B, d->T, d->H);
   AVC_REQUIRE(d->xproj && d->w_hh && d->hseq && d->c_state, "avc_lstm_seq: missing buffer");
@@ -271,38 +417,49 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   AVC_REQUIRE(d->H % kc == 0, "avc_lstm_seq: H=%d must be a multiple of %d", d->H, kc);
   const int bn = 4 * d->gate_group;
   const bool split = d->dtype == AVC_DTYPE_BF16X3;
-  const uint64_t hc = split ? 2ull * d->H : (uint64_t)d->H;   // channels of the h sequence buffer
-  const uint64_t wk = split ? 3ull * d->H : (uint64_t)d->H;   // K extent of the packed recurrent weights
+  const uint64_t H = (uint64_t)d->H;
+  const uint64_t ld = split ? 2 * H : H;     // elements per row of hseq and of the packed W_hh ([hi | lo] when split)
+  const int m_tiles = (d->B + kBlockM - 1) / kBlockM;
+  const int ctas = (m_tiles >= 2 && lstm_cta_group() == 2) ? 2 : 1;
 
   LstmParams p;
   memset(&p, 0, sizeof(p));
-  if (!encode_tmap_3d(&p.tmap_h, es, d->hseq, hc, (uint64_t)d->T, (uint64_t)d->B, hc * es, (uint64_t)d->T * hc * es, kc,
-                      1, kBlockM))
+  for (int part = 0; part < (split ? 2 : 1); ++part) {
+    const char* hb = static_cast<const char*>(d->hseq) + (size_t)part * H * es;
+    const char* wb = static_cast<const char*>(d->w_hh) + (size_t)part * H * es;
+    if (!encode_tmap_3d(&p.tmap_h[part], es, hb, H, (uint64_t)d->T, (uint64_t)d->B, ld * es, (uint64_t)d->T * ld * es, kc,
+                        1, kBlockM))
+      return -3;
+    if (!encode_tmap_2d(&p.tmap_w[part], es, wb, H, 4 * H, ld * es, kc, bn / ctas)) return -3;
+  }
+  if (!encode_tmap_3d(&p.tmap_x, 4, d->xproj, 4 * H, (uint64_t)d->T, (uint64_t)d->B, 4 * H * 4,
+                      (uint64_t)d->T * 4 * H * 4, 32, 1, kBlockM))
     return -3;
-  if (!encode_tmap_2d(&p.tmap_w, es, d->w_hh, wk, (uint64_t)4 * d->H, wk * es, kc, bn)) return -3;
-  p.a_wrap = (int)hc;
   p.xproj = d->xproj;
   p.hseq = d->hseq;
   p.hseq_f32 = d->hseq_f32;
   p.h_last = d->h_last;
   p.c_state = d->c_state;
   p.grid_barrier = d->grid_barrier;
+  p.debug_clk = d->debug_clk;
   p.B = d->B;
   p.T = d->T;
   p.H = d->H;
   p.kc_elems = kc;
-  p.num_kb = (int)(wk / kc);
+  p.num_kb = d->H / kc;
   p.n_tiles = 4 * d->H / bn;
-#define AVC_LSTM_DISPATCH(BN_)                                  \
-  switch (d->dtype) {                                           \
-    case AVC_DTYPE_TF32: return run<BN_, 0>(p, d, stream);      \
-    case AVC_DTYPE_BF16: return run<BN_, 1>(p, d, stream);      \
-    default: return run<BN_, 2>(p, d, stream);                  \
+#define AVC_LSTM_DISPATCH2(BN_, MODE_) \
+  return ctas == 2 ? run<BN_, MODE_, 2>(p, d, m_tiles, stream) : run<BN_, MODE_, 1>(p, d, m_tiles, stream);
+#define AVC_LSTM_DISPATCH(BN_)                           \
+  switch (d->dtype) {                                    \
+    case AVC_DTYPE_TF32: AVC_LSTM_DISPATCH2(BN_, 0)      \
+    case AVC_DTYPE_BF16: AVC_LSTM_DISPATCH2(BN_, 1)      \
+    default: AVC_LSTM_DISPATCH2(BN_, 2)                  \
   }
   switch (bn) {
     case 64: AVC_LSTM_DISPATCH(64)
-    case 128: AVC_LSTM_DISPATCH(128)
-    default: AVC_LSTM_DISPATCH(256)
+    default: AVC_LSTM_DISPATCH(128)
   }
 #undef AVC_LSTM_DISPATCH
+#undef AVC_LSTM_DISPATCH2
 }

@@ -20,17 +20,27 @@ constexpr int kStagingBytes = kEpiWarps * 32 * kStagingLd * 4;   // one 32 x 32 
 
 // CTAS = 1: one CTA owns a 128 x BN tile.  CTAS = 2: a CTA pair (cta_group::2) owns a 256 x BN tile; each CTA stages its
 // own 128 A rows and BN/2 of the B rows, and the leader CTA's MMA thread issues for both.
-template <int BN, int CTAS = 1>
+// PARTS = 1: a stage holds one {A, B} operand pair.  PARTS = 2 (split-bf16 recurrence): a stage holds {A_hi, A_lo,
+// B_hi, B_lo} of one 64-channel chunk, from which the three products hi*hi, lo*hi, hi*lo are issued.
+// STAGING: reserve the epilogue's per-warp transpose tiles.
+// EXTRA: bytes of kernel-specific shared memory (1024-byte aligned) placed after the stages, with one extra mbarrier.
+template <int BN, int CTAS = 1, int PARTS = 1, bool STAGING = true, int EXTRA = 0>
 struct PipeCfg {
+  static constexpr int kCtas = CTAS;
+  static constexpr int kParts = PARTS;
   static constexpr int kBTileBytes = BN / CTAS * kRowBytes;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kStageBytes = PARTS * (kATileBytes + kBTileBytes);
+  static constexpr int kBudget = (STAGING ? kSmemBudget : kSmemBudget + kStagingBytes + 8 * 1024) - EXTRA;
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   // per-epilogue-warp staging tile used to transpose 32 rows x 32 columns so that global stores are coalesced
-  static constexpr int kStagingOffset = kStages * kStageBytes;
-  static constexpr int kBarOffset = kStagingOffset + kStagingBytes;
-  // full[kStages], empty[kStages], tmem_full, then the TMEM base address word
-  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024 /* alignment slack */;
+  static constexpr int kExtraOffset = kStages * kStageBytes;
+  static constexpr int kStagingOffset = kExtraOffset + EXTRA;
+  static constexpr int kBarOffset = kStagingOffset + (STAGING ? kStagingBytes : 0);
+  // full[kStages], empty[kStages], tmem_full, extra barrier, then the TMEM base address word
+  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 2) * 8 + 16 + 1024 /* alignment slack */;
   static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
 struct PipeSmem {
@@ -39,12 +49,13 @@ struct PipeSmem {
   uint64_t* full;
   uint64_t* empty;
   uint64_t* tmem_full;
+  uint64_t* extra_bar;
+  uint8_t* extra;
   uint32_t* tmem_ptr;
 };
 
-template <int BN, int CTAS = 1>
+template <class C>
 __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
-  using C = PipeCfg<BN, CTAS>;
   PipeSmem s;
   const uint32_t addr = smem_u32(raw);
   s.base = raw + ((1024u - (addr & 1023u)) & 1023u);
@@ -52,14 +63,15 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
   s.full = reinterpret_cast<uint64_t*>(s.base + C::kBarOffset);
   s.empty = s.full + C::kStages;
   s.tmem_full = s.empty + C::kStages;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.tmem_full + 1);
+  s.extra_bar = s.tmem_full + 1;
+  s.extra = s.base + C::kExtraOffset;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.extra_bar + 1);
   return s;
 }
 
-// Barrier init (thread 0) + TMEM allocation (warp 1) + CTA sync.  Returns the TMEM base address.
-template <int BN, int CTAS = 1>
+// Barrier init (thread 0) + TMEM allocation (warp 1) + CTA / cluster sync.  Returns the TMEM base address.
+template <class C>
 __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
-  using C = PipeCfg<BN, CTAS>;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -67,10 +79,11 @@ __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
       mbar_init(&s.empty[i], 1);
     }
     mbar_init(s.tmem_full, 1);
+    mbar_init(s.extra_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (CTAS == 2) {
+    if (C::kCtas == 2) {
       tmem_alloc_2sm(s.tmem_ptr, C::kTmemCols);
       tmem_relinquish_2sm();
     } else {
@@ -79,7 +92,7 @@ __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
     }
   }
   tc_fence_before();
-  if (CTAS == 2)
+  if (C::kCtas == 2)
     cluster_sync_all();   // the peer's TMA credits bytes to the leader's barriers: inits must be visible cluster-wide
   else
     __syncthreads();
@@ -87,20 +100,20 @@ __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
   return *reinterpret_cast<volatile uint32_t*>(s.tmem_ptr);
 }
 
-template <int BN, int CTAS = 1>
+template <class C>
 __device__ __forceinline__ void pipe_teardown(uint32_t tmem_base) {
   __syncwarp();
   tc_fence_before();
-  if (CTAS == 2)
+  if (C::kCtas == 2)
     cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or multicast arrivals are pending
   else
     __syncthreads();
   if ((threadIdx.x >> 5) == 1) {
     tc_fence_after();
-    if (CTAS == 2)
-      tmem_dealloc_2sm(tmem_base, PipeCfg<BN, CTAS>::kTmemCols);
+    if (C::kCtas == 2)
+      tmem_dealloc_2sm(tmem_base, C::kTmemCols);
     else
-      tmem_dealloc(tmem_base, PipeCfg<BN, CTAS>::kTmemCols);
+      tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -116,13 +129,10 @@ struct RingState {
   }
 };
 
-// MMA issue for one k-block that has landed in `stage`: 4 x ((128 * CTAS) x BN x 32 bytes of K).
-template <int BN, bool BF16, int CTAS = 1>
-__device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, uint32_t tmem_acc, bool first) {
-  using C = PipeCfg<BN, CTAS>;
+// Four MMAs (32 bytes of K each) over one 128-byte-wide operand pair: D (+)= A[128*CTAS x 128B] . B[BN x 128B]^T.
+template <int BN, bool BF16, int CTAS>
+__device__ __forceinline__ void issue_pair(uint32_t a_addr, uint32_t b_addr, uint32_t tmem_acc, bool first) {
   constexpr uint32_t idesc = umma_idesc(kBlockM * CTAS, BN, !BF16);
-  const uint32_t a_addr = smem_u32(s.base + stage * C::kStageBytes);
-  const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
@@ -140,6 +150,14 @@ __device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, 
         umma_tf32(tmem_acc, adesc, bdesc, idesc, acc);
     }
   }
+}
+
+// MMA issue for one k-block that has landed in `stage` of a PARTS = 1 pipeline.
+template <int BN, bool BF16, int CTAS = 1>
+__device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, uint32_t tmem_acc, bool first) {
+  using C = PipeCfg<BN, CTAS>;
+  const uint32_t a_addr = smem_u32(s.base + stage * C::kStageBytes);
+  issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, tmem_acc, first);
 }
 
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }

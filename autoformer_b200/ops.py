@@ -189,25 +189,28 @@ class ConvGemm:
 def choose_gate_group(B, H, persistent=False, n_sm=148):
     """Hidden units per accumulator tile (tile width 4G): fill the SMs without exceeding one wave when persistent."""
     m_tiles = (B + 127) // 128
-    for g in (64, 32, 16):
+    if m_tiles >= 2:
+        m_tiles = (m_tiles + 1) // 2 * 2          # CTA pairs: an odd tile count is rounded up with a masked tile
+    for g in (32, 16):
         if H % g:
             continue
         ctas = m_tiles * (H // g)
         if ctas >= 96 and (not persistent or ctas <= n_sm):
             return g
-    for g in (16, 32, 64):
+    for g in (16, 32):
         if H % g == 0 and (not persistent or m_tiles * (H // g) <= n_sm):
             return g
     raise RuntimeError(f"no gate group fits B={B} H={H} persistent={persistent}")
 
 
-def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False):
+def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False,
+             debug_clk=None):
     """Run the recurrence of one uni-directional layer.  xproj [B*T][4H] fp32 (packed gate order, bias included)."""
     lib = _lib.load()
     _require_cuda(xproj, w_hh)
     dev = xproj.device
     assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
-    wk = 3 * H if precision == "fp32" else H
+    wk = 2 * H if precision == "fp32" else H
     assert w_hh.dtype == TORCH_DTYPE[precision] and w_hh.shape == (4 * H, wk) and w_hh.is_contiguous()
     if hseq is None:
         hseq = alloc_act(B, T, H, precision, dev)
@@ -233,6 +236,8 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
     if persistent:
         bar = torch.zeros(4, dtype=torch.int32, device=dev)
         d.grid_barrier = bar.data_ptr()
+    if debug_clk is not None:
+        d.debug_clk = debug_clk.data_ptr()
     with PROFILER.span("lstm_step", flops=2.0 * 4 * H * H * B * T, launches=1 if persistent else T):
         _lib.check(lib.avc_lstm_seq(ctypes.byref(d), _stream()), "avc_lstm_seq")
     return hseq

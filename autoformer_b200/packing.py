@@ -159,7 +159,7 @@ def pack_lstm_hh(w_hh, precision, group):
     w = w_hh[perm].float()
     if precision == "fp32":
         hi, lo = split_bf16(w)
-        return torch.cat([hi, hi, lo], dim=1).contiguous()      # against [h_hi | h_lo | h_hi]
+        return torch.cat([hi, lo], dim=1).contiguous()          # [w_hi | w_lo]; the kernel forms hi*hi + lo*hi + hi*lo
     return to_operand(w, precision).contiguous()
 
 

@@ -116,16 +116,17 @@ int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
  */
 typedef struct avc_lstm_desc {
   const float* xproj;        /* [B*T][4H] fp32, packed column order, biases included */
-  const void* w_hh;          /* [4H][H] packed row order, dtype; dtype 2: [4H][3H] = [w_hi | w_hi | w_lo] bf16 */
+  const void* w_hh;          /* [4H][H] packed row order, dtype; dtype 2: [4H][2H] = [w_hi | w_lo] bf16 */
   void* hseq;                /* [B][T][H] dtype (dtype 2: [B][T][2H] split bf16): output sequence and recurrent operand */
   float* hseq_f32;           /* optional exact fp32 copy of the output sequence (may be NULL) */
   float* h_last;             /* optional [B][H] fp32: h_{T-1} only (LstmDV.py:21) (may be NULL) */
   float* c_state;            /* [B][H] fp32 scratch */
   int B, T, H;
   int dtype;
-  int gate_group;            /* G: 16, 32 or 64 */
+  int gate_group;            /* G: 16 or 32 */
   int persistent;            /* 0 = one launch per step; 1 = one cooperative launch, grid barrier per step */
   unsigned int* grid_barrier;/* 1 word of scratch (persistent mode) */
+  long long* debug_clk;      /* optional device buffer, 6 x int64 per (frame, CTA): clock64 stamps (profiling aid) */
 } avc_lstm_desc;
 
 int avc_lstm_seq(const avc_lstm_desc* d, void* stream);

@@ -100,7 +100,7 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
 
 def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False):
     if precision == "fp32":
-        w = w_hh[:, :H].double() + w_hh[:, 2 * H:].double()
+        w = w_hh[:, :H].double() + w_hh[:, H:].double()
     else:
         w = w_hh.double()
     xp = xproj.double().view(B, T, 4 * H)
