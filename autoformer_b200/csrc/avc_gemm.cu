@@ -30,6 +30,7 @@ struct alignas(64) GemmParams {
   int B, T, N;
   int tb_log2, bb;       // tile = bb utterances x (1 << tb_log2) frames
   int tiles_t, n_tiles;
+  int num_units;         // (pairs of) m-tiles x n-tiles; CTAs (pairs) loop over them with stride gridDim.x / CTAS
   // epilogue
   const float* bias;
   int act;
@@ -85,7 +86,7 @@ __device__ __forceinline__ void store4(void* base, int mode, int round, long lon
 // quarter take alternate 32-column chunks.
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSmem& s, uint32_t tmem_base, int ew, int lane,
-                                              int b0, int t0, int n0) {
+                                              int b0, int t0, int n0, uint64_t* tmem_empty_bar) {
   const int q = (ew + 2) & 3;            // == warp_id % 4
   const int half = ew >> 2;              // which of the two warps of this quarter
   float* stg = s.staging + ew * (32 * kStagingLd);
@@ -114,6 +115,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
     uint32_t v[32];
     tmem_ld_32x32(lane_addr + c32 * 32, v);
     tmem_ld_wait();
+    if (c32 + kEpiWarps / 4 >= BN / 32) {   // that was this warp's last read of the accumulator buffer: hand it back
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_leader(tmem_empty_bar);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(stg + lane * kStagingLd + 4 * j) =
@@ -161,7 +166,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
 
 template <int BN, bool BF16, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = PipeCfg<BN, CTAS>;
+  // Persistent: each CTA (pair) loops over tile units; the accumulator is double-buffered in tensor memory so the
+  // epilogue of unit i runs while the MMAs of unit i+1 are being issued.
+  using C = PipeCfg<BN, CTAS, 1, true, 0, 2>;
   extern __shared__ uint8_t smem_raw[];
   const PipeSmem s = carve_smem<C>(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -170,18 +177,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   // CTA pair: rank 0 (leader) issues the MMAs of the 256-row tile; each CTA owns one 128-row m-tile of it
   const int cta_rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
-
-  // tile coordinates: n fastest so CTAs sharing an A tile are co-scheduled (A stays in L2); with CTA pairs the two
-  // CTAs of a cluster (consecutive blockIdx) take consecutive m-tiles of the same n-tile
-  const int tile = blockIdx.x / CTAS;
-  const int n_tile = tile % p.n_tiles;
-  const int m_tile = (tile / p.n_tiles) * CTAS + cta_rank;
-  const int tt = m_tile % p.tiles_t;
-  const int bt = m_tile / p.tiles_t;
+  const int unit0 = blockIdx.x / CTAS;
+  const int unit_stride = gridDim.x / CTAS;
   const int tb = 1 << p.tb_log2;
-  const int t0 = tt * tb;
-  const int b0 = bt * p.bb;
-  const int n0 = n_tile * BN;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmap_b);
@@ -191,67 +189,96 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   }
   const uint32_t tmem_base = pipe_setup<C>(s);
 
+  // unit -> tile coordinates: n fastest so units processed at the same time share A tiles in L2
+  auto coords = [&](int unit, int& b0, int& t0, int& n0) {
+    const int n_tile = unit % p.n_tiles;
+    const int m_tile = (unit / p.n_tiles) * CTAS + cta_rank;
+    t0 = (m_tile % p.tiles_t) * tb;
+    b0 = (m_tile / p.tiles_t) * p.bb;
+    n0 = n_tile * BN;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer (both CTAs of a pair: own A rows, own half of the B rows)
       RingState rs;
-      int src = 0, base = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        while (kb >= p.kb_end[src]) {
-          base = p.kb_end[src];
-          ++src;
+      for (int unit = unit0; unit < p.num_units; unit += unit_stride) {
+        int b0, t0, n0;
+        coords(unit, b0, t0, n0);
+        int src = 0, base = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          while (kb >= p.kb_end[src]) {
+            base = p.kb_end[src];
+            ++src;
+          }
+          const int local = kb - base;
+          const int tap = local / p.chunks[src];
+          const int chunk = local - tap * p.chunks[src];
+          mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
+          uint8_t* a_dst = s.base + rs.stage * C::kStageBytes;
+          if (CTAS == 2) {
+            // all bytes of the pair are credited to the leader's full barrier
+            if (leader) mbar_arrive_expect_tx(&s.full[rs.stage], 2 * C::kStageBytes);
+            tma_load_3d_2sm(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
+                            t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
+            tma_load_2d_2sm(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems,
+                            n0 + cta_rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
+            tma_load_3d(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
+                        t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
+            tma_load_2d(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems, n0);
+          }
+          rs.advance<C::kStages>();
         }
-        const int local = kb - base;
-        const int tap = local / p.chunks[src];
-        const int chunk = local - tap * p.chunks[src];
-        mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
-        uint8_t* a_dst = s.base + rs.stage * C::kStageBytes;
-        if (CTAS == 2) {
-          // all bytes of the pair are credited to the leader's full barrier
-          if (leader) mbar_arrive_expect_tx(&s.full[rs.stage], 2 * C::kStageBytes);
-          tma_load_3d_2sm(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
-                          t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
-          tma_load_2d_2sm(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems,
-                          n0 + cta_rank * (BN / 2));
-        } else {
-          mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
-          tma_load_3d(a_dst, &p.tmap_a[src], &s.full[rs.stage], chunk * p.kc_elems,
-                      t0 + p.tap_t0[src] + tap * p.tap_dt[src], b0);
-          tma_load_2d(a_dst + kATileBytes, &p.tmap_b, &s.full[rs.stage], kb * p.kc_elems, n0);
-        }
-        rs.advance<C::kStages>();
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       // ---------------- MMA issuer (leader CTA only)
       RingState rs;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&s.full[rs.stage], rs.phase);
+      int it = 0;
+      for (int unit = unit0; unit < p.num_units; unit += unit_stride, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&s.tmem_empty[buf], ((it >> 1) & 1) ^ 1u);   // epilogue(s) have drained this accumulator buffer
         tc_fence_after();
-        issue_kblock<BN, BF16, CTAS>(s, rs.stage, tmem_base, kb == 0);
-        // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-        if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
-        rs.advance<C::kStages>();
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&s.full[rs.stage], rs.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s.base + rs.stage * C::kStageBytes);
+          issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, acc, kb == 0);
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
+          rs.advance<C::kStages>();
+        }
+        if (CTAS == 2) umma_commit_2sm(&s.tmem_full[buf], 0x3); else umma_commit(&s.tmem_full[buf]);
       }
-      if (CTAS == 2) umma_commit_2sm(s.tmem_full, 0x3); else umma_commit(s.tmem_full);
     }
   } else {
     // ---------------- epilogue warps
-    const long long clk_setup = p.debug_clk ? clock64() : 0;
-    mbar_wait(s.tmem_full, 0);
-    tc_fence_after();
-    const long long clk_acc = p.debug_clk ? clock64() : 0;
-    switch (p.act) {   // the activation is resolved once per tile, not once per element
-      case AVC_ACT_RELU: epilogue_tile<BN, AVC_ACT_RELU>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
-      case AVC_ACT_TANH: epilogue_tile<BN, AVC_ACT_TANH>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
-      case AVC_ACT_LRELU: epilogue_tile<BN, AVC_ACT_LRELU>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
-      case AVC_ACT_GELU: epilogue_tile<BN, AVC_ACT_GELU>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
-      default: epilogue_tile<BN, AVC_ACT_NONE>(p, s, tmem_base, warp - 2, lane, b0, t0, n0); break;
+    int it = 0;
+    long long clk_first = 0;
+    for (int unit = unit0; unit < p.num_units; unit += unit_stride, ++it) {
+      int b0, t0, n0;
+      coords(unit, b0, t0, n0);
+      const int buf = it & 1;
+      mbar_wait(&s.tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      if (p.debug_clk && it == 0) clk_first = clock64();
+      const uint32_t acc = tmem_base + buf * BN;
+      uint64_t* eb = &s.tmem_empty[buf];
+      switch (p.act) {   // the activation is resolved once per tile, not once per element
+        case AVC_ACT_RELU: epilogue_tile<BN, AVC_ACT_RELU>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
+        case AVC_ACT_TANH: epilogue_tile<BN, AVC_ACT_TANH>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
+        case AVC_ACT_LRELU: epilogue_tile<BN, AVC_ACT_LRELU>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
+        case AVC_ACT_GELU: epilogue_tile<BN, AVC_ACT_GELU>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
+        default: epilogue_tile<BN, AVC_ACT_NONE>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
+      }
     }
     if (p.debug_clk && threadIdx.x == 64) {
       long long* d = p.debug_clk + 4LL * blockIdx.x;
-      d[0] = clk_entry; d[1] = clk_setup; d[2] = clk_acc; d[3] = clock64();
+      d[0] = clk_entry; d[1] = clk_first; d[2] = clock64(); d[3] = it;
     }
   }
   pipe_teardown<C>(tmem_base);
@@ -260,15 +287,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 template <int BN, bool BF16, int CTAS>
 static int launch_impl(const GemmParams& p, long long m_tiles, cudaStream_t stream) {
   auto kern = conv_gemm_kernel<BN, BF16, CTAS>;
-  using C = PipeCfg<BN, CTAS>;
+  using C = PipeCfg<BN, CTAS, 1, true, 0, 2>;
   static bool configured = false;   // per instantiation
   if (!configured) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;
   }
   const long long pairs_m = (m_tiles + CTAS - 1) / CTAS;          // a phantom second m-tile is masked in the epilogue
-  const long long grid = pairs_m * p.n_tiles * CTAS;
-  AVC_REQUIRE(grid > 0 && grid < (1LL << 31), "avc_conv_gemm: grid %lld", grid);
+  const long long units = pairs_m * p.n_tiles;
+  AVC_REQUIRE(units > 0 && units < (1LL << 30), "avc_conv_gemm: %lld tile units", units);
+  GemmParams pp = p;
+  pp.num_units = (int)units;
+  // persistent: one CTA (pair) per SM (pair), each looping over the units with a fixed stride
+  const long long resident = num_sms() / CTAS;
+  const long long grid = (units < resident ? units : resident) * CTAS;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kNumThreads);
@@ -281,7 +313,7 @@ static int launch_impl(const GemmParams& p, long long m_tiles, cudaStream_t stre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CTAS > 1 ? 1 : 0;
-  AVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  AVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, pp));
   count_launch();
   return 0;
 }

@@ -24,8 +24,10 @@ constexpr int kStagingBytes = kEpiWarps * 32 * kStagingLd * 4;   // one 32 x 32 
 // B_hi, B_lo} of one 64-channel chunk, from which the three products hi*hi, lo*hi, hi*lo are issued.
 // STAGING: reserve the epilogue's per-warp transpose tiles.
 // EXTRA: bytes of kernel-specific shared memory (1024-byte aligned) placed after the stages, with one extra mbarrier.
-template <int BN, int CTAS = 1, int PARTS = 1, bool STAGING = true, int EXTRA = 0>
+// ACC: accumulator buffers in tensor memory (2 = the epilogue of tile i overlaps the MMAs of tile i+1).
+template <int BN, int CTAS = 1, int PARTS = 1, bool STAGING = true, int EXTRA = 0, int ACC = 1>
 struct PipeCfg {
+  static constexpr int kAcc = ACC;
   static constexpr int kCtas = CTAS;
   static constexpr int kParts = PARTS;
   static constexpr int kBTileBytes = BN / CTAS * kRowBytes;
@@ -36,9 +38,9 @@ struct PipeCfg {
   static constexpr int kExtraOffset = kStages * kStageBytes;
   static constexpr int kStagingOffset = kExtraOffset + EXTRA;
   static constexpr int kBarOffset = kStagingOffset + (STAGING ? kStagingBytes : 0);
-  // full[kStages], empty[kStages], tmem_full, extra barrier, then the TMEM base address word
-  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 2) * 8 + 16 + 1024 /* alignment slack */;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], extra barrier, then the TMEM base address word
+  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 5) * 8 + 16 + 1024 /* alignment slack */;
+  static constexpr uint32_t kTmemCols = BN * ACC < 32 ? 32 : BN * ACC;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -48,7 +50,8 @@ struct PipeSmem {
   float* staging;
   uint64_t* full;
   uint64_t* empty;
-  uint64_t* tmem_full;
+  uint64_t* tmem_full;    // [2]
+  uint64_t* tmem_empty;   // [2]
   uint64_t* extra_bar;
   uint8_t* extra;
   uint32_t* tmem_ptr;
@@ -63,7 +66,8 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
   s.full = reinterpret_cast<uint64_t*>(s.base + C::kBarOffset);
   s.empty = s.full + C::kStages;
   s.tmem_full = s.empty + C::kStages;
-  s.extra_bar = s.tmem_full + 1;
+  s.tmem_empty = s.tmem_full + 2;
+  s.extra_bar = s.tmem_empty + 2;
   s.extra = s.base + C::kExtraOffset;
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.extra_bar + 1);
   return s;
@@ -78,7 +82,10 @@ __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], 1);
     }
-    mbar_init(s.tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.tmem_full[i], 1);
+      mbar_init(&s.tmem_empty[i], C::kCtas * kEpiWarps);   // one arrival per epilogue warp of every CTA of the pair
+    }
     mbar_init(s.extra_bar, 1);
     fence_mbar_init();
   }

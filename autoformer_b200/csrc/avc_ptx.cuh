@@ -208,6 +208,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
                : "memory");
 }
 
+// Arrive on the mbarrier at this shared-memory offset in the LEADER CTA of the pair (works from either CTA).
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 128 bytes, 8-row
 // groups 1024 bytes apart).  Field layout: bits [0,14) start address >> 4, [16,30) leading byte
 // offset >> 4 (unused for swizzled K-major, set to 1), [32,46) stride byte offset >> 4,
