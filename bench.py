@@ -306,12 +306,21 @@ def run_native(args):
     dom_e = tensor_fams[dom]
     kernel_name = {"lstm_step": "lstm_step_kernel", "conv": "conv_gemm_kernel", "inproj": "conv_gemm_kernel",
                    "linear": "conv_gemm_kernel"}[dom]
+    passes = {"fp32": 3, "tf32": 2, "bf16": 1}[args.precision]      # bf16-MMA-equivalent passes per algorithmic FLOP
+    for v in kernels.values():
+        if "tflops" in v:
+            v["tensor_pipe_frac"] = v["tflops"] * passes / pk["tflops_sustained"]
     roofline = {
         "kernel": f"{kernel_name} ({dom})", "bound": "tensor", "achieved": dom_e["tflops"],
         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": dom_e["tflops"] / pk["tflops_sustained"],
         "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained",
         "share_of_step": dom_e["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
         "avg_launch_us": dom_e["ms_per_step"] * 1e3 / max(1, dom_e["launches_per_step"]),
+        "algorithmic_flops_per_launch": dom_e["tflops"] * 1e12 * dom_e["ms_per_step"] * 1e-3 / max(1, dom_e["launches_per_step"]),
+        "mma_passes_per_flop": passes,
+        "issued_mma_frac_of_peak": dom_e["tflops"] * passes / pk["tflops_sustained"],
+        "note": "achieved = algorithmic FLOPs (2*4H*H per frame per layer for the recurrence) / CUDA-event time of the "
+                "launches; the split-bf16 'fp32' mode issues 3 bf16 MMA FLOPs per algorithmic FLOP, so frac <= 1/3",
     }
 
     # NCCL is used only to gather per-rank records (frames, time, output checksum) -- no data-path collective
