@@ -64,6 +64,23 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target
   __syncthreads();
 }
 
+// Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
+// has already synchronised with this thread through the epi_done mbarrier.
+__device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target) {
+  __threadfence();
+  atomicAdd(bar, 1u);
+  const long long t0 = clock64();
+  unsigned int seen;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    if (seen < target && clock64() - t0 > 4000000000LL) {
+      printf("avc: grid barrier timeout block %d seen %u target %u\n", (int)blockIdx.x, seen, target);
+      __trap();
+    }
+  } while (seen < target);
+  __threadfence();
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -105,6 +122,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
   uint32_t acc_phase = 0;    // epilogue: parity of tmem_full
   unsigned int sync_count = 0;
   int pre_issued = 0;        // producer: stages of the current frame whose W tiles are already in flight
+  uint32_t epi_phase = 0;    // producer: parity of epi_done
   // cell warps: the running cell state lives in registers across frames; the xproj tile of each frame is fetched by
   // the producer thread with TMA into 128-byte-swizzled shared memory (a thread-per-row read of a swizzled slab is
   // bank-conflict free) while the MMAs of that frame run, so the cell warps issue no global loads.
@@ -178,6 +196,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
             ws.advance<C::kStages>();
           }
           pre_issued = pre;
+          // the next frame's h tiles need every CTA's h_t: wait for this CTA's cell warps, then for the whole grid
+          mbar_wait(s.epi_done, epi_phase);
+          epi_phase ^= 1u;
+          ++sync_count;
+          grid_arrive_wait(p.grid_barrier, sync_count * gridDim.x);
         }
       }
       __syncwarp();
@@ -271,14 +294,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           float cn[8], hn[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float ig = sigmoid_fast(z[0][e]);
-            const float fg = sigmoid_fast(z[1][e]);
-            const float gg = tanh_fast(z[2][e]);
-            const float og = sigmoid_fast(z[3][e]);
-            cn[e] = fg * cprev[e] + ig * gg;
-            hn[e] = og * tanh_fast(cn[e]);
-          }
+          for (int e = 0; e < 8; ++e) lstm_cell(z[0][e], z[1][e], z[2][e], z[3][e], cprev[e], cn[e], hn[e]);
           cq[jj][0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
           cq[jj][1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
           if (t + 1 == p.t_end) {       // a later launch (per-step mode) resumes from global memory
@@ -319,14 +335,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
         }
       }
       fence_proxy_async_all();   // order the h stores before later async-proxy (TMA) reads
+      tc_fence_before();         // ... and this warp's TMEM reads before the next frame's MMAs (via the barrier chain)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s.epi_done);
       if (dbg && threadIdx.x == 64) dbg[5] = clock64();                    // cell update done
-    }
-    if (t + 1 < p.t_end) {
-      // the next frame's MMAs overwrite the accumulator and read h_t from every CTA: grid-wide barrier
-      tc_fence_before();
-      ++sync_count;
-      grid_sync(p.grid_barrier, sync_count * gridDim.x);
-      tc_fence_after();
     }
   }
   pipe_teardown<C>(tmem_base);
