@@ -382,3 +382,43 @@ def test_meta_parity_and_golden(kind, name, precision, tol):
         assert rel_l2(post1, torch.from_numpy(g["mel_postnet"])) < 1e-3
         assert rel_l2(codes1, torch.from_numpy(g["codes"])) < 1e-3
         assert rel_l2(m(torch.from_numpy(g["mel"]).cuda(), co1.cuda(), None), torch.from_numpy(g["codes_of_mel"])) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("B,T", [(1, 32), (130, 32), (2, 1024), (257, 64)])
+def test_autovc_edge_shapes(B, T):
+    """Smallest utterance (one code), ragged batches that leave partial / masked tiles and CTA pairs with a phantom
+    m-tile, and the longest BASELINE utterance length.  The oracle is evaluated on a few utterances only."""
+    args = (32, 256, 512, 32)
+    sd = seeded_state_dict(templates.autovc_template(*args), 5)
+    x, c_org, c_trg = synthetic_mel(B, T, 31), synthetic_speaker(B, 31, "org"), synthetic_speaker(B, 31, "trg")
+    m = _model(args, sd)
+    mel, post, codes = m(x.cuda(), c_org.cuda(), c_trg.cuda())
+    assert mel.shape == (B, 1, T, 80) and post.shape == (B, 1, T, 80) and codes.shape == (B, 64 * (T // 32))
+    assert torch.isfinite(post).all()
+    pick = sorted({0, B // 2, B - 1})
+    ref = autovc_forward(sd, x[pick], c_org[pick], c_trg[pick], 32, 32)
+    assert rel_l2(mel[pick], ref[0]) < 2e-4 and rel_l2(post[pick], ref[1]) < 2e-4 and rel_l2(codes[pick], ref[2]) < 2e-4
+    m.persistent_lstm = True
+    post_p = m(x.cuda(), c_org.cuda(), c_trg.cuda())[1]
+    assert torch.equal(post_p, post)
+
+
+def test_lstmdv_and_melgan_batch_independence():
+    import warnings
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    from autoformer_b200.factory.LstmDV import LstmDV
+    from autoformer_b200.melgan.modules import Generator
+    dv = LstmDV()
+    dv.load_state_dict(seeded_state_dict(templates.lstmdv_template(), 3, lstm_gain=1.5))
+    dv = dv.cuda().eval()
+    x = synthetic_mel(140, 48, 9).cuda()
+    e = dv(x)
+    assert rel_l2(dv(x[:3]), e[:3]) < 1e-5 and rel_l2(dv(x[137:]), e[137:]) < 1e-5
+    gen = Generator(80, 32, 3)
+    gen.load_state_dict(seeded_state_dict(templates.melgan_template(), 4))
+    gen = gen.cuda().eval()
+    mel = synthetic_mel(5, 33, 9).transpose(1, 2).contiguous().cuda()
+    w = gen(mel)
+    assert w.shape == (5, 1, 33 * 256)
+    assert rel_l2(gen(mel[1:2]), w[1:2]) < 1e-5
