@@ -37,3 +37,73 @@ def convert_and_vocode(embedder, model, generator, mel_src, mel_trg_ref):
     mel_trans = convert(model, mel_src, emb_org, emb_trg)
     wav = generator(mel_trans.transpose(2, 1).contiguous()).squeeze(1)   # MelVocoder.inverse (interface.py:43-53)
     return mel_trans, wav, emb_org, emb_trg
+
+
+class StreamingConverter:
+    """Batched conversion from HOST tensors to HOST tensors with the PCIe copies overlapped with compute.
+
+    ``submit(x, c_org, c_trg)`` (pinned or pageable CPU tensors) enqueues: H2D on a copy stream -> ``model`` on the
+    compute stream -> D2H of ``(mel, mel_postnet, codes)`` into pinned buffers on a second copy stream, and returns
+    the result of the PREVIOUS submission (or None): while batch i computes, batch i+1 uploads and batch i-1
+    downloads.  ``flush()`` returns the last result.  Results are pinned host tensors owned by the converter and are
+    overwritten two submissions later (double buffering) -- copy them if they must live longer.
+    """
+
+    def __init__(self, model, device=None):
+        self.model = model
+        self.device = torch.device(device or next(model.parameters()).device)
+        self.h2d = torch.cuda.Stream(self.device)
+        self.d2h = torch.cuda.Stream(self.device)
+        self.slot = 0
+        self.dev_in = [None, None]
+        self.host_out = [None, None]
+        self.done = [None, None]
+        self.pending = None
+
+    def _pinned_like(self, outs, slot):
+        bufs = self.host_out[slot]
+        if bufs is None or any(b.shape != o.shape for b, o in zip(bufs, outs)):
+            bufs = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            self.host_out[slot] = bufs
+        return bufs
+
+    @torch.no_grad()
+    def submit(self, x, c_org, c_trg):
+        s = self.slot
+        compute = torch.cuda.current_stream(self.device)
+        if self.done[s] is not None:
+            self.done[s].synchronize()              # the slot's previous download has finished: buffers are free
+        with torch.cuda.stream(self.h2d):
+            dev = [t.to(self.device, non_blocking=True) for t in (x, c_org, c_trg)]
+            up = torch.cuda.Event()
+            up.record(self.h2d)
+        self.dev_in[s] = dev                        # keep alive until the compute stream has consumed them
+        compute.wait_event(up)
+        outs = self.model(*dev)
+        for t in dev:
+            t.record_stream(compute)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        bufs = self._pinned_like(outs, s)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(ready)
+            for b, o in zip(bufs, outs):
+                b.copy_(o, non_blocking=True)
+                o.record_stream(self.d2h)
+            ev = torch.cuda.Event()
+            ev.record(self.d2h)
+        self.done[s] = ev
+        prev, self.pending = self.pending, (s, ev)
+        self.slot ^= 1
+        if prev is None:
+            return None
+        prev[1].synchronize()
+        return tuple(self.host_out[prev[0]])
+
+    def flush(self):
+        if self.pending is None:
+            return None
+        s, ev = self.pending
+        self.pending = None
+        ev.synchronize()
+        return tuple(self.host_out[s])

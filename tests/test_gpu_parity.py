@@ -422,3 +422,24 @@ def test_lstmdv_and_melgan_batch_independence():
     w = gen(mel)
     assert w.shape == (5, 1, 33 * 256)
     assert rel_l2(gen(mel[1:2]), w[1:2]) < 1e-5
+
+
+def test_streaming_converter_host_to_host():
+    """The public host-to-host API (what bench.py's e2e leg times) returns the same results as direct calls."""
+    from autoformer_b200.pipeline import StreamingConverter
+    args = (32, 256, 512, 32)
+    sd = seeded_state_dict(templates.autovc_template(*args), 6)
+    m = _model(args, sd)
+    sc = StreamingConverter(m)
+    batches = [(synthetic_mel(3, 64, s).pin_memory(), synthetic_speaker(3, s, "org"), synthetic_speaker(3, s, "trg")) for s in (1, 2, 3)]
+    got = []
+    for b in batches:
+        r = sc.submit(*b)
+        if r is not None:
+            got.append([t.clone() for t in r])
+    got.append([t.clone() for t in sc.flush()])
+    assert len(got) == 3 and sc.flush() is None
+    for b, r in zip(batches, got):
+        ref = m(*(t.cuda() for t in b))
+        for u, v in zip(r, ref):
+            assert not u.is_cuda and torch.equal(u, v.cpu())
