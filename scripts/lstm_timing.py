@@ -20,8 +20,9 @@ def run(precision, B=512, T=128, H=1024):
     e0.record(); ops.lstm_seq(xp, hh, B, T, H, precision, G, persistent=True, debug_clk=dbg); e1.record()
     torch.cuda.synchronize()
     d = dbg.view(T, grid, 6).double().cpu()
-    lead = d[10:T - 1, 0::2]                     # leader CTAs (MMA stamps), frames 10..T-2
-    nxt = d[11:T, 0::2, 0]
+    step = 2 if m_tiles >= 2 else 1
+    lead = d[10:T - 1, 0::step]                  # leader CTAs (MMA stamps), frames 10..T-2
+    nxt = d[11:T, 0::step, 0]
     f = lambda a: f"{a.mean():.0f}"
     print(f"{precision} B={B} H={H} G={G} grid={grid}: {e0.elapsed_time(e1) * 1e3 / T:.2f} us/frame; cycles: "
           f"start->first stage {f(lead[..., 1] - lead[..., 0])}, mainloop issue {f(lead[..., 2] - lead[..., 1])}, "
@@ -29,6 +30,14 @@ def run(precision, B=512, T=128, H=1024):
           f"cell end->next frame start (barrier) {f(nxt - lead[..., 5])}, frame {f(nxt - lead[..., 0])}; "
           f"preload issue {f(lead[..., 3] - lead[..., 0])}")
 
-for prec in ("fp32", "bf16", "tf32"):
-    run(prec)
-run("fp32", H=512)
+import sys
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    run("fp32", B=32, T=256, H=768)
+    run("fp32", B=64, T=256, H=768)
+    run("fp32", B=32, T=256, H=1024)
+    run("fp32", B=32, T=256, H=512)
+    run("bf16", B=32, T=256, H=768)
+else:
+    for prec in ("fp32", "bf16", "tf32"):
+        run(prec)
+    run("fp32", H=512)
