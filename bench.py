@@ -456,6 +456,9 @@ def run_sweep(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
