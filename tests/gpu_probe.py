@@ -1,5 +1,5 @@
 """First-contact GPU probe: runs each kernel family in its own subprocess (a device trap poisons the context),
-from the smallest case up, and prints error statistics.  Usage: python scripts/gpu_probe.py [case ...]"""
+from the smallest case up, and prints error statistics.  Usage: python tests/gpu_probe.py [case ...]"""
 import os
 import subprocess
 import sys
