@@ -67,8 +67,9 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target
 // Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
 // has already synchronised with this thread through the epi_done mbarrier.
 __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target) {
-  __threadfence();
-  atomicAdd(bar, 1u);
+  // release: everything this thread has observed (the cell warps' h stores, via epi_done) becomes visible to whoever
+  // acquires the counter; the acquire load orders the TMA issue that follows.
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
   const long long t0 = clock64();
   unsigned int seen;
   do {
@@ -78,7 +79,6 @@ __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int
       __trap();
     }
   } while (seen < target);
-  __threadfence();
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
         };
         if (!has_mma) issue_x();
         if (has_mma) {
-          fence_proxy_async_all();   // h_{t-1} was written with generic stores (other CTAs / previous launch)
+          fence_proxy_async_global();   // h_{t-1} was written with generic stores (other CTAs / previous launch)
           RingState hs = rs;         // stages whose W tiles were pre-issued: add the h tiles
           for (int kb = 0; kb < pre_issued; ++kb) {
             issue(kb, t, false, true, hs.stage);
@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           mbar_wait(s.epi_done, epi_phase);
           epi_phase ^= 1u;
           ++sync_count;
-          grid_arrive_wait(p.grid_barrier, sync_count * gridDim.x);
+          // only the CTAs that own the same utterances (all n-tiles of this m tile / m pair) exchange h:
+          // one counter per batch group (padded to its own 128-byte line)
+          grid_arrive_wait(p.grid_barrier + 32 * (unit / p.n_tiles), sync_count * (unsigned)(p.n_tiles * CTAS));
         }
       }
       __syncwarp();
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           }
         }
       }
-      fence_proxy_async_all();   // order the h stores before later async-proxy (TMA) reads
+      fence_proxy_async_global();   // order the h stores before later async-proxy (TMA) reads
       tc_fence_before();         // ... and this warp's TMEM reads before the next frame's MMAs (via the barrier chain)
       __syncwarp();
       if (lane == 0) mbar_arrive(s.epi_done);
@@ -388,7 +390,8 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
       resident = per_sm * num_sms();
     }
     AVC_REQUIRE(resident >= grid, "avc_lstm_seq: persistent grid %d does not fit (%d CTAs resident)", grid, resident);
-    AVC_CHECK_CUDA(cudaMemsetAsync(d->grid_barrier, 0, sizeof(unsigned int), stream));
+    AVC_REQUIRE((m_tiles + CTAS - 1) / CTAS <= 64, "avc_lstm_seq: at most 64 batch groups in persistent mode");
+    AVC_CHECK_CUDA(cudaMemsetAsync(d->grid_barrier, 0, 64 * 32 * sizeof(unsigned int), stream));
     p.t_begin = 0;
     p.t_end = d->T;
     AVC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));

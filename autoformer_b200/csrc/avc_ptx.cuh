@@ -26,6 +26,8 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 // Orders generic-proxy global writes (made visible by a barrier) before later TMA (async proxy) reads.
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Same, restricted to global memory (the recurrent state h is written with st.global and re-read by TMA).
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -234,7 +234,7 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
     d.persistent = 1 if persistent else 0
     bar = None
     if persistent:
-        bar = torch.zeros(4, dtype=torch.int32, device=dev)
+        bar = torch.empty(64 * 32, dtype=torch.int32, device=dev)     # zeroed by the library
         d.grid_barrier = bar.data_ptr()
     if debug_clk is not None:
         d.debug_clk = debug_clk.data_ptr()

@@ -125,7 +125,7 @@ typedef struct avc_lstm_desc {
   int dtype;
   int gate_group;            /* G: 16 or 32 */
   int persistent;            /* 0 = one launch per step; 1 = one cooperative launch, grid barrier per step */
-  unsigned int* grid_barrier;/* 1 word of scratch (persistent mode) */
+  unsigned int* grid_barrier;/* 8 KB of scratch (persistent mode): one barrier counter per batch group */
   long long* debug_clk;      /* optional device buffer, 6 x int64 per (frame, CTA): clock64 stamps (profiling aid) */
 } avc_lstm_desc;
 
