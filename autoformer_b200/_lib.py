@@ -76,6 +76,11 @@ class LstmDesc(ctypes.Structure):
         ("persistent", ctypes.c_int),
         ("grid_barrier", ctypes.c_void_p),
         ("debug_clk", ctypes.c_void_p),
+        ("xin", ctypes.c_void_p),
+        ("xin_channels", ctypes.c_int),
+        ("xin_ld", ctypes.c_longlong),
+        ("w_ih", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
     ]
 
 

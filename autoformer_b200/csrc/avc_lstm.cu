@@ -20,6 +20,7 @@
 //   persistent  one cooperative launch for all frames; a grid-wide barrier separates frames
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <type_traits>
 
 #include "../../include/avc_b200.h"
 #include "avc_host.h"
@@ -31,6 +32,10 @@ struct alignas(64) LstmParams {
   CUtensorMap tmap_h[2];   // hseq as (H, T, B), box {kc, 1, 128}; [1] = the lo half in split mode
   CUtensorMap tmap_w[2];   // w_hh as (H, 4H), box {kc, BN / CTAS}; [1] = the lo half in split mode
   CUtensorMap tmap_x;      // xproj as (4H, T, B) fp32, box {32, 1, 128}
+  CUtensorMap tmap_xi[2];  // fused input projection: input sequence as (C_in, T, B), box {kc, 1, 128}; [1] = lo half
+  CUtensorMap tmap_wi[2];  // fused input projection: w_ih as (K_in, 4H), box {kc, BN / CTAS}; [1] = lo half
+  const float* bias;       // fused input projection: b_ih + b_hh [4H], packed gate order
+  int num_kx;              // fused input projection: k-blocks of the input part
   const float* xproj;
   void* hseq;
   float* hseq_f32;
@@ -83,6 +88,44 @@ __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+
+// Stores of one cell thread's 8 new hidden values (utterance row `row` = b*T + t, hidden units u..u+7): the recurrent
+// operand in the layer's operand format, plus the optional exact fp32 copies.
+template <int MODE>
+__device__ __forceinline__ void store_h8(const LstmParams& p, long long row, int b, int t, int u, const float (&hn)[8]) {
+  const long long hoff = row * p.H + u;
+  if (MODE == 2) {
+    float lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) lo[e] = hn[e] - __bfloat162float(__float2bfloat16_rn(hn[e]));
+    __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(p.hseq) + row * (2LL * p.H) + u;
+    *reinterpret_cast<uint4*>(hp) = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]),
+                                               pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
+    *reinterpret_cast<uint4*>(hp + p.H) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]),
+                                                     pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+  } else if (MODE == 1) {
+    uint4 pk = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
+                          pack_bf16(hn[6], hn[7]));
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.hseq) + hoff) = pk;
+  } else {
+    float* hp = static_cast<float*>(p.hseq) + hoff;
+    *reinterpret_cast<float4*>(hp) =
+        make_float4(round_tf32(hn[0]), round_tf32(hn[1]), round_tf32(hn[2]), round_tf32(hn[3]));
+    *reinterpret_cast<float4*>(hp + 4) =
+        make_float4(round_tf32(hn[4]), round_tf32(hn[5]), round_tf32(hn[6]), round_tf32(hn[7]));
+  }
+  if (p.hseq_f32) {
+    float* hp = p.hseq_f32 + hoff;
+    *reinterpret_cast<float4*>(hp) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    *reinterpret_cast<float4*>(hp + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+  }
+  if (p.h_last && t == p.T - 1) {
+    float* hp = p.h_last + (long long)b * p.H + u;
+    *reinterpret_cast<float4*>(hp) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    *reinterpret_cast<float4*>(hp + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+  }
 }
 
 // MODE: 0 = tf32, 1 = bf16, 2 = split bf16 (three bf16 products per fp32 product, operands staged once)
@@ -303,37 +346,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
             *reinterpret_cast<float4*>(cp + j * 8) = cq[jj][0];
             *reinterpret_cast<float4*>(cp + j * 8 + 4) = cq[jj][1];
           }
-          const long long hoff = row * p.H + u0 + j * 8;
-          if (MODE == 2) {
-            float lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) lo[e] = hn[e] - __bfloat162float(__float2bfloat16_rn(hn[e]));
-            __nv_bfloat16* hp = static_cast<__nv_bfloat16*>(p.hseq) + row * (2LL * p.H) + u0 + j * 8;
-            *reinterpret_cast<uint4*>(hp) = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]),
-                                                       pack_bf16(hn[4], hn[5]), pack_bf16(hn[6], hn[7]));
-            *reinterpret_cast<uint4*>(hp + p.H) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]),
-                                                             pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-          } else if (MODE == 1) {
-            uint4 pk = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
-                                  pack_bf16(hn[6], hn[7]));
-            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.hseq) + hoff) = pk;
-          } else {
-            float* hp = static_cast<float*>(p.hseq) + hoff;
-            *reinterpret_cast<float4*>(hp) =
-                make_float4(round_tf32(hn[0]), round_tf32(hn[1]), round_tf32(hn[2]), round_tf32(hn[3]));
-            *reinterpret_cast<float4*>(hp + 4) =
-                make_float4(round_tf32(hn[4]), round_tf32(hn[5]), round_tf32(hn[6]), round_tf32(hn[7]));
-          }
-          if (p.hseq_f32) {
-            float* hp = p.hseq_f32 + hoff;
-            *reinterpret_cast<float4*>(hp) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(hp + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-          }
-          if (p.h_last && t == p.T - 1) {
-            float* hp = p.h_last + (long long)b * p.H + u0 + j * 8;
-            *reinterpret_cast<float4*>(hp) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-            *reinterpret_cast<float4*>(hp + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-          }
+          store_h8<MODE>(p, row, b, t, u0 + j * 8, hn);
         }
       }
       fence_proxy_async_global();   // order the h stores before later async-proxy (TMA) reads
@@ -346,10 +359,257 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
   pipe_teardown<C>(tmem_base);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused variant: the layer's input projection runs inside the recurrence kernel.
+//   z_t = [x_t | h_{t-1}] . [W_ih | W_hh]^T + (b_ih + b_hh)
+// The x_t part does not depend on the previous frame, so its MMAs (into the OTHER of two TMEM accumulators) run while
+// the cell warps are still updating frame t-1 and while the grid barrier is in flight -- the tensor pipe no longer
+// idles there -- and the fp32 xproj tensor (B*T*4H*4 bytes written and re-read per layer) never exists.
+// Warp roles: 0 = producer of everything that is independent of the recurrence (x_t tiles, W_ih tiles, W_hh tiles);
+// 1 = MMA issuer; 2..9 = cell warps; 10 = producer of the h_{t-1} tiles, which also owns the grid barrier.  Both
+// producers walk the same ring in the same order: frame t = num_kx input stages, then (t > 0) num_kb recurrent stages.
+constexpr int kFusedThreads = kNumThreads + 32;
+constexpr int kBiasBytes = 1024;
+
 template <int BN, int MODE, int CTAS>
+__global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __grid_constant__ LstmParams p) {
+  constexpr int PARTS = MODE == 2 ? 2 : 1;
+  using C = PipeCfg<BN, CTAS, PARTS, false, kBiasBytes, 2>;
+  constexpr int G = BN / 4;
+  constexpr bool BF16 = MODE != 0;
+  static_assert(BN * 4 <= kBiasBytes - 16, "bias tile + the h_ready counter");
+  extern __shared__ uint8_t smem_raw[];
+  const PipeSmem s = carve_smem<C>(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / CTAS;
+  const int n_tile = unit % p.n_tiles;
+  const int m_tile = (unit / p.n_tiles) * CTAS + cta_rank;
+  const int b0 = m_tile * kBlockM;
+  const int n0 = n_tile * BN;
+  const int nb0 = n0 + cta_rank * (BN / CTAS);
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int part = 0; part < PARTS; ++part) {
+      prefetch_tmap(&p.tmap_h[part]);
+      prefetch_tmap(&p.tmap_w[part]);
+      prefetch_tmap(&p.tmap_xi[part]);
+      prefetch_tmap(&p.tmap_wi[part]);
+    }
+  }
+  float* sbias = reinterpret_cast<float*>(s.extra);
+  // Recurrent stages whose slot the static producer has claimed (empty barrier observed, W tiles in flight).  The h
+  // producer may not test the empty barriers itself: it skips the input stages, so it can be several ring rounds
+  // ahead of the consumer, and an mbarrier parity wait only tells adjacent phases apart.
+  uint32_t* h_ready = reinterpret_cast<uint32_t*>(s.extra + kBiasBytes - 16);
+  if (threadIdx.x == 0) *h_ready = 0u;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) sbias[threadIdx.x - 64] = p.bias[n0 + threadIdx.x - 64];
+  const uint32_t tmem_base = pipe_setup<C>(s);     // (its CTA / cluster barrier also publishes the bias tile)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t h_claimed = 0;
+      // one stage = {A tile(s), W tile(s)} of a 64/32-channel chunk; this thread credits the stage's full byte count
+      // and loads everything except the h tiles
+      auto stage_static = [&](const CUtensorMap* tw, int kb, const CUtensorMap* ta, int frame) {
+        mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
+        uint8_t* st = s.base + rs.stage * C::kStageBytes;
+        uint8_t* wst = st + PARTS * kATileBytes;
+        const int kc0 = kb * p.kc_elems;
+        if (CTAS == 2) {
+          if (leader) mbar_arrive_expect_tx(&s.full[rs.stage], 2 * C::kStageBytes);
+          tma_load_2d_2sm(wst, &tw[0], &s.full[rs.stage], kc0, nb0);
+          if (PARTS == 2) tma_load_2d_2sm(wst + C::kBTileBytes, &tw[1], &s.full[rs.stage], kc0, nb0);
+          if (ta) {
+            tma_load_3d_2sm(st, &ta[0], &s.full[rs.stage], kc0, frame, b0);
+            if (PARTS == 2) tma_load_3d_2sm(st + kATileBytes, &ta[1], &s.full[rs.stage], kc0, frame, b0);
+          }
+        } else {
+          mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
+          tma_load_2d(wst, &tw[0], &s.full[rs.stage], kc0, nb0);
+          if (PARTS == 2) tma_load_2d(wst + C::kBTileBytes, &tw[1], &s.full[rs.stage], kc0, nb0);
+          if (ta) {
+            tma_load_3d(st, &ta[0], &s.full[rs.stage], kc0, frame, b0);
+            if (PARTS == 2) tma_load_3d(st + kATileBytes, &ta[1], &s.full[rs.stage], kc0, frame, b0);
+          }
+        }
+        if (!ta) {
+          ++h_claimed;
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(h_ready)), "r"(h_claimed) : "memory");
+        }
+        rs.advance<C::kStages>();
+      };
+      for (int t = p.t_begin; t < p.t_end; ++t) {
+        for (int kb = 0; kb < p.num_kx; ++kb) stage_static(p.tmap_wi, kb, p.tmap_xi, t);
+        if (t > 0)
+          for (int kb = 0; kb < p.num_kb; ++kb) stage_static(p.tmap_w, kb, nullptr, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      RingState rs;
+      for (int t = p.t_begin; t < p.t_end; ++t) {
+        long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+        const uint32_t acc = tmem_base + static_cast<uint32_t>((t & 1) * BN);
+        const int total = p.num_kx + (t > 0 ? p.num_kb : 0);
+        for (int i = 0; i < total; ++i) {
+          if (dbg && i == p.num_kx) dbg[3] = clock64();                    // input part issued
+          mbar_wait(&s.full[rs.stage], rs.phase);
+          if (dbg && i == p.num_kx) dbg[1] = clock64();                    // first recurrent stage landed
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(s.base + rs.stage * C::kStageBytes);
+          const uint32_t w_hi = a_hi + PARTS * kATileBytes;
+          issue_pair<BN, BF16, CTAS>(a_hi, w_hi, acc, i == 0);
+          if (PARTS == 2) {
+            issue_pair<BN, BF16, CTAS>(a_hi + kATileBytes, w_hi, acc, false);            // a_lo * W_hi
+            issue_pair<BN, BF16, CTAS>(a_hi, w_hi + C::kBTileBytes, acc, false);         // a_hi * W_lo
+          }
+          if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
+          rs.advance<C::kStages>();
+        }
+        if (CTAS == 2) umma_commit_2sm(&s.tmem_full[t & 1], 0x3); else umma_commit(&s.tmem_full[t & 1]);
+        if (dbg) dbg[2] = clock64();                                       // all MMAs of the frame issued
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 + kEpiWarps) {
+    if (lane == 0) {
+      RingState rs;
+      uint32_t epi_phase = 0;
+      uint32_t h_issued = 0;
+      unsigned int sync_count = 0;
+      for (int t = p.t_begin; t < p.t_end; ++t) {
+        long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+        for (int kb = 0; kb < p.num_kx; ++kb) rs.advance<C::kStages>();
+        if (t == 0) continue;
+        if (t > p.t_begin) {
+          // h_{t-1} comes from this launch: wait for this CTA's cell warps, then for every CTA that owns the same
+          // utterances (all n-tiles of this m tile / m pair): one counter per batch group on its own 128-byte line
+          mbar_wait(s.epi_done, epi_phase);
+          epi_phase ^= 1u;
+          ++sync_count;
+          grid_arrive_wait(p.grid_barrier + 32 * (unit / p.n_tiles), sync_count * (unsigned)(p.n_tiles * CTAS));
+        }
+        if (dbg) dbg[0] = clock64();                                       // barrier passed
+        fence_proxy_async_global();   // h_{t-1} was written with generic stores (other CTAs / previous launch)
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ++h_issued;
+          {
+            uint32_t seen;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(h_ready)) : "memory");
+              if (seen < h_issued && clock64() - t0 > 4000000000LL) {
+                printf("avc: h_ready timeout block %d seen %u want %u\n", (int)blockIdx.x, seen, h_issued);
+                __trap();
+              }
+            } while (seen < h_issued);
+          }
+          uint8_t* st = s.base + rs.stage * C::kStageBytes;
+          const int kc0 = kb * p.kc_elems;
+          if (CTAS == 2) {
+            tma_load_3d_2sm(st, &p.tmap_h[0], &s.full[rs.stage], kc0, t - 1, b0);
+            if (PARTS == 2) tma_load_3d_2sm(st + kATileBytes, &p.tmap_h[1], &s.full[rs.stage], kc0, t - 1, b0);
+          } else {
+            tma_load_3d(st, &p.tmap_h[0], &s.full[rs.stage], kc0, t - 1, b0);
+            if (PARTS == 2) tma_load_3d(st + kATileBytes, &p.tmap_h[1], &s.full[rs.stage], kc0, t - 1, b0);
+          }
+          rs.advance<C::kStages>();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- cell warps: thread owns utterance b; the two warps of a TMEM lane quarter take alternate groups
+    // of 8 hidden units; the running cell state stays in registers across frames
+    constexpr int NJ = (G / 8 + kEpiWarps / 4 - 1) / (kEpiWarps / 4);
+    float4 cq[NJ][2];
+    uint32_t acc_phase = 0;      // bit i = parity of tmem_full[i]
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int b = b0 + q * 32 + lane;
+    const bool valid = b < p.B;
+    const int u0 = n_tile * G;
+    float* cp = p.c_state + (long long)b * p.H + u0;
+    for (int t = p.t_begin; t < p.t_end; ++t) {
+      long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+      const long long row = (long long)b * p.T + t;
+      if (t == p.t_begin) {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+          const int j = half + jj * (kEpiWarps / 4);
+          cq[jj][0] = cq[jj][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && t > 0 && j < G / 8) {      // per-step launches carry c through global memory
+            cq[jj][0] = *reinterpret_cast<const float4*>(cp + j * 8);
+            cq[jj][1] = *reinterpret_cast<const float4*>(cp + j * 8 + 4);
+          }
+        }
+      }
+      const int buf = t & 1;
+      mbar_wait(&s.tmem_full[buf], (acc_phase >> buf) & 1u);
+      acc_phase ^= 1u << buf;
+      tc_fence_after();
+      if (dbg && threadIdx.x == 64) dbg[4] = clock64();                    // accumulator ready
+      const uint32_t lane_addr = tmem_base + static_cast<uint32_t>(buf * BN) + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll
+      for (int jj = 0; jj < NJ; ++jj) {
+        const int j = half + jj * (kEpiWarps / 4);
+        if (j >= G / 8) break;
+        uint32_t acc[4][8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld_32x8(lane_addr + g * G + j * 8, acc[g]);
+        tmem_ld_wait();
+        if (valid) {
+          float z[4][8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 x0 = *reinterpret_cast<const float4*>(sbias + g * G + j * 8);       // broadcast reads
+            const float4 x1 = *reinterpret_cast<const float4*>(sbias + g * G + j * 8 + 4);
+            z[g][0] = __uint_as_float(acc[g][0]) + x0.x;
+            z[g][1] = __uint_as_float(acc[g][1]) + x0.y;
+            z[g][2] = __uint_as_float(acc[g][2]) + x0.z;
+            z[g][3] = __uint_as_float(acc[g][3]) + x0.w;
+            z[g][4] = __uint_as_float(acc[g][4]) + x1.x;
+            z[g][5] = __uint_as_float(acc[g][5]) + x1.y;
+            z[g][6] = __uint_as_float(acc[g][6]) + x1.z;
+            z[g][7] = __uint_as_float(acc[g][7]) + x1.w;
+          }
+          const float4 c0 = cq[jj][0], c1 = cq[jj][1];
+          const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          float cn[8], hn[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) lstm_cell(z[0][e], z[1][e], z[2][e], z[3][e], cprev[e], cn[e], hn[e]);
+          cq[jj][0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+          cq[jj][1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+          if (t + 1 == p.t_end) {       // a later launch (per-step mode) resumes from global memory
+            *reinterpret_cast<float4*>(cp + j * 8) = cq[jj][0];
+            *reinterpret_cast<float4*>(cp + j * 8 + 4) = cq[jj][1];
+          }
+          store_h8<MODE>(p, row, b, t, u0 + j * 8, hn);
+        }
+      }
+      fence_proxy_async_global();   // order the h stores before later async-proxy (TMA) reads
+      tc_fence_before();            // ... and this warp's TMEM reads before the MMAs that reuse the accumulator
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s.epi_done);
+      if (dbg && threadIdx.x == 64) dbg[5] = clock64();                    // cell update done
+    }
+  }
+  pipe_teardown<C>(tmem_base);
+}
+
+template <int BN, int MODE, int CTAS, bool FUSED>
 static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t stream) {
-  auto kern = lstm_step_kernel<BN, MODE, CTAS>;
-  using C = PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes>;
+  auto kern = FUSED ? lstm_fused_kernel<BN, MODE, CTAS> : lstm_step_kernel<BN, MODE, CTAS>;
+  using C = std::conditional_t<FUSED, PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, kBiasBytes, 2>,
+                               PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes>>;
+  constexpr int kThreads = FUSED ? kFusedThreads : kNumThreads;
   static bool configured = false;
   if (!configured) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -358,7 +618,7 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
   const int grid = (m_tiles + CTAS - 1) / CTAS * CTAS * p.n_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kNumThreads);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -386,7 +646,7 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
       resident = clusters * CTAS;
     } else {
       int per_sm = 0;
-      AVC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kNumThreads, C::kSmemBytes));
+      AVC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, C::kSmemBytes));
       resident = per_sm * num_sms();
     }
     AVC_REQUIRE(resident >= grid, "avc_lstm_seq: persistent grid %d does not fit (%d CTAs resident)", grid, resident);
@@ -426,7 +686,10 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   AVC_REQUIRE(d->gate_group == 16 || d->gate_group == 32, "avc_lstm_seq: gate_group %d (16 or 32)", d->gate_group);
   AVC_REQUIRE(d->B > 0 && d->T > 0 && d->H > 0 && d->H % d->gate_group == 0, "avc_lstm_seq: bad shape B=%d T=%d H=%d",
               d->B, d->T, d->H);
-  AVC_REQUIRE(d->xproj && d->w_hh && d->hseq && d->c_state, "avc_lstm_seq: missing buffer");
+  const bool fused = d->xin != nullptr;
+  AVC_REQUIRE(d->w_hh && d->hseq && d->c_state, "avc_lstm_seq: missing buffer");
+  AVC_REQUIRE(fused ? (d->w_ih && d->bias && !d->xproj) : d->xproj != nullptr,
+              "avc_lstm_seq: give either xproj, or xin + w_ih + bias (fused input projection)");
   const int es = d->dtype == AVC_DTYPE_TF32 ? 4 : 2;
   const int kc = kRowBytes / es;
   AVC_REQUIRE(d->H % kc == 0, "avc_lstm_seq: H=%d must be a multiple of %d", d->H, kc);
@@ -447,9 +710,29 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
       return -3;
     if (!encode_tmap_2d(&p.tmap_w[part], es, wb, H, 4 * H, ld * es, kc, bn / ctas)) return -3;
   }
-  if (!encode_tmap_3d(&p.tmap_x, 4, d->xproj, 4 * H, (uint64_t)d->T, (uint64_t)d->B, 4 * H * 4,
-                      (uint64_t)d->T * 4 * H * 4, 32, 1, kBlockM))
-    return -3;
+  if (fused) {
+    // input sequence [B][T][xin_ld] holding xin_channels logical channels ([hi | lo] halves when split); channels past
+    // xin_channels are zero-filled by TMA and meet zero columns of the K-padded w_ih
+    const uint64_t cin = (uint64_t)d->xin_channels;
+    AVC_REQUIRE(d->xin_channels > 0 && (cin * es) % 16 == 0, "avc_lstm_seq: xin_channels=%d", d->xin_channels);
+    AVC_REQUIRE(d->xin_ld >= (long long)(split ? 2 * cin : cin), "avc_lstm_seq: xin_ld=%lld too small", d->xin_ld);
+    p.num_kx = (int)((cin + kc - 1) / kc);
+    const uint64_t kpad = (uint64_t)p.num_kx * kc;
+    const uint64_t ldw = split ? 2 * kpad : kpad;
+    for (int part = 0; part < (split ? 2 : 1); ++part) {
+      const char* xb = static_cast<const char*>(d->xin) + (size_t)part * cin * es;
+      const char* wb = static_cast<const char*>(d->w_ih) + (size_t)part * kpad * es;
+      if (!encode_tmap_3d(&p.tmap_xi[part], es, xb, cin, (uint64_t)d->T, (uint64_t)d->B, (uint64_t)d->xin_ld * es,
+                          (uint64_t)d->T * d->xin_ld * es, kc, 1, kBlockM))
+        return -3;
+      if (!encode_tmap_2d(&p.tmap_wi[part], es, wb, kpad, 4 * H, ldw * es, kc, bn / ctas)) return -3;
+    }
+    p.bias = d->bias;
+  } else {
+    if (!encode_tmap_3d(&p.tmap_x, 4, d->xproj, 4 * H, (uint64_t)d->T, (uint64_t)d->B, 4 * H * 4,
+                        (uint64_t)d->T * 4 * H * 4, 32, 1, kBlockM))
+      return -3;
+  }
   p.xproj = d->xproj;
   p.hseq = d->hseq;
   p.hseq_f32 = d->hseq_f32;
@@ -463,8 +746,10 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   p.kc_elems = kc;
   p.num_kb = d->H / kc;
   p.n_tiles = 4 * d->H / bn;
+#define AVC_LSTM_DISPATCH3(BN_, MODE_, CTAS_) \
+  return fused ? run<BN_, MODE_, CTAS_, true>(p, d, m_tiles, stream) : run<BN_, MODE_, CTAS_, false>(p, d, m_tiles, stream);
 #define AVC_LSTM_DISPATCH2(BN_, MODE_) \
-  return ctas == 2 ? run<BN_, MODE_, 2>(p, d, m_tiles, stream) : run<BN_, MODE_, 1>(p, d, m_tiles, stream);
+  if (ctas == 2) { AVC_LSTM_DISPATCH3(BN_, MODE_, 2) } else { AVC_LSTM_DISPATCH3(BN_, MODE_, 1) }
 #define AVC_LSTM_DISPATCH(BN_)                           \
   switch (d->dtype) {                                    \
     case AVC_DTYPE_TF32: AVC_LSTM_DISPATCH2(BN_, 0)      \
@@ -476,5 +761,6 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
     default: AVC_LSTM_DISPATCH(128)
   }
 #undef AVC_LSTM_DISPATCH
+#undef AVC_LSTM_DISPATCH3
 #undef AVC_LSTM_DISPATCH2
 }

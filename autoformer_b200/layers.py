@@ -1,4 +1,6 @@
 """Packed layer objects shared by the drop-in models: they own folded/re-packed weights and call ``ops``."""
+import os
+
 import torch
 
 from . import ops, packing
@@ -34,14 +36,30 @@ def conv_bn_layer(sd, prefix, precision, act):
     return ops.ConvGemm(*packing.pack_conv(w, b, precision), act=act, tag="conv")
 
 
-class LstmLayer:
-    """One uni-directional nn.LSTM layer: dense input projection + tensor-core recurrence."""
+def lstm_fused_default():
+    """AVC_LSTM_FUSED=0 selects the two-kernel form (dense input projection, then the recurrence) for A/B timing."""
+    return os.environ.get("AVC_LSTM_FUSED", "1") != "0"
 
-    def __init__(self, w_ih, w_hh, b_ih, b_hh, precision):
+
+class LstmLayer:
+    """One uni-directional nn.LSTM layer on the tensor-core recurrence kernel.  By default the input projection is
+    fused into that kernel (its MMAs fill the tensor pipe while the cell update and the grid barrier of the previous
+    frame are in flight); `fused=False` runs it as one dense GEMM per layer in front of the recurrence."""
+
+    def __init__(self, w_ih, w_hh, b_ih, b_hh, precision, fused=None):
         self.w_ih, self.w_hh, self.b_ih, self.b_hh = w_ih.detach(), w_hh.detach(), b_ih.detach(), b_hh.detach()
         self.precision = precision
         self.H = w_hh.shape[1]
+        self.C_in = w_ih.shape[1]
+        self.fused = lstm_fused_default() if fused is None else fused
         self._packs = {}
+        self._fused_packs = {}
+
+    def fused_packs(self, group):
+        if group not in self._fused_packs:
+            wih, bias = packing.pack_lstm_ih_fused(self.w_ih, self.b_ih, self.b_hh, self.precision, group)
+            self._fused_packs[group] = (wih, bias, packing.pack_lstm_hh(self.w_hh, self.precision, group))
+        return self._fused_packs[group]
 
     def packs(self, group):
         if group not in self._packs:
@@ -53,6 +71,10 @@ class LstmLayer:
 
     def __call__(self, x, B, T, hseq_f32=None, h_last=None, persistent=False):
         group = ops.choose_gate_group(B, self.H, persistent)
+        if self.fused:
+            wih, bias, hh = self.fused_packs(group)
+            return ops.lstm_seq(None, hh, B, T, self.H, self.precision, group, hseq_f32=hseq_f32, h_last=h_last,
+                                persistent=persistent, xin=x, w_ih=wih, bias=bias, c_in=self.C_in)
         ih, hh = self.packs(group)
         xp = torch.empty(B * T, 4 * self.H, dtype=torch.float32, device=x.device)
         ih(x, B, T, out2=xp)

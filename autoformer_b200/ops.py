@@ -204,12 +204,26 @@ def choose_gate_group(B, H, persistent=False, n_sm=148):
 
 
 def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False,
-             debug_clk=None):
-    """Run the recurrence of one uni-directional layer.  xproj [B*T][4H] fp32 (packed gate order, bias included)."""
+             debug_clk=None, xin=None, w_ih=None, bias=None, c_in=None):
+    """Run the recurrence of one uni-directional layer.  Either xproj [B*T][4H] fp32 (packed gate order, bias
+    included), or -- fused input projection -- the layer input xin [B][T][C'] in the operand format of `precision`
+    with w_ih / bias from packing.pack_lstm_ih_fused and c_in logical input channels."""
     lib = _lib.load()
-    _require_cuda(xproj, w_hh)
-    dev = xproj.device
-    assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
+    fused = xin is not None
+    _require_cuda(xin if fused else xproj, w_hh)
+    dev = w_hh.device
+    if fused:
+        assert xproj is None and w_ih is not None and bias is not None and c_in is not None
+        kp = (c_in + KC[precision] - 1) // KC[precision] * KC[precision]
+        assert xin.dim() == 3 and xin.shape[0] == B and xin.shape[1] == T and xin.dtype == TORCH_DTYPE[precision]
+        assert xin.shape[2] >= packing.act_channels(c_in, precision) and xin.stride(2) == 1
+        assert xin.stride(0) == T * xin.stride(1) and c_in % 8 == 0
+        assert w_ih.dtype == TORCH_DTYPE[precision] and w_ih.is_contiguous()
+        assert w_ih.shape == (4 * H, 2 * kp if precision == "fp32" else kp), (w_ih.shape, kp)
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == 4 * H
+        _require_cuda(w_ih, bias)
+    else:
+        assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
     wk = 2 * H if precision == "fp32" else H
     assert w_hh.dtype == TORCH_DTYPE[precision] and w_hh.shape == (4 * H, wk) and w_hh.is_contiguous()
     if hseq is None:
@@ -218,7 +232,11 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
     assert hseq.dtype == TORCH_DTYPE[precision]
     c_state = torch.empty(B, H, dtype=torch.float32, device=dev)
     d = _lib.LstmDesc()
-    d.xproj = xproj.data_ptr()
+    if fused:
+        d.xin, d.xin_channels, d.xin_ld = xin.data_ptr(), c_in, xin.stride(1)
+        d.w_ih, d.bias = w_ih.data_ptr(), bias.data_ptr()
+    else:
+        d.xproj = xproj.data_ptr()
     d.w_hh = w_hh.data_ptr()
     d.hseq = hseq.data_ptr()
     if hseq_f32 is not None:
@@ -238,7 +256,8 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
         d.grid_barrier = bar.data_ptr()
     if debug_clk is not None:
         d.debug_clk = debug_clk.data_ptr()
-    with PROFILER.span("lstm_step", flops=2.0 * 4 * H * H * B * T, launches=1 if persistent else T):
+    with PROFILER.span("lstm_step", flops=2.0 * 4 * H * (H + (c_in if fused else 0)) * B * T,
+                       launches=1 if persistent else T):
         _lib.check(lib.avc_lstm_seq(ctypes.byref(d), _stream()), "avc_lstm_seq")
     return hseq
 

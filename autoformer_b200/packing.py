@@ -153,6 +153,21 @@ def pack_lstm_ih(w_ih, b_ih, b_hh, precision, group):
     return pack_linear(w_ih[perm], (b_ih + b_hh)[perm], precision)
 
 
+def pack_lstm_ih_fused(w_ih, b_ih, b_hh, precision, group):
+    """W_ih for the recurrence kernel's fused input projection: gate-interleaved rows like W_hh, K zero-padded to whole
+    k-blocks, [w_hi | w_lo] halves in split precision.  Returns (W [4H][Kp or 2Kp], bias [4H] fp32 = b_ih + b_hh)."""
+    h, c_in = w_ih.shape[0] // 4, w_ih.shape[1]
+    perm = gate_permutation(h, group, w_ih.device)
+    kpad = _ceil_to(c_in, KC[precision])
+    w = torch.zeros(4 * h, kpad, dtype=torch.float32, device=w_ih.device)
+    w[:, :c_in] = w_ih[perm].float()
+    bias = (b_ih.float() + b_hh.float())[perm].contiguous()
+    if precision == "fp32":
+        hi, lo = split_bf16(w)
+        return torch.cat([hi, lo], dim=1).contiguous(), bias
+    return to_operand(w, precision).contiguous(), bias
+
+
 def pack_lstm_hh(w_hh, precision, group):
     h = w_hh.shape[1]
     perm = gate_permutation(h, group, w_hh.device)

@@ -313,8 +313,10 @@ def run_native(args):
     tensor_fams = {k: v for k, v in kernels.items() if "tflops" in v and k != "bilstm_small"}
     dom = max(tensor_fams, key=lambda k: tensor_fams[k]["ms_per_step"])
     dom_e = tensor_fams[dom]
-    kernel_name = {"lstm_step": "lstm_step_kernel", "conv": "conv_gemm_kernel", "inproj": "conv_gemm_kernel",
-                   "linear": "conv_gemm_kernel"}[dom]
+    from autoformer_b200.layers import lstm_fused_default
+    fused = lstm_fused_default()
+    kernel_name = {"lstm_step": "lstm_fused_kernel" if fused else "lstm_step_kernel", "conv": "conv_gemm_kernel",
+                   "inproj": "conv_gemm_kernel", "linear": "conv_gemm_kernel"}[dom]
     passes = {"fp32": 3, "tf32": 2, "bf16": 1}[args.precision]      # bf16-MMA-equivalent passes per algorithmic FLOP
     for v in kernels.values():
         if "tflops" in v:
@@ -328,8 +330,10 @@ def run_native(args):
         "algorithmic_flops_per_launch": dom_e["tflops"] * 1e12 * dom_e["ms_per_step"] * 1e-3 / max(1, dom_e["launches_per_step"]),
         "mma_passes_per_flop": passes,
         "issued_mma_frac_of_peak": dom_e["tflops"] * passes / pk["tflops_sustained"],
-        "note": "achieved = algorithmic FLOPs (2*4H*H per frame per layer for the recurrence) / CUDA-event time of the "
-                "launches; the split-bf16 'fp32' mode issues 3 bf16 MMA FLOPs per algorithmic FLOP, so frac <= 1/3",
+        "note": "achieved = algorithmic FLOPs (recurrence 2*4H*H per frame per layer"
+                + (" + its fused input projection 2*4H*C_in" if fused else "") + ") / CUDA-event time of the launches; "
+                "the split-bf16 'fp32' mode issues 3 bf16 MMA FLOPs per algorithmic FLOP, so frac <= 1/3 there "
+                "(issued_mma_frac_of_peak is the tensor-pipe figure)",
     }
 
     # NCCL is used only to gather per-rank records (frames, time, output checksum) -- no data-path collective
@@ -356,6 +360,7 @@ def run_native(args):
             "config": {"workload": "AutoVC(32,256,512,32) conversion forward (encoder+decoder+postnet), "
                                    f"{B} utterances x {T} frames x 80 mel per GPU (BASELINE.json configs[1])",
                        "batch_per_gpu": B, "frames": T, "precision": args.precision, "lstm_launch": lstm_mode,
+                       "lstm_input_projection": "fused into the recurrence kernel" if fused else "separate GEMM",
                        "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "l2": f"no explicit flush: each step streams ~{act_gb:.1f} GB of activations/projections, "
                              "far beyond the 126 MB L2"},

@@ -108,14 +108,14 @@ int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
 
 /*
  * Recurrence of one uni-directional LSTM layer with hidden size H (multiple of gate_group, >= 64):
- * for t = 0..T-1:  z = xproj[b,t,:] + W_hh h_{t-1};  c = s(z_f) c + s(z_i) tanh(z_g);  h = s(z_o) tanh(c)
+ * for t = 0..T-1:  z = xproj[b,t,:] + W_hh h_{t-1}   (xproj = W_ih x_t + b_ih + b_hh, precomputed or fused);  c = s(z_f) c + s(z_i) tanh(z_g);  h = s(z_o) tanh(c)
  * (nn.LSTM semantics, gate order i,f,g,o, zero initial state; factory/AutoVC.py:77,96,103,110;
  * factory/LstmDV.py:12,20).  Each step is a [B x H] x [H x 4H] tensor-core GEMM whose epilogue is the
  * cell update; rows of W_hh and columns of xproj are gate-interleaved in groups of `gate_group`
  * hidden units:  packed index = (u / G) * 4G + gate * G + (u % G).
  */
 typedef struct avc_lstm_desc {
-  const float* xproj;        /* [B*T][4H] fp32, packed column order, biases included */
+  const float* xproj;        /* [B*T][4H] fp32, packed column order, biases included; NULL when xin is given */
   const void* w_hh;          /* [4H][H] packed row order, dtype; dtype 2: [4H][2H] = [w_hi | w_lo] bf16 */
   void* hseq;                /* [B][T][H] dtype (dtype 2: [B][T][2H] split bf16): output sequence and recurrent operand */
   float* hseq_f32;           /* optional exact fp32 copy of the output sequence (may be NULL) */
@@ -127,6 +127,14 @@ typedef struct avc_lstm_desc {
   int persistent;            /* 0 = one launch per step; 1 = one cooperative launch, grid barrier per step */
   unsigned int* grid_barrier;/* 8 KB of scratch (persistent mode): one barrier counter per batch group */
   long long* debug_clk;      /* optional device buffer, 6 x int64 per (frame, CTA): clock64 stamps (profiling aid) */
+  /* Fused input projection (xproj == NULL): z = [x_t | h_{t-1}] [W_ih | W_hh]^T + bias inside the recurrence kernel;
+   * the x_t products of frame t+1 run on the tensor pipe while the cell update and grid barrier of frame t are in
+   * flight, and the [B*T][4H] fp32 projection is never materialised. */
+  const void* xin;           /* [B][T][xin_ld] layer input in the operand format of dtype (dtype 2: [hi | lo] halves) */
+  int xin_channels;          /* C_in logical channels (multiple of 8) */
+  long long xin_ld;          /* elements per input row */
+  const void* w_ih;          /* [4H][Kp] packed row order, Kp = C_in rounded up to the k-block; dtype 2: [4H][2Kp] */
+  const float* bias;         /* [4H] fp32 b_ih + b_hh, packed order */
 } avc_lstm_desc;
 
 int avc_lstm_seq(const avc_lstm_desc* d, void* stream);

@@ -1,0 +1,50 @@
+"""Per-frame clock64 breakdown of the fused (input projection + recurrence) persistent LSTM kernel (profiling aid).
+Stamps per (frame, CTA): 0 barrier passed (h producer), 1 first recurrent stage landed, 2 all MMAs issued,
+3 input-part MMAs issued, 4 accumulator ready (cell warps), 5 cell update done."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from autoformer_b200 import ops, packing
+
+
+def run(precision, B=512, T=128, H=1024, I=1024):
+    torch.manual_seed(0)
+    G = ops.choose_gate_group(B, H, True)
+    w_hh, w_ih = torch.randn(4 * H, H) * 0.03, torch.randn(4 * H, I) * 0.03
+    b = torch.zeros(4 * H)
+    hh = packing.pack_lstm_hh(w_hh, precision, G).cuda()
+    wih, bias = packing.pack_lstm_ih_fused(w_ih, b, b, precision, G)
+    wih, bias = wih.cuda(), bias.cuda()
+    x = packing.to_act(torch.randn(B, T, I), precision).cuda()
+    m_tiles = (B + 127) // 128
+    m_tiles = (m_tiles + 1) // 2 * 2 if m_tiles >= 2 else m_tiles
+    grid = m_tiles * (H // G)
+    kw = dict(xin=x, w_ih=wih, bias=bias, c_in=I, persistent=True)
+    for _ in range(2):
+        ops.lstm_seq(None, hh, B, T, H, precision, G, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.lstm_seq(None, hh, B, T, H, precision, G, **kw); e1.record()
+    torch.cuda.synchronize()
+    plain = e0.elapsed_time(e1) * 1e3 / T
+    dbg = torch.zeros(T * grid * 6, dtype=torch.int64, device="cuda")
+    ops.lstm_seq(None, hh, B, T, H, precision, G, debug_clk=dbg, **kw)
+    torch.cuda.synchronize()
+    d = dbg.view(T, grid, 6).double().cpu()
+    step = 2 if m_tiles >= 2 else 1
+    lead = d[10:T - 1, 0::step]
+    nxt = d[11:T, 0::step]
+    f = lambda a: f"{a.mean():.0f}"
+    print(f"fused {precision} B={B} H={H} I={I} G={G} grid={grid}: {plain:.2f} us/frame; cycles: "
+          f"barrier->first h stage {f(lead[..., 1] - lead[..., 0])}, h mainloop issue {f(lead[..., 2] - lead[..., 1])}, "
+          f"issue end->acc ready {f(lead[..., 4] - lead[..., 2])}, cell {f(lead[..., 5] - lead[..., 4])}, "
+          f"cell end->next barrier passed {f(nxt[..., 0] - lead[..., 5])}, "
+          f"x part issued relative to barrier {f(lead[..., 3] - lead[..., 0])} (negative = hidden), "
+          f"frame {f(nxt[..., 0] - lead[..., 0])}")
+
+
+if __name__ == "__main__":
+    for prec in ("fp32", "bf16", "tf32"):
+        run(prec, I=1024)
+    run("fp32", I=512)
+    run("fp32", H=512, I=320)
+    run("fp32", B=32, T=256, H=768, I=80)

@@ -98,12 +98,23 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
     return out if out is not None else (out2 if out2 is not None else out_raw)
 
 
-def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False):
+def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False,
+                  xin=None, w_ih=None, bias=None, c_in=None):
     if precision == "fp32":
         w = w_hh[:, :H].double() + w_hh[:, H:].double()
     else:
         w = w_hh.double()
-    xp = xproj.double().view(B, T, 4 * H)
+    if xin is not None:      # fused input projection: K zero-padded to whole k-blocks, [hi | lo] halves when split
+        assert xproj is None
+        kc = KC[precision]
+        kp = (c_in + kc - 1) // kc * kc
+        assert w_ih.shape == (4 * H, 2 * kp if precision == "fp32" else kp) and bias.shape == (4 * H,)
+        wi = (w_ih[:, :kp].double() + w_ih[:, kp:].double()) if precision == "fp32" else w_ih.double()
+        assert float(wi[:, c_in:].abs().max()) == 0.0 if kp > c_in else True
+        assert xin.shape[:2] == (B, T) and xin.dtype == packing.TORCH_DTYPE[precision]
+        xa = packing.act_to_float(xin[..., :packing.act_channels(c_in, precision)], precision).double()
+        xproj = xa @ wi[:, :c_in].t() + bias.double()
+    xp = xproj.double().reshape(B, T, 4 * H)
     h = torch.zeros(B, H, dtype=torch.float64)
     c = torch.zeros(B, H, dtype=torch.float64)
     outs = torch.zeros(B, T, H, dtype=torch.float64)

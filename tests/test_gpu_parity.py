@@ -83,11 +83,13 @@ def test_conv_gemm_residual_and_reflect_halo():
     assert rel_l2(packing.act_to_float(out, "fp32"), padded) < 5e-5
 
 
+@pytest.mark.parametrize("fused", [True, False])      # input projection inside the recurrence kernel / as its own GEMM
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("B,T,I,H,persistent", [(4, 8, 64, 128, False), (130, 16, 320, 512, False),
                                                 (64, 24, 512, 1024, False), (3, 12, 80, 768, False),
-                                                (130, 16, 320, 512, True), (256, 20, 512, 1024, True)])
-def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent):
+                                                (130, 16, 320, 512, True), (256, 20, 512, 1024, True),
+                                                (300, 9, 80, 768, True), (512, 12, 1024, 1024, True)])
+def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent, fused):
     from autoformer_b200 import layers, packing
     torch.manual_seed(H + T)
     k = 1.0 / H ** 0.5
@@ -95,7 +97,7 @@ def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent):
     b_ih, b_hh = (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
     x = torch.randn(B, T, I)
     ref = lstm_explicit(x.double(), w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
-    layer = layers.LstmLayer(w_ih.cuda(), w_hh.cuda(), b_ih.cuda(), b_hh.cuda(), precision)
+    layer = layers.LstmLayer(w_ih.cuda(), w_hh.cuda(), b_ih.cuda(), b_hh.cuda(), precision, fused=fused)
     f32 = torch.full((B, T, H), float("nan"), device="cuda")
     last = torch.full((B, H), float("nan"), device="cuda")
     hseq = layer(packing.to_act(x, precision).cuda(), B, T, hseq_f32=f32, h_last=last, persistent=persistent)
