@@ -71,11 +71,12 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target
 
 // Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
 // has already synchronised with this thread through the epi_done mbarrier.
-__device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target) {
+__device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target, long long* stamp = nullptr) {
   // release: everything this thread has observed (the cell warps' h stores, via epi_done) becomes visible to whoever
   // acquires the counter; the acquire load orders the TMA issue that follows.
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
   const long long t0 = clock64();
+  if (stamp) *stamp = t0;                                                  // arrival issued (after the release fence)
   unsigned int seen;
   do {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
     if (lane == 0 && leader) {
       RingState rs;
       for (int t = p.t_begin; t < p.t_end; ++t) {
-        long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+        long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 8 : nullptr;
         const uint32_t acc = tmem_base + static_cast<uint32_t>((t & 1) * BN);
         const int total = p.num_kx + (t > 0 ? p.num_kb : 0);
         for (int i = 0; i < total; ++i) {
@@ -485,16 +486,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
       uint32_t h_issued = 0;
       unsigned int sync_count = 0;
       for (int t = p.t_begin; t < p.t_end; ++t) {
-        long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+        long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 8 : nullptr;
         for (int kb = 0; kb < p.num_kx; ++kb) rs.advance<C::kStages>();
         if (t == 0) continue;
         if (t > p.t_begin) {
           // h_{t-1} comes from this launch: wait for this CTA's cell warps, then for every CTA that owns the same
           // utterances (all n-tiles of this m tile / m pair): one counter per batch group on its own 128-byte line
+          ++sync_count;
           mbar_wait(s.epi_done, epi_phase);
           epi_phase ^= 1u;
-          ++sync_count;
-          grid_arrive_wait(p.grid_barrier + 32 * (unit / p.n_tiles), sync_count * (unsigned)(p.n_tiles * CTAS));
+          if (dbg) dbg[6] = clock64();                                     // this CTA's cell warps are done
+          grid_arrive_wait(p.grid_barrier + 32 * (unit / p.n_tiles), sync_count * (unsigned)(p.n_tiles * CTAS),
+                           dbg ? dbg + 7 : nullptr);
         }
         if (dbg) dbg[0] = clock64();                                       // barrier passed
         fence_proxy_async_global();   // h_{t-1} was written with generic stores (other CTAs / previous launch)
@@ -538,7 +541,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
     const int u0 = n_tile * G;
     float* cp = p.c_state + (long long)b * p.H + u0;
     for (int t = p.t_begin; t < p.t_end; ++t) {
-      long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 6 : nullptr;
+      long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 8 : nullptr;
       const long long row = (long long)b * p.T + t;
       if (t == p.t_begin) {
 #pragma unroll

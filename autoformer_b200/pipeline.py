@@ -18,11 +18,18 @@ def pad_to_multiple(mel, multiple):
 
 
 @torch.no_grad()
-def convert(model, mel_src, emb_org, emb_trg):
-    """AutoVC conversion with pad -> convert -> trim.  Returns the converted mel (B, T, 80)."""
+def convert(model, mel_src, emb_org, emb_trg, mel_target=None):
+    """Conversion with pad -> convert -> trim.  Returns the converted mel (B, T, 80).
+
+    ``mel_target`` (B, T2, 80) selects the ``*_Adjust`` call of the reference's Evaluator (util/evaluate.py:79-80:
+    ``model(mel_source, emb_org, emb_trg, True, mel_target)``, 4-tuple return); otherwise the plain 3-argument call."""
     T = mel_src.shape[1]
     x, pad = pad_to_multiple(mel_src, model.freq)
-    _, mel_trans, _ = model(x, emb_org, emb_trg)                 # util/evaluate.py:83
+    if mel_target is not None:
+        xt, _ = pad_to_multiple(mel_target, model.freq)
+        _, _, mel_trans, _ = model(x, emb_org, emb_trg, True, xt)   # util/evaluate.py:79-80
+    else:
+        _, mel_trans, _ = model(x, emb_org, emb_trg)             # util/evaluate.py:83
     mel_trans = mel_trans.squeeze(1)                             # :85
     return mel_trans[:, :T, :] if pad else mel_trans             # :87-90
 

@@ -126,7 +126,7 @@ typedef struct avc_lstm_desc {
   int gate_group;            /* G: 16 or 32 */
   int persistent;            /* 0 = one launch per step; 1 = one cooperative launch, grid barrier per step */
   unsigned int* grid_barrier;/* 8 KB of scratch (persistent mode): one barrier counter per batch group */
-  long long* debug_clk;      /* optional device buffer, 6 x int64 per (frame, CTA): clock64 stamps (profiling aid) */
+  long long* debug_clk;      /* optional device buffer, 6 (fused input projection: 8) x int64 per (frame, CTA): clock64 stamps (profiling aid) */
   /* Fused input projection (xproj == NULL): z = [x_t | h_{t-1}] [W_ih | W_hh]^T + bias inside the recurrence kernel;
    * the x_t products of frame t+1 run on the tensor pipe while the cell update and grid barrier of frame t are in
    * flight, and the [B*T][4H] fp32 projection is never materialised. */

@@ -97,6 +97,31 @@ def golden_melgan(ref, name, B, T, wseed, xseed):
     print(name, tuple(wav.shape), "std", float(wav.std()), "mean", float(wav.mean()))
 
 
+def golden_adjust(ref, name, cls_name, args, B, T, wseed, xseed):
+    """*_Adjust models: 4-tuple return, training-style call (c_trg adjusted with x) and conversion-style call
+    (isConvert=True with a target utterance), plus the codes-only path."""
+    torch.manual_seed(0)
+    model = getattr(ref, cls_name)(*args).eval()
+    sd = seeded_state_dict(model.state_dict(), wseed)
+    model.load_state_dict(sd)
+    x = synthetic_mel(B, T, xseed)
+    x_target = synthetic_mel(B, T, xseed + 1000)
+    c_org = synthetic_speaker(B, xseed, "org")
+    c_trg = synthetic_speaker(B, xseed, "trg")
+    with torch.no_grad():
+        a = model(x, c_org, c_trg)
+        b = model(x, c_org, c_trg, True, x_target)
+        codes_only = model(x, c_org, None)
+        adj = model.adjust(x, c_org)
+    rec = dict(cls=cls_name, args=np.array(args), B=B, T=T, wseed=wseed, xseed=xseed, adjust_of_c_org=adj.numpy(),
+               codes_only=codes_only.numpy())
+    for tag, out in (("train", a), ("convert", b)):
+        for key, t in zip(("c_org", "mel", "mel_postnet", "codes"), out):
+            rec[f"{tag}_{key}"] = t.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "mel", tuple(a[1].shape), "|mel|", float(a[1].norm()), "|mel_convert|", float(b[1].norm()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -109,6 +134,9 @@ def main():
     golden_melgan(ref, "melgan_b2_t17", 2, 17, 5, 7)
     golden_autovc(ref, "metapool_b1_t176", "MetaPool", (44, 256, 512, 22), 1, 176, 6, 8)
     golden_autovc(ref, "metaconv_b1_t176", "MetaConv", (44, 256, 512, 22), 1, 176, 7, 9)
+    golden_adjust(ref, "autovc_adjust_b2_t64", "AutoVC_Adjust", (32, 256, 512, 32), 2, 64, 10, 11)
+    golden_adjust(ref, "metapool_adjust_b1_t176", "MetaPool_Adjust", (44, 256, 512, 22), 1, 176, 12, 13)
+    golden_adjust(ref, "metaconv_adjust_b1_t176", "MetaConv_Adjust", (44, 256, 512, 22), 1, 176, 14, 15)
 
 
 if __name__ == "__main__":

@@ -48,4 +48,8 @@ def load():
     ns.MetaConv = importlib.import_module("factory.MetaConv").MetaConv
     ns.LstmDV = importlib.import_module("factory.LstmDV").LstmDV
     ns.Generator = importlib.import_module("melgan.modules").Generator
+    ns.Adjust = importlib.import_module("factory.Adjust").Adjust
+    ns.AutoVC_Adjust = importlib.import_module("factory.AutoVC_Adjust").AutoVC_Adjust
+    ns.MetaPool_Adjust = importlib.import_module("factory.MetaPool_Adjust").MetaPool     # (sic) the file's class name
+    ns.MetaConv_Adjust = importlib.import_module("factory.MetaConv_Adjust").MetaConv_Adjust
     return ns

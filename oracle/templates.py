@@ -156,3 +156,26 @@ def meta_template(kind, dim_neck, dim, dim_pre, freq):
     sd["decoder.linear_projection.linear_layer.bias"] = _z(80)
     _postnet(sd)
     return sd
+
+
+def _adjust(sd, dim_emb, prefix="adjust", dim_cell=768):
+    """factory/Adjust.py:8-27."""
+    for i in range(3):
+        _conv_bn(sd, f"{prefix}.convolutions.{i}", 512, 80 + dim_emb if i == 0 else 512)
+    _lstm(sd, f"{prefix}.lstm", 512, dim_cell, 3)
+    sd[f"{prefix}.embedding.linear_layer.weight"] = _z(256, dim_cell)
+    sd[f"{prefix}.embedding.linear_layer.bias"] = _z(256)
+
+
+def autovc_adjust_template(dim_neck, dim_emb, dim_pre, freq):
+    """factory/AutoVC_Adjust.py:169-175: AutoVC + ``adjust``."""
+    sd = autovc_template(dim_neck, dim_emb, dim_pre, freq)
+    _adjust(sd, dim_emb)
+    return sd
+
+
+def meta_adjust_template(kind, dim_neck, dim_emb, dim_pre, freq):
+    """factory/MetaPool_Adjust.py:250-256 / MetaConv_Adjust.py: Meta model + ``adjust``."""
+    sd = meta_template(kind, dim_neck, dim_emb, dim_pre, freq)
+    _adjust(sd, dim_emb)
+    return sd

@@ -445,3 +445,29 @@ def test_streaming_converter_host_to_host():
         ref = m(*(t.cuda() for t in b))
         for u, v in zip(r, ref):
             assert not u.is_cuda and torch.equal(u, v.cpu())
+
+
+@pytest.mark.parametrize("name,kind", [("autovc_adjust_b2_t64", None), ("metapool_adjust_b1_t176", "pool"),
+                                       ("metaconv_adjust_b1_t176", "conv")])
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 5e-2)])
+def test_adjust_models_parity_and_golden(name, kind, precision, tol):
+    """AutoVC_Adjust / MetaPool_Adjust / MetaConv_Adjust on the GPU kernels against the reference's
+    own outputs: training-style call, conversion-style call with a target utterance, codes-only call, bare Adjust."""
+    from tests.test_host_logic import _adjust_model
+    from tests.test_oracle_golden import adjust_case
+    g, args, sd, i, fwd = adjust_case(name, kind)
+    m = _adjust_model(kind, args, sd).cuda()
+    m.precision = precision
+    c = {k: v.cuda() for k, v in i.items()}
+    G = lambda k: torch.from_numpy(g[k])
+    out = m(c["x"], c["c_org"], c["c_trg"])
+    conv = m(c["x"], c["c_org"], c["c_trg"], True, c["x_target"])
+    for tag, o in (("train", out), ("convert", conv)):
+        assert len(o) == 4
+        for key, t in zip(("c_org", "mel", "mel_postnet", "codes"), o):
+            assert rel_l2(t, G(f"{tag}_{key}")) < tol, (tag, key, rel_l2(t, G(f"{tag}_{key}")))
+    assert rel_l2(m(c["x"], c["c_org"], None), G("codes_only")) < tol
+    assert rel_l2(m.adjust(c["x"], c["c_org"]), G("adjust_of_c_org")) < tol
+    if precision == "fp32":                     # negative control: another utterance must not pass
+        bad = m(c["x_target"], c["c_org"], c["c_trg"])
+        assert rel_l2(bad[2], G("train_mel_postnet")) > 1e-2

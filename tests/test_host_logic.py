@@ -110,3 +110,31 @@ def test_meta_host_logic(cpu_kernels, kind):
     assert rel_l2(m(x, c_org, None), ref[2]) < 1e-4
     with pytest.raises(RuntimeError):
         m(synthetic_mel(1, 128, 8), c_org, c_trg)          # the reference's hard-wired T = 176
+
+
+def _adjust_model(kind, args, sd):
+    from autoformer_b200.factory.AutoVC_Adjust import AutoVC_Adjust
+    from autoformer_b200.factory.MetaConv_Adjust import MetaConv_Adjust
+    from autoformer_b200.factory.MetaPool_Adjust import MetaPool as MetaPool_Adjust
+    m = {None: AutoVC_Adjust, "pool": MetaPool_Adjust, "conv": MetaConv_Adjust}[kind](*args)
+    m.load_state_dict(sd)                      # the reference's key names, incl. adjust.*
+    return m.eval()
+
+
+@pytest.mark.parametrize("name,kind", [("autovc_adjust_b2_t64", None), ("metapool_adjust_b1_t176", "pool"),
+                                       ("metaconv_adjust_b1_t176", "conv")])
+def test_adjust_models_host_logic(cpu_kernels, name, kind):
+    """*_Adjust drop-ins: 4-tuple return, isConvert / x_target routing, codes-only path, checked
+    against the reference's own outputs (golden) through the CPU stand-ins."""
+    from tests.test_oracle_golden import adjust_case
+    g, args, sd, i, _ = adjust_case(name, kind)
+    m = _adjust_model(kind, args, sd)
+    G = lambda k: torch.from_numpy(g[k])
+    out = m(i["x"], i["c_org"], i["c_trg"])
+    conv = m(i["x"], i["c_org"], i["c_trg"], True, i["x_target"])
+    for tag, o in (("train", out), ("convert", conv)):
+        assert len(o) == 4
+        for key, t in zip(("c_org", "mel", "mel_postnet", "codes"), o):
+            assert t.shape == g[f"{tag}_{key}"].shape and rel_l2(t, G(f"{tag}_{key}")) < 2e-4, (tag, key)
+    assert rel_l2(m(i["x"], i["c_org"], None), G("codes_only")) < 2e-4
+    assert rel_l2(m.adjust(i["x"], i["c_org"]), G("adjust_of_c_org")) < 2e-4
