@@ -94,28 +94,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
   const int rsub = lane >> 3;            // this lane's row inside a group of 4 rows
   const int tb = 1 << p.tb_log2;
   const int t_out = p.T * p.phases;      // output frames per utterance
-  // the 8 rows this lane stores (one per 4-row group) are the same for every chunk: precompute their row indices
-  long long lrow[8], orow[8];
-  int time0[8];
-  unsigned valid = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = q * 32 + 4 * i + rsub;
-    const int b = b0 + (m >> p.tb_log2);
-    const int t = t0 + (m & (tb - 1));
-    if (b < p.B && t < p.T) valid |= 1u << i;
-    time0[i] = t * p.phases;
-    lrow[i] = (long long)b * t_out + time0[i];
-    orow[i] = (long long)b * p.out_rows_per_utt + p.out_row0 + time0[i];
-  }
   const bool has_res = p.residual != nullptr, res_after = p.res_after != 0;
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  // 32-column chunks of this tile that hold real output channels.  With a single one (N <= 32: the late MelGAN
+  // stages) the two warps of a lane quarter split its ROWS instead of idling one of them.
+  const int chunks = min(BN / 32, (p.N - n0 + 31) / 32);
+  const bool split_rows = chunks == 1;
+  const int c_first = split_rows ? 0 : half;
+  const int g_first = split_rows ? half * 4 : 0, g_last = split_rows ? half * 4 + 4 : 8;
+  // bias of the first chunk is requested before anything else so its L2 latency overlaps the TMEM load; the bias of
+  // chunk c + 2 is requested while chunk c is being stored
+  auto load_bias = [&](int c32) {
+    const int n = n0 + c32 * 32 + cl;
+    return n < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 bv_next = c_first < chunks ? load_bias(c_first) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // The row loop is deliberately NOT fully unrolled: with 8 copies of the (mode x output x halo) store code the
+  // epilogue was ~4000 instructions, and layers with few k-blocks per tile (MelGAN stages 2-3, 1x1 convolutions) spent
+  // 7 K cycles per 32-column chunk fetching instructions (ncu: 20 % stall_no_inst; time per tile independent of K).
 #pragma unroll 1
-  for (int c32 = half; c32 < BN / 32; c32 += kEpiWarps / 4) {
+  for (int c32 = c_first; c32 < chunks; c32 += kEpiWarps / 4) {
     uint32_t v[32];
     tmem_ld_32x32(lane_addr + c32 * 32, v);
     tmem_ld_wait();
-    if (c32 + kEpiWarps / 4 >= BN / 32) {   // that was this warp's last read of the accumulator buffer: hand it back
+    if (c32 + kEpiWarps / 4 >= chunks) {    // that was this warp's last read of the accumulator buffer: hand it back
       tc_fence_before();
       if (lane == 0) mbar_arrive_leader(tmem_empty_bar);
     }
@@ -126,15 +128,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
                       __uint_as_float(v[4 * j + 3]));
     __syncwarp();
     const int n = n0 + c32 * 32 + cl;
+    const float4 bv = bv_next;
+    if (c32 + kEpiWarps / 4 < chunks) bv_next = load_bias(c32 + kEpiWarps / 4);
     if (n < p.N) {
       const int phase = p.phases == 1 ? 0 : n / p.cs;
       const int c = n - phase * p.cs;
-      const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (valid & (1u << i)) {
+#pragma unroll 2
+      for (int i = g_first; i < g_last; ++i) {
+        const int m = q * 32 + 4 * i + rsub;
+        const int b = b0 + (m >> p.tb_log2);
+        const int t = t0 + (m & (tb - 1));
+        if (b < p.B && t < p.T) {
+          const int time = t * p.phases + phase;
+          const long long lr = (long long)b * t_out + time;
           const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
-          const long long lr = lrow[i] + phase;
           float o[4] = {a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w};
           float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (has_res) {
@@ -146,14 +153,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
           for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
           if (has_res && res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
           if (p.out) {
-            const long long orw = orow[i] + phase;
+            const long long orw = (long long)b * p.out_rows_per_utt + p.out_row0 + time;
             store4(p.out, p.out_mode, p.out_round, orw, p.out_ld, c, p.cs, o);
-            if (p.out_reflect > 0) {   // reflected halo rows (ReflectionPad1d of the consumer)
-              const int time = time0[i] + phase;
-              if (time >= 1 && time <= p.out_reflect)
-                store4(p.out, p.out_mode, p.out_round, orw - 2LL * time, p.out_ld, c, p.cs, o);
-              if (time <= t_out - 2 && time >= t_out - 1 - p.out_reflect)
-                store4(p.out, p.out_mode, p.out_round, orw + 2LL * (t_out - 1 - time), p.out_ld, c, p.cs, o);
+            if (p.out_reflect > 0) {   // reflected halo rows (ReflectionPad1d of the consumer); rare: one shared copy
+              long long mirror = -1;
+              if (time >= 1 && time <= p.out_reflect) mirror = orw - 2LL * time;
+              if (mirror >= 0) store4(p.out, p.out_mode, p.out_round, mirror, p.out_ld, c, p.cs, o);
+              mirror = -1;
+              if (time <= t_out - 2 && time >= t_out - 1 - p.out_reflect) mirror = orw + 2LL * (t_out - 1 - time);
+              if (mirror >= 0) store4(p.out, p.out_mode, p.out_round, mirror, p.out_ld, c, p.cs, o);
             }
           }
           if (p.out2) *reinterpret_cast<float4*>(p.out2 + lr * p.out2_ld + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -161,6 +169,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
       }
     }
     __syncwarp();   // the staging tile is overwritten by the next chunk
+  }
+  if (c_first >= chunks) {   // a warp without a chunk (cannot happen while every n-tile holds a real column) still hands back
+    tc_fence_before();
+    if (lane == 0) mbar_arrive_leader(tmem_empty_bar);
   }
 }
 
