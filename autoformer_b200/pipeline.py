@@ -39,8 +39,14 @@ def convert_and_vocode(embedder, model, generator, mel_src, mel_trg_ref):
     """mel_src (B, T, 80): utterances to convert; mel_trg_ref (B, T2, 80): utterances of the target speakers.
 
     Returns (converted mel (B, T, 80), waveform (B, 256 T), emb_org, emb_trg)."""
-    emb_org = embedder(mel_src)                                  # LstmDV d-vectors (factory/LstmDV.py:19-24)
-    emb_trg = embedder(mel_trg_ref)
+    if mel_src.shape == mel_trg_ref.shape:
+        # utterances are independent in the embedder, so both sets share one launch sequence: at B = 32 the LSTM
+        # recurrences are latency-bound and twice the rows per frame cost almost nothing extra
+        emb = embedder(torch.cat((mel_src, mel_trg_ref), dim=0))     # LstmDV d-vectors (factory/LstmDV.py:19-24)
+        emb_org, emb_trg = emb[:mel_src.shape[0]], emb[mel_src.shape[0]:]
+    else:
+        emb_org = embedder(mel_src)
+        emb_trg = embedder(mel_trg_ref)
     mel_trans = convert(model, mel_src, emb_org, emb_trg)
     wav = generator(mel_trans.transpose(2, 1).contiguous()).squeeze(1)   # MelVocoder.inverse (interface.py:43-53)
     return mel_trans, wav, emb_org, emb_trg

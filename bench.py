@@ -57,6 +57,33 @@ def peaks():
     return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+class stdout_to_stderr:
+    """stdout carries exactly ONE JSON line.  NCCL prints its version banner to the process's file descriptor 1 when the
+    first communicator is created (NCCL_DEBUG=VERSION from the environment or from /etc/nccl.conf), so the descriptor
+    itself is pointed at stderr while the process group comes up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+def init_nccl(dev):
+    import torch
+    import torch.distributed as dist
+    with stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)                     # forces communicator creation (and the banner) inside the redirect
+        torch.cuda.synchronize()
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -180,7 +207,7 @@ def run_native(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     _lib.load()
 
     B, T = args.batch, args.frames
@@ -395,7 +422,7 @@ def run_sweep(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     torch.manual_seed(1234)
     model = AutoVC(*MODEL_ARGS).to(dev).eval()
     model.precision = args.precision
@@ -462,8 +489,8 @@ def run_sweep(args):
 
 def main():
     # stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints to stdout) out of it
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "WARN").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # an explicit value also overrides /etc/nccl.conf
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
