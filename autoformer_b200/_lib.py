@@ -13,7 +13,7 @@ ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU
 EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm", "avc_lstm_seq",
            "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_transpose_pad",
            "avc_conv_to_mono_tanh", "avc_gn_stats", "avc_gn_pool_residual", "avc_gn_apply", "avc_patchify",
-           "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes"]
+           "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes", "avc_global_stats", "avc_adain"]
 
 
 MAX_SOURCES = 4
@@ -129,6 +129,9 @@ def load():
     lib.avc_ln_transpose.argtypes = [vp, vp, vp, ci, vp, ci, ci, vp, vp, ci, ci, ci, vp]
     lib.avc_meta_decoder_input.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.avc_gather_codes.argtypes = [vp, vp, ci, ci, ci, ci, vp]
+    lib.avc_global_stats.argtypes = [vp, ctypes.c_longlong, vp, vp, vp]
+    lib.avc_adain.argtypes = [vp, vp, vp, vp, vp, ci, ci, ctypes.c_longlong, ci, vp]
+    lib.avc_global_stats.restype = lib.avc_adain.restype = ctypes.c_int
     for fn in (lib.avc_gn_stats, lib.avc_gn_pool_residual, lib.avc_gn_apply, lib.avc_patchify, lib.avc_ln_transpose,
                lib.avc_meta_decoder_input, lib.avc_gather_codes):
         fn.restype = ctypes.c_int

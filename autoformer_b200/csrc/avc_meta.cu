@@ -102,6 +102,78 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------- batch-global mean / unbiased std (AdaIN "2" variants)
+// x.mean(), x.std() over ALL elements of a tensor (factory/AutoVC2.py:60, factory/Norm.py:91-93).  Two deterministic
+// stages: kGlobalParts CTAs write double partial sums in a fixed order, one CTA finishes.
+constexpr int kGlobalParts = 256;
+
+__global__ void __launch_bounds__(256) global_stats_partial_kernel(const float* __restrict__ x, long long n4,
+                                                                   double* __restrict__ part) {
+  const float4* xs = reinterpret_cast<const float4*>(x);
+  double s = 0.0, ss = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(xs + i);
+    s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+    ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      a += red[0][i];
+      b += red[1][i];
+    }
+    part[2 * blockIdx.x] = a;
+    part[2 * blockIdx.x + 1] = b;
+  }
+}
+
+__global__ void global_stats_final_kernel(const double* __restrict__ part, int parts, long long n,
+                                          float* __restrict__ stats) {
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < parts; ++i) {
+      a += part[2 * i];
+      b += part[2 * i + 1];
+    }
+    const double mean = a / (double)n;
+    double var = (b - (double)n * mean * mean) / (double)(n - 1);      // torch.std(): Bessel-corrected
+    if (var < 0.0) var = 0.0;
+    stats[0] = (float)mean;
+    stats[1] = (float)sqrt(var);
+  }
+}
+
+// ---------------------------------------------------------------- AdaIN: (x - mean_x) / std_x * std_t + mu_t
+__global__ void __launch_bounds__(256) adain_kernel(const float* __restrict__ x, const float* __restrict__ xs,
+                                                    const float* __restrict__ ts, float* __restrict__ out_f32,
+                                                    void* __restrict__ out_op, int mode, int round, long long total4,
+                                                    int C) {
+  const int c4n = C >> 2;
+  const float mean = __ldg(xs), inv = 1.0f / __ldg(xs + 1), mu = __ldg(ts), sd = __ldg(ts + 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c4n;
+    const int c = static_cast<int>(i - row * c4n) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + row * C + c));
+    float4 y;      // same operation order as the reference: ((x - mean) / std) * std_t + mu_t
+    y.x = (v.x - mean) * inv * sd + mu;
+    y.y = (v.y - mean) * inv * sd + mu;
+    y.z = (v.z - mean) * inv * sd + mu;
+    y.w = (v.w - mean) * inv * sd + mu;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
+    if (out_op) store_op4(out_op, mode, round, row, op_ld(C, mode), c, C, y);
+  }
+}
+
 // ---------------------------------------------------------------- patchify (+ GroupNorm(1, S))
 // image I[h][w] = a[b][w][h] (h = channel, w = length).  token n = (h/p)*(S/p) + w/p, feature f = (h%p)*p + w%p.
 // One thread per (w, h/4): reads 4 consecutive channels, writes 4 features p apart.
@@ -362,6 +434,32 @@ extern "C" int avc_gather_codes(const float* out, float* codes, int B, int T, in
   AVC_REQUIRE(out && codes && B > 0 && T > 0 && H > 0 && freq > 0 && T % freq == 0, "avc_gather_codes: bad arguments");
   const long long total = (long long)B * (T / freq) * 2 * H;
   gather_codes_kernel<<<grid_for(total), 256, 0, stream>>>(out, codes, total, T, H, freq);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_global_stats(const float* x, long long n, float* stats, double* scratch, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(x && stats && scratch && n > 1 && n % 4 == 0, "avc_global_stats: bad arguments n=%lld", n);
+  int parts = grid_for(n / 4);
+  if (parts > kGlobalParts) parts = kGlobalParts;
+  global_stats_partial_kernel<<<parts, 256, 0, stream>>>(x, n / 4, scratch);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  global_stats_final_kernel<<<1, 32, 0, stream>>>(scratch, parts, n, stats);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+
+extern "C" int avc_adain(const float* x, const float* x_stats, const float* t_stats, float* out_f32, void* out_op,
+                         int out_dtype, int out_round_tf32, long long rows, int C, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(x && x_stats && t_stats && (out_f32 || out_op), "avc_adain: null buffer");
+  AVC_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 2, "avc_adain: bad shape");
+  const long long total4 = rows * (C / 4);
+  adain_kernel<<<grid_for(total4), 256, 0, stream>>>(x, x_stats, t_stats, out_f32, out_op, out_dtype, out_round_tf32,
+                                                     total4, C);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -90,6 +90,13 @@ class AutoVC(nn.Module):
     def _plan(self):
         return self._cache.get(self, (self.precision,), lambda: _Plan(self, self.precision))
 
+    # hooks of the AdaIN "2" variants (factory/_adain.py); the plain model uses the mel as is and the plain postnet
+    def _encoder_features(self, x, plan, B, T):
+        return x
+
+    def _run_postnet(self, plan, mel_op, mel, B, T, taps):
+        return plan.postnet(mel_op, mel, B, T, taps)
+
     @torch.no_grad()
     def forward(self, x, c_org, c_trg):
         if self.training and not self._warned_train:
@@ -113,6 +120,7 @@ class AutoVC(nn.Module):
             taps.clear()
 
         # ---- encoder: concat speaker code, 3x conv+BN+ReLU, BiLSTM, code down-sampling (AutoVC.py:45-68)
+        x = self._encoder_features(x, plan, B, T)
         h = ops.concat_bcast(x, c_org, T, 1, prec)
         for i, conv in enumerate(plan.enc_convs):
             o = ops.alloc_act(B, T, 512, prec, dev)
@@ -152,7 +160,7 @@ class AutoVC(nn.Module):
         plan.linear(h, B, T, out=mel_op, out2=mel.view(B * T, 80))
 
         # ---- postnet + residual (AutoVC.py:173-179, 206-209)
-        post = plan.postnet(mel_op, mel, B, T, taps)
+        post = self._run_postnet(plan, mel_op, mel, B, T, taps)
         if taps is not None:
             taps["mel"] = mel
             taps["mel_postnet"] = post

@@ -231,6 +231,13 @@ class MetaBase(nn.Module):
     def _plan(self):
         return self._cache.get(self, (self.precision,), lambda: _Plan(self, self.KIND, self.precision))
 
+    # hooks of the AdaIN "2" variants (factory/_adain.py)
+    def _encoder_features(self, x, plan, B, T):
+        return x
+
+    def _run_postnet(self, plan, mel_op, mel, B, T, taps):
+        return plan.postnet(mel_op, mel, B, T, taps)
+
     @torch.no_grad()
     def forward(self, x, c_org, c_trg):
         if self.training and not self._warned_train:
@@ -257,6 +264,7 @@ class MetaBase(nn.Module):
             taps.clear()
 
         # ---- encoder (MetaPool.py:109-133)
+        x = self._encoder_features(x, plan, B, T)
         h = ops.concat_bcast(x, c_org, T, 1, prec)
         xe = torch.empty(B, T, 512, dtype=torch.float32, device=dev)
         plan.enc_embed(h, B, T, out2=xe.view(B * T, 512))
@@ -302,7 +310,7 @@ class MetaBase(nn.Module):
         mel_op = ops.alloc_act(B, T, 80, prec, dev)
         plan.linear(c2t, B, T, out=mel_op, out2=mel.view(B * T, 80))               # Linear(88 -> 80)
 
-        post = plan.postnet(mel_op, mel, B, T, taps)
+        post = self._run_postnet(plan, mel_op, mel, B, T, taps)
         if taps is not None:
             taps["mel"] = mel
             taps["mel_postnet"] = post

@@ -139,8 +139,8 @@ class Postnet:
         self.convs = [conv_bn_layer(sd, f"{prefix}.convolutions.{i}", precision, "tanh" if i < 4 else "none")
                       for i in range(5)]
 
-    def __call__(self, mel_op, mel_f32, B, T, taps=None):
-        """mel_op: [B][T][80] operand dtype; mel_f32: exact fp32 [B][T][80].  Returns mel + postnet(mel), fp32."""
+    def hidden(self, mel_op, B, T, taps=None):
+        """The four conv+BN+tanh layers: [B][T][80] -> [B][T][512], operand format."""
         h = mel_op
         for i in range(4):
             o = ops.alloc_act(B, T, 512, self.precision, h.device)
@@ -148,6 +148,11 @@ class Postnet:
             h = o
             if taps is not None:
                 taps[f"post_conv{i}"] = packing.act_to_float(h, self.precision)
+        return h
+
+    def __call__(self, mel_op, mel_f32, B, T, taps=None):
+        """mel_op: [B][T][80] operand dtype; mel_f32: exact fp32 [B][T][80].  Returns mel + postnet(mel), fp32."""
+        h = self.hidden(mel_op, B, T, taps)
         out = torch.empty(B, T, 80, dtype=torch.float32, device=h.device)
         self.convs[4](h, B, T, out2=out.view(B * T, 80), residual=mel_f32.view(B * T, 80))
         return out

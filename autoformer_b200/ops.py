@@ -440,3 +440,33 @@ def gather_codes(out, H, freq):
     codes = torch.empty(B, T // freq, 2 * H, dtype=torch.float32, device=out.device)
     _lib.check(lib.avc_gather_codes(out.data_ptr(), codes.data_ptr(), B, T, H, freq, _stream()), "avc_gather_codes")
     return codes
+
+
+# ------------------------------------------------------------------------------------------------ AdaIN "2" variants
+def global_stats(x, out=None):
+    """x fp32 (any shape) -> out [2] = (x.mean(), x.std()) over ALL elements, torch defaults (Bessel-corrected std)."""
+    lib = _lib.load()
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    if out is None:
+        out = torch.empty(2, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(512, dtype=torch.float64, device=x.device)
+    with PROFILER.span("global_stats", bytes=4.0 * x.numel(), launches=2):
+        _lib.check(lib.avc_global_stats(x.data_ptr(), x.numel(), out.data_ptr(), scratch.data_ptr(), _stream()),
+                   "avc_global_stats")
+    return out
+
+
+def adain(x, x_stats, t_stats, precision, want_f32=False):
+    """x [B][T][C] fp32 -> ((x - x_stats[0]) / x_stats[1] * t_stats[1] + t_stats[0]) in operand format (+ fp32 copy)."""
+    lib = _lib.load()
+    _require_cuda(x, x_stats, t_stats)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    assert x_stats.dtype == torch.float32 and t_stats.dtype == torch.float32 and x_stats.numel() == 2 and t_stats.numel() == 2
+    B, T, C = x.shape
+    out_op = alloc_act(B, T, C, precision, x.device)
+    out_f32 = torch.empty_like(x) if want_f32 else None
+    with PROFILER.span("adain", bytes=4.0 * x.numel() * 2):
+        _lib.check(lib.avc_adain(x.data_ptr(), x_stats.data_ptr(), t_stats.data_ptr(), _ptr(out_f32), out_op.data_ptr(),
+                                 _dt(precision), 1, B * T, C, _stream()), "avc_adain")
+    return out_op, out_f32

@@ -226,6 +226,18 @@ int avc_meta_decoder_input(const float* codes, const float* c_trg, void* out_op,
  * codes[b][j] = [ out[b][j*freq + freq-1][0:H] || out[b][j*freq][H:2H] ],  out [B][T][2H] fp32. */
 int avc_gather_codes(const float* out, float* codes, int B, int T, int H, int freq, void* stream);
 
+/*
+ * AdaIN "2" variants (factory/AutoVC2.py, MetaPool2.py, MetaConv2.py).
+ * avc_global_stats: stats = {x.mean(), x.std()} over ALL n fp32 elements (torch defaults: Bessel-corrected std), as the
+ *   encoder records after each feature_pre_extract layer (factory/AutoVC2.py:57-60).  scratch: 512 doubles.
+ * avc_adain: out = (x - x_stats[0]) / x_stats[1] * t_stats[1] + t_stats[0]   (factory/Norm.py:86-94, AutoVC2.py:197-198)
+ *   x [rows][C] fp32 -> out_f32 [rows][C] and/or out_op (operand format); the four scalars are read from device memory
+ *   so a conversion never synchronises with the host.
+ */
+int avc_global_stats(const float* x, long long n, float* stats, double* scratch, void* stream);
+int avc_adain(const float* x, const float* x_stats, const float* t_stats, float* out_f32, void* out_op, int out_dtype,
+              int out_round_tf32, long long rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

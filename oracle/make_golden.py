@@ -122,6 +122,32 @@ def golden_adjust(ref, name, cls_name, args, B, T, wseed, xseed):
     print(name, "mel", tuple(a[1].shape), "|mel|", float(a[1].norm()), "|mel_convert|", float(b[1].norm()))
 
 
+def golden_adain(ref, name, cls_name, args, B, T, wseed, xseed):
+    """AdaIN "2" variants: features-only call, self-styled conversion, conversion styled with another batch's features
+    (the Evaluator's isAdain recipe, util/evaluate.py:81-82)."""
+    torch.manual_seed(0)
+    model = getattr(ref, cls_name)(*args).eval()
+    sd = seeded_state_dict(model.state_dict(), wseed)
+    model.load_state_dict(sd)
+    x = synthetic_mel(B, T, xseed)
+    x_other = synthetic_mel(B, T, xseed + 1000)
+    c_org = synthetic_speaker(B, xseed, "org")
+    c_trg = synthetic_speaker(B, xseed, "trg")
+    with torch.no_grad():
+        codes, feats = model(x, c_org, None, None)
+        _, feats_other = model(x_other, c_org, None, None)
+        own = model(x, c_org, c_trg)
+        styled = model(x, c_org, c_trg, feats_other)
+    rec = dict(cls=cls_name, args=np.array(args), B=B, T=T, wseed=wseed, xseed=xseed, codes_only=codes.numpy(),
+               features=np.array([[float(m), float(s)] for m, s in feats], dtype=np.float64),
+               features_other=np.array([[float(m), float(s)] for m, s in feats_other], dtype=np.float64))
+    for tag, out in (("own", own), ("styled", styled)):
+        for key, t in zip(("mel", "mel_postnet", "codes"), out):
+            rec[f"{tag}_{key}"] = t.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "|post own|", float(own[1].norm()), "|post styled|", float(styled[1].norm()), rec["features"].tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -137,6 +163,9 @@ def main():
     golden_adjust(ref, "autovc_adjust_b2_t64", "AutoVC_Adjust", (32, 256, 512, 32), 2, 64, 10, 11)
     golden_adjust(ref, "metapool_adjust_b1_t176", "MetaPool_Adjust", (44, 256, 512, 22), 1, 176, 12, 13)
     golden_adjust(ref, "metaconv_adjust_b1_t176", "MetaConv_Adjust", (44, 256, 512, 22), 1, 176, 14, 15)
+    golden_adain(ref, "autovc2_b2_t64", "AutoVC2", (32, 256, 512, 32), 2, 64, 16, 17)
+    golden_adain(ref, "metapool2_b1_t176", "MetaPool2", (44, 256, 512, 22), 1, 176, 18, 19)
+    golden_adain(ref, "metaconv2_b1_t176", "MetaConv2", (44, 256, 512, 22), 1, 176, 20, 21)
 
 
 if __name__ == "__main__":

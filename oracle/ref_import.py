@@ -52,4 +52,7 @@ def load():
     ns.AutoVC_Adjust = importlib.import_module("factory.AutoVC_Adjust").AutoVC_Adjust
     ns.MetaPool_Adjust = importlib.import_module("factory.MetaPool_Adjust").MetaPool     # (sic) the file's class name
     ns.MetaConv_Adjust = importlib.import_module("factory.MetaConv_Adjust").MetaConv_Adjust
+    ns.AutoVC2 = importlib.import_module("factory.AutoVC2").AutoVC2
+    ns.MetaPool2 = importlib.import_module("factory.MetaPool2").MetaPool2
+    ns.MetaConv2 = importlib.import_module("factory.MetaConv2").MetaConv2
     return ns

@@ -179,3 +179,23 @@ def meta_adjust_template(kind, dim_neck, dim_emb, dim_pre, freq):
     sd = meta_template(kind, dim_neck, dim_emb, dim_pre, freq)
     _adjust(sd, dim_emb)
     return sd
+
+
+def _adain_parts(sd):
+    """factory/AutoVC2.py:19-33 (encoder.feature_pre_extract) and :176-190 (postnet.feature_last_combine)."""
+    for i in range(3):
+        _conv_bn(sd, f"encoder.feature_pre_extract.{i}", 80, 80)
+        sd[f"postnet.feature_last_combine.{i}.0.conv.weight"] = _z(80, 80, 5)
+        sd[f"postnet.feature_last_combine.{i}.0.conv.bias"] = _z(80)
+
+
+def autovc2_template(dim_neck, dim_emb, dim_pre, freq):
+    sd = autovc_template(dim_neck, dim_emb, dim_pre, freq)
+    _adain_parts(sd)
+    return sd
+
+
+def meta2_template(kind, dim_neck, dim_emb, dim_pre, freq):
+    sd = meta_template(kind, dim_neck, dim_emb, dim_pre, freq)
+    _adain_parts(sd)
+    return sd

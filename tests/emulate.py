@@ -246,7 +246,24 @@ def _emu_gather_codes(out, H, freq):
     return torch.cat((out[:, freq - 1::freq, :H], out[:, ::freq, H:]), dim=-1).contiguous()
 
 
+def _emu_global_stats(x, out=None):
+    v = x.double().reshape(-1)
+    r = torch.stack([v.mean(), v.std()]).float()
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+def _emu_adain(x, x_stats, t_stats, precision, want_f32=False):
+    xs, ts = x_stats.double(), t_stats.double()
+    y = ((x.double() - xs[0]) / xs[1] * ts[1] + ts[0]).float()
+    return packing.to_act(y, precision), (y if want_f32 else None)
+
+
 def install_cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops, "global_stats", _emu_global_stats)
+    monkeypatch.setattr(ops, "adain", _emu_adain)
     monkeypatch.setattr(ops, "gn_stats", _emu_gn_stats)
     monkeypatch.setattr(ops, "gn_pool_residual", _emu_gn_pool_residual)
     monkeypatch.setattr(ops, "gn_apply", _emu_gn_apply)

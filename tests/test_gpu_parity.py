@@ -471,3 +471,34 @@ def test_adjust_models_parity_and_golden(name, kind, precision, tol):
     if precision == "fp32":                     # negative control: another utterance must not pass
         bad = m(c["x_target"], c["c_org"], c["c_trg"])
         assert rel_l2(bad[2], G("train_mel_postnet")) > 1e-2
+
+
+@pytest.mark.parametrize("name,kind", [("autovc2_b2_t64", None), ("metapool2_b1_t176", "pool"),
+                                       ("metaconv2_b1_t176", "conv")])
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-4), ("bf16", 5e-2)])
+def test_adain_models_parity_and_golden(name, kind, precision, tol):
+    """AutoVC2 / MetaPool2 / MetaConv2 on the GPU kernels against the reference's own outputs:
+    batch-global statistics (avc_global_stats), AdaIN + combine convolutions, styling with another batch's features."""
+    from tests.test_host_logic import _adain_model
+    from tests.test_oracle_golden import adain_case, check_adain_outputs
+    g, args, sd, i, _ = adain_case(name, kind)
+    m = _adain_model(kind, args, sd).cuda()
+    m.precision = precision
+    c = {k: v.cuda() for k, v in i.items()}
+    check_adain_outputs(g, lambda xk, conv, tf: m(c[xk], c["c_org"], c["c_trg"] if conv else None, tf), tol,
+                        1e-4 if precision == "fp32" else 5e-2)
+
+
+def test_global_stats_and_adain_kernels():
+    from autoformer_b200 import ops, packing
+    torch.manual_seed(3)
+    x = (torch.randn(7, 96, 80) * 2.5 + 0.7).cuda()
+    st = ops.global_stats(x)
+    ref = torch.stack([x.double().mean(), x.double().std()]).float()
+    assert torch.allclose(st.cpu(), ref.cpu(), rtol=1e-6, atol=1e-6)
+    t = torch.tensor([-0.3, 1.7], device="cuda")
+    for prec in ("fp32", "tf32", "bf16"):
+        op, f32 = ops.adain(x, st, t, prec, want_f32=True)
+        want = (x - x.mean()) / x.std() * 1.7 - 0.3
+        assert rel_l2(f32, want) < 1e-6
+        assert rel_l2(packing.act_to_float(op, prec), want) < {"fp32": 1e-5, "tf32": 1e-3, "bf16": 1e-2}[prec]

@@ -138,3 +138,24 @@ def test_adjust_models_host_logic(cpu_kernels, name, kind):
             assert t.shape == g[f"{tag}_{key}"].shape and rel_l2(t, G(f"{tag}_{key}")) < 2e-4, (tag, key)
     assert rel_l2(m(i["x"], i["c_org"], None), G("codes_only")) < 2e-4
     assert rel_l2(m.adjust(i["x"], i["c_org"]), G("adjust_of_c_org")) < 2e-4
+
+
+def _adain_model(kind, args, sd):
+    from autoformer_b200.factory.AutoVC2 import AutoVC2
+    from autoformer_b200.factory.MetaConv2 import MetaConv2
+    from autoformer_b200.factory.MetaPool2 import MetaPool2
+    m = {None: AutoVC2, "pool": MetaPool2, "conv": MetaConv2}[kind](*args)
+    m.load_state_dict(sd)                      # the reference's key names, incl. feature_pre_extract / feature_last_combine
+    return m.eval()
+
+
+@pytest.mark.parametrize("name,kind", [("autovc2_b2_t64", None), ("metapool2_b1_t176", "pool"),
+                                       ("metaconv2_b1_t176", "conv")])
+def test_adain_models_host_logic(cpu_kernels, name, kind):
+    """AdaIN "2" drop-ins through the CPU stand-ins against the reference's own outputs."""
+    from tests.test_oracle_golden import adain_case, check_adain_outputs
+    g, args, sd, i, _ = adain_case(name, kind)
+    m = _adain_model(kind, args, sd)
+    check_adain_outputs(g, lambda xk, conv, tf: m(i[xk], i["c_org"], i["c_trg"] if conv else None, tf), 2e-4, 1e-4)
+    with pytest.raises(AttributeError):
+        m(i["x"], i["c_org"], None, [[0.0, 1.0]] * 3)      # the reference dereferences c_trg here
