@@ -635,9 +635,14 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
   }
   if (d->persistent) {
     AVC_REQUIRE(d->grid_barrier != nullptr, "avc_lstm_seq: persistent mode needs grid_barrier scratch");
-    attr[na].id = cudaLaunchAttributeCooperative;
-    attr[na].val.cooperative = 1;
-    ++na;
+    // AVC_LSTM_NO_COOP=1 (profiling aid): launch without the cooperative attribute.  Co-residency is then only
+    // implied by the occupancy check below on an otherwise idle GPU; the bounded waits turn a violation into a trap.
+    static const bool no_coop = getenv("AVC_LSTM_NO_COOP") != nullptr;
+    if (!no_coop) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;

@@ -348,10 +348,18 @@ def run_native(args):
     for v in kernels.values():
         if "tflops" in v:
             v["tensor_pipe_frac"] = v["tflops"] * passes / pk["tflops_sustained"]
+    # DRAM traffic per launch of the dominant kernel, from the committed `ncu --set full` capture of this very
+    # configuration (profiles/r01_lstm_fused_persistent_ncu_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of the
+    # three persistent launches of one forward: 193.6 + 406.5 + 556.7 MB); null for any other configuration
+    traffic = None
+    if (dom == "lstm_step" and fused and lstm_mode == "persistent" and args.precision == "fp32" and B == 512
+            and T == 128):
+        traffic = (193.6e6 + 406.5e6 + 556.7e6) / 3
     roofline = {
         "kernel": f"{kernel_name} ({dom})", "bound": "tensor", "achieved": dom_e["tflops"],
         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": dom_e["tflops"] / pk["tflops_sustained"],
-        "traffic": None, "peak_source": pk["source"] + " bf16_tflops_sustained",
+        "traffic": traffic, "traffic_unit": "bytes per launch (mean of the 3 launches per step), ncu dram read+write",
+        "peak_source": pk["source"] + " bf16_tflops_sustained",
         "share_of_step": dom_e["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
         "avg_launch_us": dom_e["ms_per_step"] * 1e3 / max(1, dom_e["launches_per_step"]),
         "algorithmic_flops_per_launch": dom_e["tflops"] * 1e12 * dom_e["ms_per_step"] * 1e-3 / max(1, dom_e["launches_per_step"]),
