@@ -5,6 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libavc_b200.so")
 
+ERR_NOT_RESIDENT = -4
 DTYPE_TF32 = 0
 DTYPE_BF16 = 1
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU, ACT_GELU = 0, 1, 2, 3, 4

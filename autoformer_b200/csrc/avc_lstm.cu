@@ -657,7 +657,10 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
       AVC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, C::kSmemBytes));
       resident = per_sm * num_sms();
     }
-    AVC_REQUIRE(resident >= grid, "avc_lstm_seq: persistent grid %d does not fit (%d CTAs resident)", grid, resident);
+    if (resident < grid) {   // distinct code: the caller may fall back to one launch per frame
+      set_error("avc_lstm_seq: persistent grid %d does not fit (%d CTAs resident)", grid, resident);
+      return AVC_ERR_NOT_RESIDENT;
+    }
     AVC_REQUIRE((m_tiles + CTAS - 1) / CTAS <= 64, "avc_lstm_seq: at most 64 batch groups in persistent mode");
     AVC_CHECK_CUDA(cudaMemsetAsync(d->grid_barrier, 0, 64 * 32 * sizeof(unsigned int), stream));
     p.t_begin = 0;

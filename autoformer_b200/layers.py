@@ -77,16 +77,26 @@ class LstmLayer:
         kx = (self.C_in + packing.KC[self.precision] - 1) // packing.KC[self.precision]
         return self.fused and (kx <= 6 or B >= 192)
 
-    def __call__(self, x, B, T, hseq_f32=None, h_last=None, persistent=False):
+    def __call__(self, x, B, T, hseq_f32=None, h_last=None, persistent=False, hseq=None):
+        cap = ops.persistent_batch_cap(self.H) if persistent else 0
+        if persistent and B > cap > 0:
+            # utterances are independent: a batch too large for one wave of the persistent grid runs as sub-batches
+            # (slices along the utterance axis are contiguous views, so nothing is copied)
+            out = ops.alloc_act(B, T, self.H, self.precision, x.device) if hseq is None else hseq
+            for b0 in range(0, B, cap):
+                b1 = min(B, b0 + cap)
+                self(x[b0:b1], b1 - b0, T, hseq_f32=hseq_f32[b0:b1] if hseq_f32 is not None else None,
+                     h_last=h_last[b0:b1] if h_last is not None else None, persistent=True, hseq=out[b0:b1])
+            return out
         group = ops.choose_gate_group(B, self.H, persistent)
         if self.use_fused(B):
             wih, bias, hh = self.fused_packs(group)
-            return ops.lstm_seq(None, hh, B, T, self.H, self.precision, group, hseq_f32=hseq_f32, h_last=h_last,
-                                persistent=persistent, xin=x, w_ih=wih, bias=bias, c_in=self.C_in)
+            return ops.lstm_seq(None, hh, B, T, self.H, self.precision, group, hseq=hseq, hseq_f32=hseq_f32,
+                                h_last=h_last, persistent=persistent, xin=x, w_ih=wih, bias=bias, c_in=self.C_in)
         ih, hh = self.packs(group)
         xp = torch.empty(B * T, 4 * self.H, dtype=torch.float32, device=x.device)
         ih(x, B, T, out2=xp)
-        return ops.lstm_seq(xp, hh, B, T, self.H, self.precision, group, hseq_f32=hseq_f32, h_last=h_last,
+        return ops.lstm_seq(xp, hh, B, T, self.H, self.precision, group, hseq=hseq, hseq_f32=hseq_f32, h_last=h_last,
                             persistent=persistent)
 
 

@@ -1,6 +1,7 @@
 """Thin Python wrappers over the C ABI (include/avc_b200.h).  torch is used only for device memory and the
 current stream; every arithmetic operation runs in libavc_b200.so.  Nothing here falls back to torch math."""
 import ctypes
+import warnings
 
 import torch
 
@@ -58,6 +59,7 @@ class Profiler:
 
 
 PROFILER = Profiler()
+_warned_not_resident = False
 
 
 def _require_cuda(*tensors):
@@ -186,6 +188,19 @@ class ConvGemm:
         return out if out is not None else (out2 if out2 is not None else out_raw)
 
 
+def persistent_batch_cap(H, n_sm=148):
+    """Largest batch whose persistent LSTM grid (m-tiles x H/G n-tiles, one CTA each) fits one wave of the SMs."""
+    best = 0
+    for g in (32, 16):
+        if H % g:
+            continue
+        m_tiles = n_sm // (H // g)
+        if m_tiles >= 2:
+            m_tiles -= m_tiles % 2                 # CTA pairs
+        best = max(best, m_tiles * 128)
+    return best
+
+
 def choose_gate_group(B, H, persistent=False, n_sm=148):
     """Hidden units per accumulator tile (tile width 4G): fill the SMs without exceeding one wave when persistent."""
     m_tiles = (B + 127) // 128
@@ -258,7 +273,18 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
         d.debug_clk = debug_clk.data_ptr()
     with PROFILER.span("lstm_step", flops=2.0 * 4 * H * (H + (c_in if fused else 0)) * B * T,
                        launches=1 if persistent else T):
-        _lib.check(lib.avc_lstm_seq(ctypes.byref(d), _stream()), "avc_lstm_seq")
+        rc = lib.avc_lstm_seq(ctypes.byref(d), _stream())
+        if rc == _lib.ERR_NOT_RESIDENT and persistent:
+            # the one-wave persistent grid does not fit this device (fewer SMs available than planned): same kernel,
+            # one launch per frame
+            global _warned_not_resident
+            if not _warned_not_resident:
+                warnings.warn("persistent LSTM grid is not co-resident on this device; using per-frame launches: "
+                              + lib.avc_last_error().decode("utf-8", "replace"))
+                _warned_not_resident = True
+            d.persistent = 0
+            rc = lib.avc_lstm_seq(ctypes.byref(d), _stream())
+        _lib.check(rc, "avc_lstm_seq")
     return hseq
 
 

@@ -137,6 +137,9 @@ typedef struct avc_lstm_desc {
   const float* bias;         /* [4H] fp32 b_ih + b_hh, packed order */
 } avc_lstm_desc;
 
+/* Returned by avc_lstm_seq in persistent mode when the grid cannot be co-resident (one wave); nothing was launched. */
+#define AVC_ERR_NOT_RESIDENT (-4)
+
 int avc_lstm_seq(const avc_lstm_desc* d, void* stream);
 
 /*

@@ -88,7 +88,8 @@ def test_conv_gemm_residual_and_reflect_halo():
 @pytest.mark.parametrize("B,T,I,H,persistent", [(4, 8, 64, 128, False), (130, 16, 320, 512, False),
                                                 (64, 24, 512, 1024, False), (3, 12, 80, 768, False),
                                                 (130, 16, 320, 512, True), (256, 20, 512, 1024, True),
-                                                (300, 9, 80, 768, True), (512, 12, 1024, 1024, True)])
+                                                (300, 9, 80, 768, True), (512, 12, 1024, 1024, True),
+                                                (600, 5, 320, 1024, True)])       # > one wave: runs as sub-batches
 def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent, fused):
     from autoformer_b200 import layers, packing
     torch.manual_seed(H + T)

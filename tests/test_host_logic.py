@@ -159,3 +159,24 @@ def test_adain_models_host_logic(cpu_kernels, name, kind):
     check_adain_outputs(g, lambda xk, conv, tf: m(i[xk], i["c_org"], i["c_trg"] if conv else None, tf), 2e-4, 1e-4)
     with pytest.raises(AttributeError):
         m(i["x"], i["c_org"], None, [[0.0, 1.0]] * 3)      # the reference dereferences c_trg here
+
+
+def test_lstm_layer_sub_batches_when_persistent_grid_exceeds_one_wave(cpu_kernels):
+    """B = 600 at H = 1024 needs 192 CTAs > 148 SMs: the layer must split the batch (utterances are independent) and
+    still fill every output the caller asked for."""
+    from autoformer_b200 import layers, ops, packing
+    from oracle.layers import lstm_explicit
+    assert ops.persistent_batch_cap(1024) == 512 and ops.persistent_batch_cap(512) == 1024
+    torch.manual_seed(0)
+    B, T, I, H = 600, 3, 64, 1024
+    k = 1.0 / H ** 0.5
+    w_ih, w_hh = (torch.rand(4 * H, I) * 2 - 1) * k, (torch.rand(4 * H, H) * 2 - 1) * k
+    b_ih, b_hh = (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
+    x = torch.randn(B, T, I)
+    ref = lstm_explicit(x.double(), w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
+    layer = layers.LstmLayer(w_ih, w_hh, b_ih, b_hh, "fp32")
+    f32 = torch.full((B, T, H), float("nan"))
+    last = torch.full((B, H), float("nan"))
+    hseq = layer(packing.to_act(x, "fp32"), B, T, hseq_f32=f32, h_last=last, persistent=True)
+    assert rel_l2(f32, ref) < 1e-4 and rel_l2(last, ref[:, -1]) < 1e-4
+    assert rel_l2(packing.act_to_float(hseq, "fp32"), ref) < 1e-4
