@@ -8,13 +8,15 @@ LIB_PATH = os.path.join(_HERE, "libavc_b200.so")
 ERR_NOT_RESIDENT = -4
 DTYPE_TF32 = 0
 DTYPE_BF16 = 1
-ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU, ACT_GELU = 0, 1, 2, 3, 4
-ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU, "gelu": ACT_GELU}
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU, ACT_GELU, ACT_LOG10_CLAMP = 0, 1, 2, 3, 4, 5
+ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU, "gelu": ACT_GELU,
+        "log10_clamp": ACT_LOG10_CLAMP}
 
 EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm", "avc_lstm_seq",
            "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_transpose_pad",
            "avc_conv_to_mono_tanh", "avc_gn_stats", "avc_gn_pool_residual", "avc_gn_apply", "avc_patchify",
-           "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes", "avc_global_stats", "avc_adain"]
+           "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes", "avc_global_stats", "avc_adain", "avc_audio_frames",
+           "avc_complex_mag"]
 
 
 MAX_SOURCES = 4
@@ -133,6 +135,9 @@ def load():
     lib.avc_global_stats.argtypes = [vp, ctypes.c_longlong, vp, vp, vp]
     lib.avc_adain.argtypes = [vp, vp, vp, vp, vp, ci, ci, ctypes.c_longlong, ci, vp]
     lib.avc_global_stats.restype = lib.avc_adain.restype = ctypes.c_int
+    lib.avc_audio_frames.argtypes = [vp, vp, ci, ctypes.c_longlong, ci, ci, ci, ci, ci, vp]
+    lib.avc_complex_mag.argtypes = [vp, vp, ctypes.c_longlong, ci, ci, ci, ci, vp]
+    lib.avc_audio_frames.restype = lib.avc_complex_mag.restype = ctypes.c_int
     for fn in (lib.avc_gn_stats, lib.avc_gn_pool_residual, lib.avc_gn_apply, lib.avc_patchify, lib.avc_ln_transpose,
                lib.avc_meta_decoder_input, lib.avc_gather_codes):
         fn.restype = ctypes.c_int

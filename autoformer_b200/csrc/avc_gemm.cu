@@ -54,6 +54,7 @@ __device__ __forceinline__ float apply_act(float v) {
   if (ACT == AVC_ACT_TANH) return tanh_fast(v);
   if (ACT == AVC_ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
   if (ACT == AVC_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  if (ACT == AVC_ACT_LOG10_CLAMP) return log10f(fmaxf(v, 1e-5f));
   return v;
 }
 
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         case AVC_ACT_TANH: epilogue_tile<BN, AVC_ACT_TANH>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
         case AVC_ACT_LRELU: epilogue_tile<BN, AVC_ACT_LRELU>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
         case AVC_ACT_GELU: epilogue_tile<BN, AVC_ACT_GELU>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
+        case AVC_ACT_LOG10_CLAMP: epilogue_tile<BN, AVC_ACT_LOG10_CLAMP>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
         default: epilogue_tile<BN, AVC_ACT_NONE>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
       }
     }

@@ -4,6 +4,7 @@
 #include "../../include/avc_b200.h"
 #include "avc_host.h"
 #include "avc_pipe.cuh"
+#include "avc_store.cuh"
 
 namespace avc {
 
@@ -349,6 +350,93 @@ extern "C" int avc_transpose_pad(const float* in, void* out, int B, int C, int L
   AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "avc_transpose_pad: out_dtype %d", out_dtype);
   dim3 grid((L + 31) / 32, (C + 31) / 32, B);
   transpose_pad_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, C, L, pad, out_dtype, out_round_tf32);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Audio2Mel front end glue (melgan/modules.py:55-66): reflect padding + framing rows, complex magnitude
+// ---------------------------------------------------------------------------------------------
+namespace avc {
+
+__global__ void __launch_bounds__(256) audio_frames_kernel(const float* __restrict__ audio, void* __restrict__ out,
+                                                           long long L, int pad, int hop, int rows, int mode, int round,
+                                                           long long total4) {
+  const int c4n = hop >> 2;
+  const long long padded = L + 2LL * pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c4n;                     // b * rows + r
+    const int c = static_cast<int>(i - row * c4n) << 2;
+    const long long b = row / rows;
+    const long long r = row - b * rows;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long j = r * hop + c + e;             // index in the padded signal
+      long long src = j - pad;
+      if (src < 0) src = -src;                         // F.pad(..., "reflect"): no edge repeat
+      if (src >= L) src = 2 * (L - 1) - src;
+      v[e] = (j < padded && src >= 0 && src < L) ? __ldg(audio + b * L + src) : 0.0f;
+    }
+    store_op4(out, mode, round, row, op_ld(hop, mode), c, hop, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+__global__ void __launch_bounds__(256) complex_mag_kernel(const float* __restrict__ spec, void* __restrict__ mag,
+                                                          int bins, int bins_pad, int mode, int round, long long total4) {
+  const int c4n = bins_pad >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c4n;
+    const int c = static_cast<int>(i - row * c4n) << 2;
+    const float* re = spec + row * (2LL * bins);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = c + e;
+      float m = 0.0f;
+      if (k < bins) {
+        const float a = __ldg(re + k), b = __ldg(re + bins + k);
+        m = sqrtf(a * a + b * b);
+      }
+      v[e] = m;
+    }
+    store_op4(mag, mode, round, row, op_ld(bins_pad, mode), c, bins_pad, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+static int ew_grid(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+}  // namespace avc
+
+extern "C" int avc_audio_frames(const float* audio, void* out, int B, long long L, int pad, int hop, int rows,
+                                int out_dtype, int out_round_tf32, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(audio && out, "avc_audio_frames: null buffer");
+  AVC_REQUIRE(B > 0 && L > pad && pad >= 0 && hop > 0 && hop % 8 == 0 && rows > 0 && out_dtype >= 0 && out_dtype <= 2,
+              "avc_audio_frames: bad shape B=%d L=%lld pad=%d hop=%d rows=%d", B, L, pad, hop, rows);
+  const long long total4 = (long long)B * rows * (hop / 4);
+  audio_frames_kernel<<<ew_grid(total4), 256, 0, stream>>>(audio, out, L, pad, hop, rows, out_dtype, out_round_tf32,
+                                                           total4);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_complex_mag(const float* spec, void* mag, long long rows, int bins, int bins_pad, int out_dtype,
+                               int out_round_tf32, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(spec && mag, "avc_complex_mag: null buffer");
+  AVC_REQUIRE(rows > 0 && bins > 0 && bins_pad >= bins && bins_pad % 8 == 0 && out_dtype >= 0 && out_dtype <= 2,
+              "avc_complex_mag: bad shape rows=%lld bins=%d bins_pad=%d", rows, bins, bins_pad);
+  const long long total4 = rows * (bins_pad / 4);
+  complex_mag_kernel<<<ew_grid(total4), 256, 0, stream>>>(spec, mag, bins, bins_pad, out_dtype, out_round_tf32, total4);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -73,6 +73,74 @@ class _Plan:
         self.b_out = float(b(f"model.{idx + 2}")[0])
 
 
+class Audio2Mel(nn.Module):
+    """Drop-in ``Audio2Mel`` (melgan/modules.py:26-69): audio (B, 1, L) -> log10-mel (B, n_mel, L // hop).
+
+    The STFT is an implicit-GEMM convolution on the tensor cores: the reflect-padded signal is viewed as rows of
+    ``hop`` samples, a frame is n_fft / hop consecutive rows, and the hann-windowed DFT basis is a (2 * bins, hop,
+    n_fft / hop) convolution weight; magnitude, mel projection (``mel_basis`` buffer, same name as the reference's) and
+    ``log10(clamp(., 1e-5))`` follow as one small kernel and one GEMM with the log in its epilogue."""
+
+    def __init__(self, n_fft=1024, hop_length=256, win_length=1024, sampling_rate=22050, n_mel_channels=80,
+                 mel_fmin=0.0, mel_fmax=None):
+        super().__init__()
+        from .filters import mel_filterbank
+        assert n_fft % hop_length == 0 and hop_length % 8 == 0 and win_length <= n_fft
+        self.register_buffer("mel_basis", torch.from_numpy(mel_filterbank(sampling_rate, n_fft, n_mel_channels,
+                                                                          mel_fmin, mel_fmax)).float())
+        self.register_buffer("window", torch.hann_window(win_length).float())
+        self.n_fft, self.hop_length, self.win_length = n_fft, hop_length, win_length
+        self.sampling_rate, self.n_mel_channels = sampling_rate, n_mel_channels
+        self.precision = "fp32"
+        self._cache = layers.PlanCache()
+
+    def _plan(self):
+        def build():
+            N, hop, bins = self.n_fft, self.hop_length, self.n_fft // 2 + 1
+            dev = self.mel_basis.device
+            win = torch.zeros(N, dtype=torch.float64, device=dev)
+            lo = (N - self.win_length) // 2                     # torch.stft centres a short window in the frame
+            win[lo:lo + self.win_length] = self.window.double()
+            j = torch.arange(N, dtype=torch.float64, device=dev)
+            k = torch.arange(bins, dtype=torch.float64, device=dev)
+            ang = 2.0 * torch.pi * k[:, None] * j[None, :] / N
+            bins_pad = (bins + 7) // 8 * 8                      # 513 -> 520: channel counts must be multiples of 8
+            basis = torch.zeros(2 * bins_pad, N, dtype=torch.float64, device=dev)           # re | im halves
+            basis[:bins] = torch.cos(ang) * win
+            basis[bins_pad:bins_pad + bins] = -torch.sin(ang) * win
+            w = basis.view(2 * bins_pad, N // hop, hop).permute(0, 2, 1).contiguous().float()   # (C_out, C_in = hop, taps)
+            stft = ops.ConvGemm(*packing.pack_conv(w, torch.zeros(2 * bins_pad, device=dev), self.precision),
+                                tap_t0=[0], tag="stft")
+            mb = torch.zeros(self.n_mel_channels, bins_pad, dtype=torch.float32, device=dev)
+            mb[:, :bins] = self.mel_basis.float()
+            mel = ops.ConvGemm(*packing.pack_linear(mb, torch.zeros(self.n_mel_channels, device=dev), self.precision),
+                               act="log10_clamp", tag="mel")
+            return dict(stft=stft, mel=mel, bins=bins, bins_pad=bins_pad)
+        return self._cache.get(self, (self.precision,), build)
+
+    @torch.no_grad()
+    def forward(self, audio):
+        ops._require_cuda(audio)
+        if audio.dim() == 3:
+            audio = audio.squeeze(1)                            # (B, 1, L), modules.py:56-57
+        audio = audio.contiguous().float()
+        B, L = audio.shape
+        plan = self._plan()
+        hop, taps = self.hop_length, self.n_fft // self.hop_length
+        pad = (self.n_fft - hop) // 2                           # modules.py:55
+        if L <= pad:
+            raise RuntimeError(f"reflect padding of {pad} samples needs more than {pad} input samples (got {L})")
+        frames = (L + 2 * pad - self.n_fft) // hop + 1
+        rows = frames + taps - 1
+        x = ops.audio_frames(audio, pad, hop, rows, self.precision)
+        spec = torch.empty(B * frames, 2 * plan["bins_pad"], dtype=torch.float32, device=audio.device)
+        plan["stft"](x, B, frames, out2=spec)                   # torch.stft(center=False), modules.py:58-65
+        mag = ops.complex_mag(spec, plan["bins_pad"], plan["bins_pad"], self.precision)      # :66 (pad bins are 0)
+        out = torch.empty(B * frames, self.n_mel_channels, dtype=torch.float32, device=audio.device)
+        plan["mel"](mag.view(B, frames, -1), B, frames, out2=out)                          # :67-68
+        return out.view(B, frames, self.n_mel_channels).transpose(1, 2).contiguous()
+
+
 class Generator(nn.Module):
     def __init__(self, input_size, ngf, n_residual_layers):
         super().__init__()

@@ -496,3 +496,30 @@ def adain(x, x_stats, t_stats, precision, want_f32=False):
         _lib.check(lib.avc_adain(x.data_ptr(), x_stats.data_ptr(), t_stats.data_ptr(), _ptr(out_f32), out_op.data_ptr(),
                                  _dt(precision), 1, B * T, C, _stream()), "avc_adain")
     return out_op, out_f32
+
+
+# ------------------------------------------------------------------------------------------------ Audio2Mel front end
+def audio_frames(audio, pad, hop, rows, precision):
+    """audio [B][L] fp32 -> reflect-padded signal as rows of `hop` samples [B][rows][hop] in operand format."""
+    lib = _lib.load()
+    _require_cuda(audio)
+    assert audio.dtype == torch.float32 and audio.is_contiguous() and audio.dim() == 2
+    B, L = audio.shape
+    out = alloc_act(B, rows, hop, precision, audio.device)
+    with PROFILER.span("audio_frames", bytes=float(audio.numel() * 4 + out.numel() * out.element_size())):
+        _lib.check(lib.avc_audio_frames(audio.data_ptr(), out.data_ptr(), B, L, pad, hop, rows, _dt(precision), 1,
+                                        _stream()), "avc_audio_frames")
+    return out
+
+
+def complex_mag(spec, bins, bins_pad, precision):
+    """spec [rows][2*bins] fp32 (re | im) -> |spec| [rows][bins_pad] in operand format (zero padding channels)."""
+    lib = _lib.load()
+    _require_cuda(spec)
+    assert spec.dtype == torch.float32 and spec.is_contiguous() and spec.dim() == 2 and spec.shape[1] == 2 * bins
+    rows = spec.shape[0]
+    out = alloc_act(1, rows, bins_pad, precision, spec.device)
+    with PROFILER.span("complex_mag", bytes=float(spec.numel() * 4 + out.numel() * out.element_size())):
+        _lib.check(lib.avc_complex_mag(spec.data_ptr(), out.data_ptr(), rows, bins, bins_pad, _dt(precision), 1,
+                                       _stream()), "avc_complex_mag")
+    return out

@@ -39,6 +39,7 @@ extern "C" {
 #define AVC_ACT_TANH 2
 #define AVC_ACT_LRELU 3 /* slope 0.2, melgan/modules.py:75,100,120 */
 #define AVC_ACT_GELU 4  /* exact erf GELU, nn.GELU() default, factory/MLPMixer.py:19 */
+#define AVC_ACT_LOG10_CLAMP 5 /* log10(max(v, 1e-5)), melgan/modules.py:67-68 (Audio2Mel) */
 
 int avc_version(void);
 const char* avc_last_error(void);
@@ -240,6 +241,22 @@ int avc_gather_codes(const float* out, float* codes, int B, int T, int H, int fr
 int avc_global_stats(const float* x, long long n, float* stats, double* scratch, void* stream);
 int avc_adain(const float* x, const float* x_stats, const float* t_stats, float* out_f32, void* out_op, int out_dtype,
               int out_round_tf32, long long rows, int C, void* stream);
+
+/*
+ * Audio2Mel front end (melgan/modules.py:26-69): reflect-pad by (n_fft - hop)/2, STFT(n_fft, hop, hann, center=False),
+ * magnitude, mel filter bank, log10(clamp(., 1e-5)).  The STFT runs as an implicit-GEMM convolution on the tensor cores:
+ * the padded signal is viewed as rows of `hop` samples (hop = 256 "channels"), a frame is n_fft / hop = 4 consecutive
+ * rows, and the windowed DFT basis is a 4-tap convolution weight with 2 * (n_fft/2 + 1) output channels (avc_conv_gemm);
+ * the mel projection is a second avc_conv_gemm with the AVC_ACT_LOG10_CLAMP epilogue.
+ *   avc_audio_frames: audio [B][L] fp32 -> out [B][rows][hop] operand format, out row r holds padded samples
+ *     [r*hop, (r+1)*hop); padded sample j = audio[reflect(j - pad)], zero past the padded length.
+ *   avc_complex_mag: spec [rows][2*bins] fp32 (re | im halves) -> mag [rows][bins_pad] operand format,
+ *     sqrt(re^2 + im^2) in the first `bins` channels, zero in the padding channels.
+ */
+int avc_audio_frames(const float* audio, void* out, int B, long long L, int pad, int hop, int rows, int out_dtype,
+                     int out_round_tf32, void* stream);
+int avc_complex_mag(const float* spec, void* mag, long long rows, int bins, int bins_pad, int out_dtype,
+                    int out_round_tf32, void* stream);
 
 #ifdef __cplusplus
 }

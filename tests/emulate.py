@@ -56,7 +56,7 @@ import torch.nn.functional as F  # noqa: E402
 from autoformer_b200 import ops, packing  # noqa: E402
 
 _ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(v, 0.2),
-        4: lambda v: 0.5 * v * (1.0 + torch.erf(v / 2 ** 0.5))}
+        4: lambda v: 0.5 * v * (1.0 + torch.erf(v / 2 ** 0.5)), 5: lambda v: torch.log10(torch.clamp(v, min=1e-5))}
 
 
 def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
@@ -261,7 +261,24 @@ def _emu_adain(x, x_stats, t_stats, precision, want_f32=False):
     return packing.to_act(y, precision), (y if want_f32 else None)
 
 
+def _emu_audio_frames(audio, pad, hop, rows, precision):
+    B, L = audio.shape
+    padded = F.pad(audio.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    buf = torch.zeros(B, rows * hop, dtype=torch.float32)
+    n = min(rows * hop, padded.shape[1])
+    buf[:, :n] = padded[:, :n]
+    return packing.to_act(buf.view(B, rows, hop), precision)
+
+
+def _emu_complex_mag(spec, bins, bins_pad, precision):
+    mag = torch.zeros(spec.shape[0], bins_pad, dtype=torch.float64)
+    mag[:, :bins] = torch.sqrt(spec[:, :bins].double() ** 2 + spec[:, bins:].double() ** 2)
+    return packing.to_act(mag.float().unsqueeze(0), precision)
+
+
 def install_cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops, "audio_frames", _emu_audio_frames)
+    monkeypatch.setattr(ops, "complex_mag", _emu_complex_mag)
     monkeypatch.setattr(ops, "global_stats", _emu_global_stats)
     monkeypatch.setattr(ops, "adain", _emu_adain)
     monkeypatch.setattr(ops, "gn_stats", _emu_gn_stats)
