@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) concat_bcast_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int kSmallWarps = 8;   // 4 utterances x 2 directions per CTA
 
-template <int UPL>   // hidden units per lane: 1 (H <= 32) or 2 (H <= 64)
+// REGW (H == 32 only): every lane keeps the 4 x 32 recurrent weights of its hidden unit in registers and h_{t-1} is
+// exchanged with warp shuffles, so a step issues 32 SHFL + 128 FMA instead of 64 shared-memory loads (the shared-memory
+// variant is bound by those loads: 2.2 K cycles per step against ~0.6 K here).
+template <int UPL, bool REGW>   // hidden units per lane: 1 (H <= 32) or 2 (H <= 64)
 __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
     const float* __restrict__ xproj, const float* __restrict__ w_hh, void* __restrict__ out, int out_mode, int round,
     float* __restrict__ codes, int B, int T, int H, int freq) {
@@ -101,6 +104,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
     }
   };
   load_x(dir ? T - 1 : 0, zx);
+  float4 wreg[REGW ? 32 : 1];
+  float hprev = 0.0f;
+  if (REGW) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) wreg[k] = W[k * HP + lane];
+  }
   for (int s = 0; s < T; ++s) {
     const int t = dir ? T - 1 - s : s;
     float z[UPL][4];
@@ -109,19 +118,30 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
 #pragma unroll
       for (int g = 0; g < 4; ++g) z[e][g] = zx[e][g];
     if (s + 1 < T) load_x(dir ? t - 1 : t + 1, zx);   // prefetch the next frame's projection
-#pragma unroll 4
-    for (int k = 0; k < H; ++k) {
-      const float hk = hb[k];
+    if (REGW) {
 #pragma unroll
-      for (int e = 0; e < UPL; ++e) {
-        const float4 w = W[k * HP + lane + 32 * e];
-        z[e][0] = fmaf(w.x, hk, z[e][0]);
-        z[e][1] = fmaf(w.y, hk, z[e][1]);
-        z[e][2] = fmaf(w.z, hk, z[e][2]);
-        z[e][3] = fmaf(w.w, hk, z[e][3]);
+      for (int k = 0; k < 32; ++k) {
+        const float hk = __shfl_sync(0xffffffffu, hprev, k);
+        z[0][0] = fmaf(wreg[k].x, hk, z[0][0]);
+        z[0][1] = fmaf(wreg[k].y, hk, z[0][1]);
+        z[0][2] = fmaf(wreg[k].z, hk, z[0][2]);
+        z[0][3] = fmaf(wreg[k].w, hk, z[0][3]);
       }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < H; ++k) {
+        const float hk = hb[k];
+#pragma unroll
+        for (int e = 0; e < UPL; ++e) {
+          const float4 w = W[k * HP + lane + 32 * e];
+          z[e][0] = fmaf(w.x, hk, z[e][0]);
+          z[e][1] = fmaf(w.y, hk, z[e][1]);
+          z[e][2] = fmaf(w.z, hk, z[e][2]);
+          z[e][3] = fmaf(w.w, hk, z[e][3]);
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
     float h[UPL];
 #pragma unroll
     for (int e = 0; e < UPL; ++e) {
@@ -131,9 +151,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
       const float og = sigmoid_fast(z[e][3]);
       c[e] = fg * c[e] + ig * gg;
       h[e] = og * tanh_fast(c[e]);
-      hb[lane + 32 * e] = h[e];
+      if (!REGW) hb[lane + 32 * e] = h[e];
     }
-    __syncwarp();
+    if (REGW) hprev = h[0]; else __syncwarp();
 #pragma unroll
     for (int e = 0; e < UPL; ++e) {
       const int u = lane + 32 * e;
@@ -314,14 +334,18 @@ extern "C" int avc_bilstm_small(const float* xproj, const float* w_hh, void* out
   const int hp = upl * 32;
   const size_t smem = (size_t)2 * H * hp * sizeof(float4) + (size_t)kSmallWarps * hp * sizeof(float);
   const int grid = (B + kSmallWarps / 2 - 1) / (kSmallWarps / 2);
-  if (upl == 1) {
-    AVC_CHECK_CUDA(cudaFuncSetAttribute(bilstm_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bilstm_small_kernel<1><<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32,
-                                                                     codes, B, T, H, freq);
+  if (H == 32) {          // AutoVC "A" (dim_neck = 32): recurrent weights in registers
+    auto kern = bilstm_small_kernel<1, true>;
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32, codes, B, T, H, freq);
+  } else if (upl == 1) {
+    auto kern = bilstm_small_kernel<1, false>;
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32, codes, B, T, H, freq);
   } else {
-    AVC_CHECK_CUDA(cudaFuncSetAttribute(bilstm_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bilstm_small_kernel<2><<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32,
-                                                                     codes, B, T, H, freq);
+    auto kern = bilstm_small_kernel<2, false>;
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32, codes, B, T, H, freq);
   }
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
