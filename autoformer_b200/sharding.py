@@ -29,22 +29,36 @@ def make_batches(buckets, max_batch=512):
     return batches
 
 
-def assign_batches(batches, world_size):
-    """Greedy longest-processing-time assignment by frame count.  Deterministic, identical on every rank.
+def frames_cost(T, n):
+    """Cost of a batch of n utterances x T frames when only the frame count matters."""
+    return float(T * n)
+
+
+def autovc_cost(T, n):
+    """Measured cost model of one AutoVC conversion batch on a B200 (default precision), in microseconds: the LSTM
+    layers run one tile row per frame whatever the batch size up to 512 (47.5 us per frame, profiles/r01_bench_final_1gpu:
+    6.08 ms / 128 frames), everything else scales with utterances x frames (3.9 ms / 65,536).  A 212-utterance tail batch
+    therefore costs 77 % of a full one for 41 % of its frames, which a frames-only balance does not see."""
+    return float(T) * (47.5 + 0.0596 * n)
+
+
+def assign_batches(batches, world_size, cost=frames_cost):
+    """Greedy longest-processing-time assignment by ``cost(T, n)``.  Deterministic, identical on every rank.
 
     Returns a list (one entry per rank) of batch lists."""
-    order = sorted(range(len(batches)), key=lambda i: (-batches[i][0] * len(batches[i][1]), i))
-    load = [0] * world_size
+    c = [cost(t, len(ids)) for t, ids in batches]
+    order = sorted(range(len(batches)), key=lambda i: (-c[i], i))
+    load = [0.0] * world_size
     out = [[] for _ in range(world_size)]
     for i in order:
         r = min(range(world_size), key=lambda k: (load[k], k))
         out[r].append(batches[i])
-        load[r] += batches[i][0] * len(batches[i][1])
+        load[r] += c[i]
     return out
 
 
-def plan(lengths, world_size, max_batch=512):
-    return assign_batches(make_batches(bucket_by_length(lengths), max_batch), world_size)
+def plan(lengths, world_size, max_batch=512, cost=frames_cost):
+    return assign_batches(make_batches(bucket_by_length(lengths), max_batch), world_size, cost)
 
 
 def gather_records(record, device=None):

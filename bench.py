@@ -437,7 +437,7 @@ def run_sweep(args):
     model.persistent_lstm = args.lstm != "per-step"
     rng = random.Random(1234)
     lengths = [rng.choice(range(128, 1025, 32)) for _ in range(args.utterances)]
-    mine = sharding.plan(lengths, world, args.batch)[rank]
+    mine = sharding.plan(lengths, world, args.batch, cost=sharding.autovc_cost)[rank]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = {}
 
@@ -483,7 +483,7 @@ def run_sweep(args):
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": f"AutoVC(32,256,512,32) conversion of {args.utterances} utterances x 128..1024 "
                                        "frames (BASELINE.json configs[4]), bucketed by exact length, batches <= "
-                                       f"{args.batch}, sharded by frames over {world} ranks",
+                                       f"{args.batch}, LPT-sharded over {world} ranks by a measured per-batch cost model",
                            "frames_total": total, "batches": sum(1 for _ in sharding.make_batches(
                                sharding.bucket_by_length(lengths), args.batch))},
                 "frac_of_model_roofline": total / (ms_max * 1e-3) / world / (pk["tflops_sustained"] * 1e12 / FLOP_PER_FRAME),

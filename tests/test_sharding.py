@@ -74,3 +74,21 @@ def test_two_rank_gloo_gather():
     assert sum(r[0] for r in recs) == float(sum(lens))
     assert [int(v[0]) for v in full] == list(range(300))                # every utterance landed at its own index
     assert [int(v[1]) for v in full] == lens
+
+
+def test_cost_model_balances_tail_batches():
+    """LPT by the measured AutoVC cost model (LSTM time per frame is independent of the batch size up to 512) must
+    balance the modelled time better than LPT by frame count, and still cover every utterance exactly once."""
+    import random
+    from autoformer_b200 import sharding
+    rng = random.Random(1234)
+    lengths = [rng.choice(range(128, 1025, 32)) for _ in range(8192)]
+    spread = {}
+    for cost in (sharding.frames_cost, sharding.autovc_cost):
+        plan = sharding.plan(lengths, 8, 512, cost=cost)
+        seen = sorted(i for rank in plan for _, ids in rank for i in ids)
+        assert seen == list(range(len(lengths)))
+        loads = [sum(sharding.autovc_cost(t, len(ids)) for t, ids in rank) for rank in plan]
+        spread[cost.__name__] = max(loads) / (sum(loads) / len(loads))
+    assert spread["autovc_cost"] <= spread["frames_cost"] + 1e-9
+    assert spread["autovc_cost"] < 1.05
