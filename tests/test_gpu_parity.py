@@ -503,3 +503,37 @@ def test_global_stats_and_adain_kernels():
         want = (x - x.mean()) / x.std() * 1.7 - 0.3
         assert rel_l2(f32, want) < 1e-6
         assert rel_l2(packing.act_to_float(op, prec), want) < {"fp32": 1e-5, "tf32": 1e-3, "bf16": 1e-2}[prec]
+
+
+def test_autovc_full_bench_config_properties():
+    """BASELINE configs[1] at full size (512 utterances x 128 frames, both batch groups of the persistent LSTM grid):
+    size-independent properties -- persistent == per-frame launches bit for bit, a slice of the big batch == the same
+    utterances converted alone, fused == unfused input projection within fp32-grade tolerance -- plus the oracle on a
+    few utterances."""
+    from autoformer_b200 import layers
+    args = (32, 256, 512, 32)
+    sd = seeded_state_dict(templates.autovc_template(*args), 21)
+    B, T = 512, 128
+    x, c_org, c_trg = synthetic_mel(B, T, 31).cuda(), synthetic_speaker(B, 31, "org").cuda(), synthetic_speaker(B, 31, "trg").cuda()
+    m = _model(args, sd, persistent=True)
+    big = m(x, c_org, c_trg)
+    m.persistent_lstm = False
+    step = m(x, c_org, c_trg)
+    for u, v in zip(big, step):
+        assert torch.equal(u, v)
+    idx = [0, 127, 128, 255, 256, 300, 511]                      # both CTAs of both pairs
+    sel = torch.tensor(idx, device="cuda")
+    m.persistent_lstm = True
+    small = m(x[sel], c_org[sel], c_trg[sel])
+    for u, v in zip(small, big):
+        # not bit-identical: 7 utterances take other tile shapes and the un-fused projection for the wide-input layer
+        assert rel_l2(u, v[sel]) < 5e-5
+    ref = autovc_forward(sd, x[sel].cpu(), c_org[sel].cpu(), c_trg[sel].cpu(), 32, 32)
+    for u, v in zip(big, ref):
+        assert rel_l2(u[sel], v) < 2e-4
+    unfused = _model(args, sd, persistent=True)
+    for lyr in unfused._plan().lstm1 + unfused._plan().lstm2:
+        lyr.fused = False
+    for u, v in zip(unfused(x, c_org, c_trg), big):
+        assert rel_l2(u, v) < 1e-4
+    assert isinstance(unfused._plan().lstm2[0], layers.LstmLayer)
