@@ -215,10 +215,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     if (lane == 0) {
       // ---------------- TMA producer (both CTAs of a pair: own A rows, own half of the B rows)
       RingState rs;
-      for (int unit = unit0; unit < p.num_units; unit += unit_stride) {
+      int itp = 0;
+      for (int unit = unit0; unit < p.num_units; unit += unit_stride, ++itp) {
         int b0, t0, n0;
         coords(unit, b0, t0, n0);
         int src = 0, base = 0;
+        // per-unit stamps of CTA 0 (profiling aid): 8 slots per unit after the 4-per-CTA block
+        long long* ud = (p.debug_clk && blockIdx.x == 0 && itp < 256) ? p.debug_clk + 4LL * gridDim.x + 8 * itp : nullptr;
+        if (ud) ud[0] = clock64();                                         // producer starts the unit
         for (int kb = 0; kb < p.num_kb; ++kb) {
           while (kb >= p.kb_end[src]) {
             base = p.kb_end[src];
@@ -244,6 +248,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           }
           rs.advance<C::kStages>();
         }
+        if (ud) ud[1] = clock64();                                         // all loads of the unit issued
       }
     }
   } else if (warp == 1) {
@@ -253,11 +258,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       int it = 0;
       for (int unit = unit0; unit < p.num_units; unit += unit_stride, ++it) {
         const int buf = it & 1;
+        long long* ud = (p.debug_clk && blockIdx.x == 0 && it < 256) ? p.debug_clk + 4LL * gridDim.x + 8 * it : nullptr;
+        if (ud) ud[2] = clock64();                                         // MMA thread reaches the unit
         mbar_wait(&s.tmem_empty[buf], ((it >> 1) & 1) ^ 1u);   // epilogue(s) have drained this accumulator buffer
         tc_fence_after();
+        if (ud) ud[3] = clock64();                                         // accumulator buffer free
         const uint32_t acc = tmem_base + buf * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&s.full[rs.stage], rs.phase);
+          if (ud && kb == 0) ud[4] = clock64();                            // first k-block landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.base + rs.stage * C::kStageBytes);
           issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, acc, kb == 0);
@@ -266,6 +275,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           rs.advance<C::kStages>();
         }
         if (CTAS == 2) umma_commit_2sm(&s.tmem_full[buf], 0x3); else umma_commit(&s.tmem_full[buf]);
+        if (ud) ud[5] = clock64();                                         // all MMAs of the unit issued
       }
     }
   } else {
@@ -279,6 +289,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       mbar_wait(&s.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       if (p.debug_clk && it == 0) clk_first = clock64();
+      long long* ud = (p.debug_clk && blockIdx.x == 0 && it < 256 && threadIdx.x == 64) ? p.debug_clk + 4LL * gridDim.x + 8 * it : nullptr;
+      if (ud) ud[6] = clock64();                                           // accumulator ready (epilogue warp 0)
       const uint32_t acc = tmem_base + buf * BN;
       uint64_t* eb = &s.tmem_empty[buf];
       switch (p.act) {   // the activation is resolved once per tile, not once per element
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         case AVC_ACT_LOG10_CLAMP: epilogue_tile<BN, AVC_ACT_LOG10_CLAMP>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
         default: epilogue_tile<BN, AVC_ACT_NONE>(p, s, acc, warp - 2, lane, b0, t0, n0, eb); break;
       }
+      if (ud) ud[7] = clock64();                                           // epilogue of the unit done (warp 0)
     }
     if (p.debug_clk && threadIdx.x == 64) {
       long long* d = p.debug_clk + 4LL * blockIdx.x;

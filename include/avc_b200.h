@@ -102,7 +102,10 @@ typedef struct avc_gemm_desc {
   int block_n;               /* 64 / 128 / 256; 0 = choose */
   int cta_group;             /* 2 = CTA pairs (tcgen05 cta_group::2, 256-row tiles), 1 = single CTA, 0 = default (2) */
   long long* debug_clk;      /* optional device buffer, 4 x int64 per CTA: clock64 at entry / setup done / accumulator
-                                ready / epilogue done (profiling aid; NULL in production) */
+                                ready / epilogue done, followed by 8 x int64 per tile unit of CTA 0 (first 256 units):
+                                producer start / loads issued / MMA thread at unit / accumulator buffer free / first
+                                k-block landed / MMAs issued / accumulator ready / epilogue done
+                                (profiling aid; NULL in production) */
 } avc_gemm_desc;
 
 int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
