@@ -1,23 +1,24 @@
-// Large-H LSTM recurrence on tcgen05 (see include/avc_b200.h: avc_lstm_seq).
+// Large-H LSTM layers on tcgen05 (see include/avc_b200.h: avc_lstm_seq).
 //
-// One time step is the GEMM  Z[B x 4H] = h_{t-1}[B x H] . W_hh^T  with the LSTM cell as its epilogue.
-// W_hh rows (and the xproj columns) are gate-interleaved in groups of G hidden units, so a 128 x 4G
-// accumulator tile holds all four gates of G units for 128 utterances: the epilogue thread that owns
-// accumulator row b updates c[b, u] / h[b, u] for those G units without any cross-thread traffic.
-// h_{t-1} is read by TMA straight out of the output sequence [B][T][H] (a 3-D box {128 B, 1 frame,
-// 128 utterances} at frame t-1), so there is no separate recurrent-state buffer.
+// One time step is the GEMM  Z[B x 4H] = [x_t | h_{t-1}] . [W_ih | W_hh]^T  with the LSTM cell as its epilogue.
+// Weight rows are gate-interleaved in groups of G hidden units, so a 128 x 4G accumulator tile holds all four gates
+// of G units for 128 utterances: the epilogue thread that owns accumulator row b updates c[b, u] / h[b, u] for those G
+// units without any cross-thread traffic.  h_{t-1} is read by TMA straight out of the output sequence [B][T][H] (a 3-D
+// box {128 B, 1 frame, 128 utterances} at frame t-1), so there is no separate recurrent-state buffer.
 //
-// The step is bound by streaming the operands from L2 into shared memory (W_hh is re-read every frame), so the
-// kernel minimises bytes per MMA:
-//   * CTA pairs (cta_group::2): a pair owns 256 utterances x 4G gate columns and each CTA stages only half of the
-//     W_hh tile;
-//   * split-bf16 ("fp32") mode loads {h_hi, h_lo, W_hi, W_lo} of a 64-channel chunk ONCE per stage and issues the
-//     three products hi*hi, lo*hi, hi*lo from them (4 tiles instead of the 6 a K-concatenated GEMM would load);
-//   * the epilogue L2-prefetches the next frame's xproj rows so the cell update does not wait on HBM.
+// The step is bound by the shared-memory port (MMA operand reads + TMA fills), so the kernels
+// minimise shared-memory bytes per MMA:
+//   * CTA pairs (cta_group::2): a pair owns 256 utterances x 4G gate columns and each CTA stages only half of the W tile;
+//   * split-bf16 ("fp32") mode loads {a_hi, a_lo, W_hi, W_lo} of a 64-channel chunk ONCE per stage and issues the
+//     three products hi*hi, lo*hi, hi*lo from them (4 tiles instead of the 6 a K-concatenated GEMM would load).
 //
-// Two launch modes share the kernel:
+// Two kernels:
+//   lstm_fused_kernel  (default) input projection and recurrence in one kernel, two TMEM accumulators: the x_t products
+//                      of frame t+1 run while the cell update and the grid barrier of frame t are in flight
+//   lstm_step_kernel   recurrence only, on a precomputed fp32 projection (xproj) -- small batches with wide inputs
+// and two launch modes for each:
 //   per-step    t_end = t_begin + 1, one launch per frame (stream order is the time dependency)
-//   persistent  one cooperative launch for all frames; a grid-wide barrier separates frames
+//   persistent  one cooperative launch for all frames; a barrier among the CTAs of a batch group separates frames
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include <type_traits>
@@ -49,26 +50,6 @@ struct alignas(64) LstmParams {
   int t_begin, t_end;
 };
 
-// All threads of all CTAs call this; `target` = number of arrivals expected so far (monotonic counter).
-__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    const long long t0 = clock64();
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-      if (seen < target && clock64() - t0 > 4000000000LL) {
-        printf("avc: grid barrier timeout block %d seen %u target %u\n", (int)blockIdx.x, seen, target);
-        __trap();
-      }
-    } while (seen < target);
-    __threadfence();
-  }
-  __syncthreads();
-}
-
 // Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
 // has already synchronised with this thread through the epi_done mbarrier.
 __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target, long long* stamp = nullptr) {
@@ -86,11 +67,6 @@ __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int
     }
   } while (seen < target);
 }
-
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 
 // Stores of one cell thread's 8 new hidden values (utterance row `row` = b*T + t, hidden units u..u+7): the recurrent
 // operand in the layer's operand format, plus the optional exact fp32 copies.
