@@ -10,7 +10,10 @@
 // minimise shared-memory bytes per MMA:
 //   * CTA pairs (cta_group::2): a pair owns 256 utterances x 4G gate columns and each CTA stages only half of the W tile;
 //   * split-bf16 ("fp32") mode loads {a_hi, a_lo, W_hi, W_lo} of a 64-channel chunk ONCE per stage and issues the
-//     three products hi*hi, lo*hi, hi*lo from them (4 tiles instead of the 6 a K-concatenated GEMM would load).
+//     three products hi*hi, lo*hi, hi*lo from them (4 tiles instead of the 6 a K-concatenated GEMM would load);
+//   * the W_hi and W_lo tiles of a stage are adjacent, so a_hi * [W_hi | W_lo] is ONE MMA of width 2 * BN into a
+//     2 * BN-column accumulator (the a_hi tile is read once for both products) and a_lo * W_hi a second MMA of width BN
+//     onto columns of the same gates; the cell warps add the two column blocks (SplitAcc below).
 //
 // Two kernels:
 //   lstm_fused_kernel  (default) input projection and recurrence in one kernel, two TMEM accumulators: the x_t products
@@ -50,6 +53,31 @@ struct alignas(64) LstmParams {
   int t_begin, t_end;
 };
 
+// Accumulator layout of the split-bf16 mode.  Wide MMA (N = 2 * BN): B rows = this CTA's [W_hi tile ; W_lo tile], so with
+// h = BN / CTAS gate columns per CTA the accumulator columns are, per CTA r of the pair, [hi*hi (h) | hi*lo (h)] at
+// 2 * h * r.  Narrow MMA (N = BN, a_lo * W_hi): CTA r's h columns land at kLoOffset + h * r; with kLoOffset = h (pair) or 0
+// (single CTA) every one of them falls on a block of the SAME gate columns, and z = first(c) + second(c).
+template <int BN, int CTAS, bool SPLIT>
+struct SplitAcc {
+  static constexpr int kHalf = BN / CTAS;
+  static constexpr int kCols = SPLIT ? 2 * BN : BN;                 // accumulator width in TMEM columns
+  static constexpr int kLoOffset = (SPLIT && CTAS == 2) ? kHalf : 0;
+  __device__ static constexpr int first(int c) { return (SPLIT && CTAS == 2 && c >= kHalf) ? c + kHalf : c; }
+  __device__ static constexpr int second(int c) { return first(c) + kHalf; }
+};
+
+// The MMAs of one landed stage (a_hi at `a_hi`, W tile(s) at `w_hi`) into the accumulator at `acc`.
+template <int BN, int MODE, int CTAS>
+__device__ __forceinline__ void issue_stage(uint32_t a_hi, uint32_t w_hi, uint32_t acc, bool first) {
+  constexpr bool BF16 = MODE != 0;
+  if (MODE == 2) {
+    issue_pair<2 * BN, BF16, CTAS>(a_hi, w_hi, acc, first);                                        // a_hi * [W_hi | W_lo]
+    issue_pair<BN, BF16, CTAS>(a_hi + kATileBytes, w_hi, acc + SplitAcc<BN, CTAS, true>::kLoOffset, false);  // a_lo * W_hi
+  } else {
+    issue_pair<BN, BF16, CTAS>(a_hi, w_hi, acc, first);
+  }
+}
+
 // Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
 // has already synchronised with this thread through the epi_done mbarrier.
 __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target, long long* stamp = nullptr) {
@@ -66,6 +94,31 @@ __device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int
       __trap();
     }
   } while (seen < target);
+}
+
+// Pre-activations (without bias / xproj) of hidden units j*8 .. j*8+7 of the tile for the four gates, from the
+// accumulator row this thread owns; in split mode the sum of the two column blocks of SplitAcc.
+template <class SA, int G>
+__device__ __forceinline__ void load_gates(uint32_t lane_addr, int j, float (&z)[4][8]) {
+  uint32_t a[4][8];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) tmem_ld_32x8(lane_addr + SA::first(g * G + j * 8), a[g]);
+  if (SA::kCols != 4 * G) {
+    uint32_t b[4][8];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_ld_32x8(lane_addr + SA::second(g * G + j * 8), b[g]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[g][e] = __uint_as_float(a[g][e]) + __uint_as_float(b[g][e]);
+  } else {
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[g][e] = __uint_as_float(a[g][e]);
+  }
 }
 
 // Stores of one cell thread's 8 new hidden values (utterance row `row` = b*T + t, hidden units u..u+7): the recurrent
@@ -111,9 +164,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
   constexpr int PARTS = MODE == 2 ? 2 : 1;
   constexpr int kXSlabs = BN / 32;                         // xproj tile = BN/32 swizzled slabs of 128 rows x 128 B
   constexpr int kXBytes = kXSlabs * kATileBytes;
-  using C = PipeCfg<BN, CTAS, PARTS, false, kXBytes>;
+  using SA = SplitAcc<BN, CTAS, MODE == 2>;
+  using C = PipeCfg<BN, CTAS, PARTS, false, kXBytes, 1, SA::kCols>;
   constexpr int G = BN / 4;
-  constexpr bool BF16 = MODE != 0;
   extern __shared__ uint8_t smem_raw[];
   const PipeSmem s = carve_smem<C>(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -234,11 +287,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           tc_fence_after();
           const uint32_t a_hi = smem_u32(s.base + rs.stage * C::kStageBytes);
           const uint32_t w_hi = a_hi + PARTS * kATileBytes;
-          issue_pair<BN, BF16, CTAS>(a_hi, w_hi, tmem_base, kb == 0);
-          if (PARTS == 2) {
-            issue_pair<BN, BF16, CTAS>(a_hi + kATileBytes, w_hi, tmem_base, false);            // h_lo * W_hi
-            issue_pair<BN, BF16, CTAS>(a_hi, w_hi + C::kBTileBytes, tmem_base, false);         // h_hi * W_lo
-          }
+          issue_stage<BN, MODE, CTAS>(a_hi, w_hi, tmem_base, kb == 0);
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
           rs.advance<C::kStages>();
         }
@@ -282,16 +331,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
       for (int jj = 0; jj < NJ; ++jj) {
         const int j = half + jj * (kEpiWarps / 4);
         if (j >= G / 8) break;
-        uint32_t acc[4][8];
+        float acc[4][8];
         if (has_mma) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) tmem_ld_32x8(lane_addr + g * G + j * 8, acc[g]);
-          tmem_ld_wait();
+          load_gates<SA, G>(lane_addr, j, acc);
         } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[g][e] = 0u;
+            for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
         }
         if (valid) {
           float z[4][8];
@@ -303,14 +350,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
             const int ch = (col & 31) >> 2;
             const float4 x0 = *reinterpret_cast<const float4*>(slab + ((ch ^ (xr & 7)) << 4));
             const float4 x1 = *reinterpret_cast<const float4*>(slab + (((ch + 1) ^ (xr & 7)) << 4));
-            z[g][0] = __uint_as_float(acc[g][0]) + x0.x;
-            z[g][1] = __uint_as_float(acc[g][1]) + x0.y;
-            z[g][2] = __uint_as_float(acc[g][2]) + x0.z;
-            z[g][3] = __uint_as_float(acc[g][3]) + x0.w;
-            z[g][4] = __uint_as_float(acc[g][4]) + x1.x;
-            z[g][5] = __uint_as_float(acc[g][5]) + x1.y;
-            z[g][6] = __uint_as_float(acc[g][6]) + x1.z;
-            z[g][7] = __uint_as_float(acc[g][7]) + x1.w;
+            z[g][0] = acc[g][0] + x0.x;
+            z[g][1] = acc[g][1] + x0.y;
+            z[g][2] = acc[g][2] + x0.z;
+            z[g][3] = acc[g][3] + x0.w;
+            z[g][4] = acc[g][4] + x1.x;
+            z[g][5] = acc[g][5] + x1.y;
+            z[g][6] = acc[g][6] + x1.z;
+            z[g][7] = acc[g][7] + x1.w;
           }
           const float4 c0 = cq[jj][0], c1 = cq[jj][1];
           const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
@@ -352,9 +399,9 @@ constexpr int kBiasBytes = 1024;
 template <int BN, int MODE, int CTAS>
 __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __grid_constant__ LstmParams p) {
   constexpr int PARTS = MODE == 2 ? 2 : 1;
-  using C = PipeCfg<BN, CTAS, PARTS, false, kBiasBytes, 2>;
+  using SA = SplitAcc<BN, CTAS, MODE == 2>;
+  using C = PipeCfg<BN, CTAS, PARTS, false, kBiasBytes, 2, SA::kCols>;
   constexpr int G = BN / 4;
-  constexpr bool BF16 = MODE != 0;
   static_assert(BN * 4 <= kBiasBytes - 16, "bias tile + the h_ready counter");
   extern __shared__ uint8_t smem_raw[];
   const PipeSmem s = carve_smem<C>(smem_raw);
@@ -433,7 +480,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
       RingState rs;
       for (int t = p.t_begin; t < p.t_end; ++t) {
         long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 8 : nullptr;
-        const uint32_t acc = tmem_base + static_cast<uint32_t>((t & 1) * BN);
+        const uint32_t acc = tmem_base + static_cast<uint32_t>((t & 1) * SA::kCols);
         const int total = p.num_kx + (t > 0 ? p.num_kb : 0);
         for (int i = 0; i < total; ++i) {
           if (dbg && i == p.num_kx) dbg[3] = clock64();                    // input part issued
@@ -442,11 +489,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
           tc_fence_after();
           const uint32_t a_hi = smem_u32(s.base + rs.stage * C::kStageBytes);
           const uint32_t w_hi = a_hi + PARTS * kATileBytes;
-          issue_pair<BN, BF16, CTAS>(a_hi, w_hi, acc, i == 0);
-          if (PARTS == 2) {
-            issue_pair<BN, BF16, CTAS>(a_hi + kATileBytes, w_hi, acc, false);            // a_lo * W_hi
-            issue_pair<BN, BF16, CTAS>(a_hi, w_hi + C::kBTileBytes, acc, false);         // a_hi * W_lo
-          }
+          issue_stage<BN, MODE, CTAS>(a_hi, w_hi, acc, i == 0);
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
           rs.advance<C::kStages>();
         }
@@ -535,29 +578,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
       acc_phase ^= 1u << buf;
       tc_fence_after();
       if (dbg && threadIdx.x == 64) dbg[4] = clock64();                    // accumulator ready
-      const uint32_t lane_addr = tmem_base + static_cast<uint32_t>(buf * BN) + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t lane_addr =
+          tmem_base + static_cast<uint32_t>(buf * SA::kCols) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
       for (int jj = 0; jj < NJ; ++jj) {
         const int j = half + jj * (kEpiWarps / 4);
         if (j >= G / 8) break;
-        uint32_t acc[4][8];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld_32x8(lane_addr + g * G + j * 8, acc[g]);
-        tmem_ld_wait();
+        float acc[4][8];
+        load_gates<SA, G>(lane_addr, j, acc);
         if (valid) {
           float z[4][8];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const float4 x0 = *reinterpret_cast<const float4*>(sbias + g * G + j * 8);       // broadcast reads
             const float4 x1 = *reinterpret_cast<const float4*>(sbias + g * G + j * 8 + 4);
-            z[g][0] = __uint_as_float(acc[g][0]) + x0.x;
-            z[g][1] = __uint_as_float(acc[g][1]) + x0.y;
-            z[g][2] = __uint_as_float(acc[g][2]) + x0.z;
-            z[g][3] = __uint_as_float(acc[g][3]) + x0.w;
-            z[g][4] = __uint_as_float(acc[g][4]) + x1.x;
-            z[g][5] = __uint_as_float(acc[g][5]) + x1.y;
-            z[g][6] = __uint_as_float(acc[g][6]) + x1.z;
-            z[g][7] = __uint_as_float(acc[g][7]) + x1.w;
+            z[g][0] = acc[g][0] + x0.x;
+            z[g][1] = acc[g][1] + x0.y;
+            z[g][2] = acc[g][2] + x0.z;
+            z[g][3] = acc[g][3] + x0.w;
+            z[g][4] = acc[g][4] + x1.x;
+            z[g][5] = acc[g][5] + x1.y;
+            z[g][6] = acc[g][6] + x1.z;
+            z[g][7] = acc[g][7] + x1.w;
           }
           const float4 c0 = cq[jj][0], c1 = cq[jj][1];
           const float cprev[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
@@ -586,8 +628,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
 template <int BN, int MODE, int CTAS, bool FUSED>
 static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t stream) {
   auto kern = FUSED ? lstm_fused_kernel<BN, MODE, CTAS> : lstm_step_kernel<BN, MODE, CTAS>;
-  using C = std::conditional_t<FUSED, PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, kBiasBytes, 2>,
-                               PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes>>;
+  constexpr int kAccCols = SplitAcc<BN, CTAS, MODE == 2>::kCols;
+  using C = std::conditional_t<FUSED, PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, kBiasBytes, 2, kAccCols>,
+                               PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes, 1, kAccCols>>;
   constexpr int kThreads = FUSED ? kFusedThreads : kNumThreads;
   static bool configured = false;
   if (!configured) {

@@ -25,7 +25,8 @@ constexpr int kStagingBytes = kEpiWarps * 32 * kStagingLd * 4;   // one 32 x 32 
 // STAGING: reserve the epilogue's per-warp transpose tiles.
 // EXTRA: bytes of kernel-specific shared memory (1024-byte aligned) placed after the stages, with one extra mbarrier.
 // ACC: accumulator buffers in tensor memory (2 = the epilogue of tile i overlaps the MMAs of tile i+1).
-template <int BN, int CTAS = 1, int PARTS = 1, bool STAGING = true, int EXTRA = 0, int ACC = 1>
+// ACCW: tensor-memory columns per accumulator buffer (BN, or 2 * BN for the split recurrence's wide accumulator).
+template <int BN, int CTAS = 1, int PARTS = 1, bool STAGING = true, int EXTRA = 0, int ACC = 1, int ACCW = BN>
 struct PipeCfg {
   static constexpr int kAcc = ACC;
   static constexpr int kCtas = CTAS;
@@ -40,7 +41,9 @@ struct PipeCfg {
   static constexpr int kBarOffset = kStagingOffset + (STAGING ? kStagingBytes : 0);
   // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], extra barrier, epilogue-done barrier, TMEM address word
   static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 6) * 8 + 16 + 1024 /* alignment slack */;
-  static constexpr uint32_t kTmemCols = BN * ACC < 32 ? 32 : BN * ACC;
+  static constexpr int kAccCols = ACCW;
+  static constexpr uint32_t kTmemCols = ACCW * ACC < 32 ? 32 : ACCW * ACC;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two, at most 512");
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
