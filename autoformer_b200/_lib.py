@@ -16,7 +16,7 @@ EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm",
            "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_transpose_pad",
            "avc_conv_to_mono_tanh", "avc_gn_stats", "avc_gn_pool_residual", "avc_gn_apply", "avc_patchify",
            "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes", "avc_global_stats", "avc_adain", "avc_audio_frames",
-           "avc_complex_mag"]
+           "avc_complex_mag", "avc_resblock"]
 
 
 MAX_SOURCES = 4
@@ -87,6 +87,32 @@ class LstmDesc(ctypes.Structure):
     ]
 
 
+class ResblockDesc(ctypes.Structure):
+    """struct avc_resblock_desc"""
+    _fields_ = [
+        ("xa", ctypes.c_void_p),
+        ("xa_ld", ctypes.c_longlong),
+        ("x", ctypes.c_void_p),
+        ("x_ld", ctypes.c_longlong),
+        ("w", ctypes.c_void_p),
+        ("bias3", ctypes.c_void_p),
+        ("bias1", ctypes.c_void_p),
+        ("B", ctypes.c_int),
+        ("L", ctypes.c_int),
+        ("C", ctypes.c_int),
+        ("dilation", ctypes.c_int),
+        ("out", ctypes.c_void_p),
+        ("out_ld", ctypes.c_longlong),
+        ("out_rows_per_utt", ctypes.c_int),
+        ("out_row0", ctypes.c_int),
+        ("out_reflect", ctypes.c_int),
+        ("out_raw", ctypes.c_void_p),
+        ("out_raw_ld", ctypes.c_longlong),
+        ("out2", ctypes.c_void_p),
+        ("out2_ld", ctypes.c_longlong),
+    ]
+
+
 _lib = None
 
 
@@ -107,6 +133,8 @@ def load():
     lib.avc_conv_gemm.restype = ctypes.c_int
     lib.avc_lstm_seq.argtypes = [ctypes.POINTER(LstmDesc), ctypes.c_void_p]
     lib.avc_lstm_seq.restype = ctypes.c_int
+    lib.avc_resblock.argtypes = [ctypes.POINTER(ResblockDesc), ctypes.c_void_p]
+    lib.avc_resblock.restype = ctypes.c_int
     lib.avc_bilstm_small.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]

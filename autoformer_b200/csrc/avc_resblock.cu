@@ -1,0 +1,420 @@
+// Fused MelGAN ResnetBlock for the narrow, long stages (C = 32 / 64 channels), split-bf16 precision
+// (see include/avc_b200.h: avc_resblock; melgan/modules.py:72-85).
+//
+//   y = W_sc x + W_1 LeakyReLU( W_3 *_d LeakyReLU(x) + b_3 ) + (b_1 + b_sc)
+//
+// Run layer by layer these blocks are bound by HBM and by bytes in flight: the dilated k3 convolution re-loads
+// every activation row once per tap and per split-precision term (9 k-blocks of 16 KB per 128-row tile, of which
+// 2 are new data), and the intermediate makes a round trip through HBM.  Here one CTA owns a tile of 128 output
+// samples of one utterance and
+//   * keeps all five weight matrices of the block resident in shared memory (80 KB for C = 64),
+//   * loads ONE window of 128 + 2d rows of LeakyReLU(x); the three taps are the same shared-memory tile read through
+//     operand descriptors whose start address is advanced by d rows (the 128-byte swizzle is a function of the
+//     absolute shared-memory address, so a row-shifted descriptor stays consistent: scripts/ubench/desc_shift.cu),
+//   * runs conv k3 -> TMEM -> (bias, LeakyReLU, hi/lo split) -> shared memory -> k1 + shortcut GEMM -> TMEM, so the
+//     intermediate never leaves the SM,
+//   * writes y / LeakyReLU(y) with TMA stores from swizzled staging tiles (full 128-byte rows).
+// HBM traffic per block: read LeakyReLU(x) + x, write y + LeakyReLU(y) -- 4 tensor passes instead of 6, and every
+// byte a CTA has in flight is new data.
+//
+// Split-bf16 products with one MMA per operand tile:
+//   C = 64: activation tiles a_hi, a_lo (128 B rows); weight tile rows [W_hi (64) ; W_lo (64)]:
+//           a_hi x tile (N = 128) -> D[0:64] = hi*hi, D[64:128] = hi*lo;  a_lo x tile[0:64] (N = 64) -> D[0:64] += lo*hi
+//   C = 32: one activation tile whose 128-byte rows are [a_hi (32) | a_lo (32)]; weight tile rows
+//           [ [W_hi | W_hi] (32) ; [W_lo | 0] (32) ]:  a x tile (N = 64) -> D[0:32] = hi*hi + lo*hi, D[32:64] = hi*lo
+// and in both cases z[c] = D[c] + D[C + c].
+//
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two warps per TMEM lane quarter, half of the
+// channels each).  Per tile: GEMM1 -> epilogue 1 (intermediate to shared memory) -> GEMM2 -> epilogue 2 (stores);
+// the window and x tiles of tile i+1 are loaded as soon as GEMM1 / GEMM2 of tile i have consumed theirs, and GEMM1 of
+// tile i+1 runs under epilogue 2 of tile i.  C = 32 runs two CTAs per SM.
+#include <cuda_bf16.h>
+
+#include "../../include/avc_b200.h"
+#include "avc_host.h"
+#include "avc_pipe.cuh"
+
+namespace avc {
+
+template <int C>
+struct RbCfg {
+  static_assert(C == 32 || C == 64, "fused ResnetBlock: 32 or 64 channels");
+  static constexpr int kParts = C == 64 ? 2 : 1;              // operand tiles per block of rows
+  static constexpr int kMaxDilation = 16;
+  static constexpr int kWinTile = (kBlockM + 2 * kMaxDilation) * kRowBytes;   // 20 KB
+  static constexpr int kWTile = 2 * C * kRowBytes;
+  static constexpr int kOffW = 0;                              // W3 tap 0..2, W1, Wsc
+  static constexpr int kOffWin = kOffW + 5 * kWTile;
+  static constexpr int kOffXr = kOffWin + kParts * kWinTile;
+  static constexpr int kOffMid = kOffXr + kParts * kATileBytes;
+  static constexpr int kOffStage = kOffMid + kParts * kATileBytes;     // 128 rows x C x 4 bytes
+  static constexpr int kOffBias = kOffStage + kParts * kATileBytes;
+  static constexpr int kOffBar = kOffBias + 1024;
+  static constexpr int kSmemBytes = kOffBar + 128 + 1024 /* alignment slack */;
+  static constexpr uint32_t kTmemCols = 4 * C;                 // D1 and D2, 2C columns each
+  static constexpr int kCtasPerSm = C == 32 ? 2 : 1;
+  static_assert(kSmemBytes * kCtasPerSm + 1024 * kCtasPerSm <= 228 * 1024, "shared memory budget exceeded");
+};
+
+constexpr int kRbThreads = 64 + 32 * kEpiWarps;
+
+struct alignas(64) RbParams {
+  CUtensorMap tmap_win[2];    // LeakyReLU(x) with halo rows, (64, L + 2d, B) bf16, box {64, 128 + 2d, 1}
+  CUtensorMap tmap_xr[2];     // x, (64, L, B), box {64, 128, 1}
+  CUtensorMap tmap_out[2];    // LeakyReLU(y), operand format
+  CUtensorMap tmap_raw[2];    // y, operand format
+  CUtensorMap tmap_out2[2];   // LeakyReLU(y), fp32 (32, B * L), box {32, 128}
+  const uint4* w;             // [5][2C][8 x 16 B]
+  const float* bias3;
+  const float* bias1;
+  __nv_bfloat16* out;
+  long long out_ld;
+  int out_rows_per_utt, out_row0, out_reflect;
+  int has_out, has_raw, has_out2;
+  int B, L, dilation;
+  int n_tiles, tiles_per_utt;
+};
+
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the committed stores have finished READING shared memory (the tiles may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); }
+
+// z[e] = D[col + e] + D[col + C + e] for NCH consecutive channels of the accumulator row this thread owns.
+template <int C, int NCH>
+__device__ __forceinline__ void load_sum(uint32_t taddr, float (&z)[NCH]) {
+  uint32_t a[NCH], b[NCH];
+  if constexpr (NCH == 32) {
+    tmem_ld_32x32(taddr, a);
+    tmem_ld_32x32(taddr + C, b);
+  } else {
+    tmem_ld_32x16(taddr, a);
+    tmem_ld_32x16(taddr + C, b);
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int e = 0; e < NCH; ++e) z[e] = __uint_as_float(a[e]) + __uint_as_float(b[e]);
+}
+
+// The MMAs of one activation source (tiles a0 [, a1]) against one weight tile.
+template <int C>
+__device__ __forceinline__ void issue_src(uint32_t a0, uint32_t a1, uint32_t w, uint32_t d, bool first) {
+  if (C == 64) {
+    constexpr uint32_t wide = umma_idesc(kBlockM, 128, false), narrow = umma_idesc(kBlockM, 64, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(w + k * 32), wide, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16(d, umma_desc_sw128(a1 + k * 32), umma_desc_sw128(w + k * 32), narrow, 1u);
+  } else {
+    constexpr uint32_t idesc = umma_idesc(kBlockM, 64, false);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(d, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(w + k * 32), idesc, (first && k == 0) ? 0u : 1u);
+  }
+}
+
+__device__ __forceinline__ float lrelu(float v) { return v > 0.0f ? v : 0.2f * v; }
+
+// Writes NCH channels starting at channel c0 of row `row` as split bf16 into operand tile(s) at `tiles`
+// (C = 64: hi tile, lo tile; C = 32: one tile with [hi | lo] rows), 128-byte swizzle.
+template <int C, int NCH>
+__device__ __forceinline__ void write_split(uint8_t* tiles, int row, int c0, const float (&v)[NCH], uint4 (&hi)[NCH / 8],
+                                            uint4 (&lo)[NCH / 8]) {
+#pragma unroll
+  for (int j = 0; j < NCH / 8; ++j) {
+    float l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) l[e] = v[j * 8 + e] - __bfloat162float(__float2bfloat16_rn(v[j * 8 + e]));
+    hi[j] = make_uint4(pack_bf16(v[j * 8], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                       pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+    lo[j] = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+    const int chunk = c0 / 8 + j;
+    uint8_t* r = tiles + row * kRowBytes;
+    if (C == 64) {
+      *reinterpret_cast<uint4*>(r + ((chunk ^ (row & 7)) << 4)) = hi[j];
+      *reinterpret_cast<uint4*>(r + kATileBytes + ((chunk ^ (row & 7)) << 4)) = lo[j];
+    } else {
+      *reinterpret_cast<uint4*>(r + ((chunk ^ (row & 7)) << 4)) = hi[j];
+      *reinterpret_cast<uint4*>(r + (((chunk + 4) ^ (row & 7)) << 4)) = lo[j];
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kRbThreads, RbCfg<C>::kCtasPerSm) resblock_kernel(const __grid_constant__ RbParams p) {
+  using Cfg = RbCfg<C>;
+  constexpr int P = Cfg::kParts;
+  constexpr int NCH = C / 2;                 // channels per epilogue thread
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = base + Cfg::kOffW;
+  uint8_t* s_win = base + Cfg::kOffWin;
+  uint8_t* s_xr = base + Cfg::kOffXr;
+  uint8_t* s_mid = base + Cfg::kOffMid;
+  uint8_t* s_stage = base + Cfg::kOffStage;
+  float* s_bias = reinterpret_cast<float*>(base + Cfg::kOffBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + Cfg::kOffBar);
+  uint64_t* win_full = bars + 0;
+  uint64_t* xr_full = bars + 1;
+  uint64_t* d1_full = bars + 2;      // GEMM1 done: accumulator 1 ready, window tile free
+  uint64_t* d2_full = bars + 3;      // GEMM2 done: accumulator 2 ready, x and intermediate tiles free
+  uint64_t* mid_ready = bars + 4;    // intermediate written (and accumulator 1 drained) by all epilogue warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int win_rows = kBlockM + 2 * p.dilation;
+
+  if (threadIdx.x == 0) {
+    mbar_init(win_full, 1);
+    mbar_init(xr_full, 1);
+    mbar_init(d1_full, 1);
+    mbar_init(d2_full, 1);
+    mbar_init(mid_ready, kEpiWarps);
+    fence_mbar_init();
+#pragma unroll
+    for (int part = 0; part < P; ++part) {
+      prefetch_tmap(&p.tmap_win[part]);
+      prefetch_tmap(&p.tmap_xr[part]);
+    }
+  }
+  // weight tiles -> shared memory, 128-byte swizzle (row n, 16-byte chunk c at n * 128 + ((c ^ n % 8) << 4))
+  for (int i = threadIdx.x; i < 5 * 2 * C * 8; i += kRbThreads) {
+    const int n = i >> 3, c = i & 7;         // n runs over the rows of all five tiles (tiles are contiguous)
+    *reinterpret_cast<uint4*>(s_w + n * kRowBytes + ((c ^ (n & 7)) << 4)) = p.w[i];
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += kRbThreads) s_bias[i] = i < C ? p.bias3[i] : p.bias1[i - C];
+  fence_proxy_async();          // the tensor core reads the weight tiles through the async proxy
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
+  const uint32_t d1 = tmem_base, d2 = tmem_base + 2 * C;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
+        if (it > 0) mbar_wait(d1_full, (it - 1) & 1);
+        mbar_arrive_expect_tx(win_full, P * win_rows * kRowBytes);
+#pragma unroll
+        for (int part = 0; part < P; ++part)
+          tma_load_3d(s_win + part * Cfg::kWinTile, &p.tmap_win[part], win_full, 0, t0, b);
+        if (it > 0) mbar_wait(d2_full, (it - 1) & 1);
+        mbar_arrive_expect_tx(xr_full, P * kATileBytes);
+#pragma unroll
+        for (int part = 0; part < P; ++part)
+          tma_load_3d(s_xr + part * kATileBytes, &p.tmap_xr[part], xr_full, 0, t0, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t w = smem_u32(s_w), win = smem_u32(s_win), xr = smem_u32(s_xr), mid = smem_u32(s_mid);
+      const uint32_t shift = p.dilation * kRowBytes;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(win_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int tap = 0; tap < 3; ++tap)
+          issue_src<C>(win + tap * shift, win + Cfg::kWinTile + tap * shift, w + tap * Cfg::kWTile, d1, tap == 0);
+        umma_commit(d1_full);
+        mbar_wait(mid_ready, it & 1);
+        mbar_wait(xr_full, it & 1);
+        tc_fence_after();
+        issue_src<C>(mid, mid + kATileBytes, w + 3 * Cfg::kWTile, d2, true);
+        issue_src<C>(xr, xr + kATileBytes, w + 4 * Cfg::kWTile, d2, false);
+        umma_commit(d2_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int h = (warp - 2) >> 2;             // which half of the channels
+    const int row = q * 32 + lane;
+    const int c0 = h * NCH;
+    const uint32_t lane_addr = (static_cast<uint32_t>(q * 32) << 16) + c0;
+    const bool storer = threadIdx.x == 64;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
+      float v[NCH];
+      uint4 hi[NCH / 8], lo[NCH / 8];
+      // ---- epilogue 1: intermediate = LeakyReLU(conv3 + b3) as an operand tile in shared memory
+      mbar_wait(d1_full, it & 1);
+      tc_fence_after();
+      load_sum<C, NCH>(d1 + lane_addr, v);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) v[e] = lrelu(v[e] + s_bias[c0 + e]);
+      if (it > 0) {          // the previous tile's TMA stores must have read the staging tiles (mid, stage)
+        if (storer) bulk_wait_read();
+        epilogue_bar();
+      }
+      write_split<C, NCH>(s_mid, row, c0, v, hi, lo);
+      fence_proxy_async();   // generic-proxy writes -> tensor-core (async proxy) reads
+      tc_fence_before();     // ... and this warp's reads of accumulator 1 before the next GEMM1
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mid_ready);
+      // ---- epilogue 2: y = k1(mid) + shortcut(x) + bias; stores
+      mbar_wait(d2_full, it & 1);
+      tc_fence_after();
+      load_sum<C, NCH>(d2 + lane_addr, v);
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) v[e] += s_bias[C + c0 + e];
+      if (p.has_raw) write_split<C, NCH>(s_mid, row, c0, v, hi, lo);      // GEMM2 has consumed the intermediate
+#pragma unroll
+      for (int e = 0; e < NCH; ++e) v[e] = lrelu(v[e]);
+      if (p.has_out) {
+        write_split<C, NCH>(s_stage, row, c0, v, hi, lo);
+        if (p.out_reflect > 0) {       // ReflectionPad1d rows of the consumer: time -k = time k, time L-1+k = time L-1-k
+          const int t = t0 + row;
+          int dst[2] = {-1, -1};
+          if (t >= 1 && t <= p.out_reflect) dst[0] = p.out_row0 - t;
+          if (t <= p.L - 2 && t >= p.L - 1 - p.out_reflect) dst[1] = p.out_row0 + 2 * (p.L - 1) - t;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            if (dst[s] < 0) continue;
+            __nv_bfloat16* o = p.out + ((long long)b * p.out_rows_per_utt + dst[s]) * p.out_ld + c0;
+#pragma unroll
+            for (int j = 0; j < NCH / 8; ++j) {
+              *reinterpret_cast<uint4*>(o + j * 8) = hi[j];
+              *reinterpret_cast<uint4*>(o + C + j * 8) = lo[j];
+            }
+          }
+        }
+      } else if (p.has_out2) {         // exact fp32 rows of 32 floats per 128-byte tile row
+#pragma unroll
+        for (int j = 0; j < NCH / 4; ++j) {
+          const int f = c0 + j * 4;
+          uint8_t* r = s_stage + (f >> 5) * kATileBytes + row * kRowBytes;
+          *reinterpret_cast<float4*>(r + ((((f & 31) >> 2) ^ (row & 7)) << 4)) =
+              make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        }
+      }
+      fence_proxy_async();   // staging tiles -> TMA store (async proxy)
+      tc_fence_before();
+      epilogue_bar();
+      if (storer) {
+#pragma unroll
+        for (int part = 0; part < P; ++part) {
+          if (p.has_raw) tma_store_3d(&p.tmap_raw[part], s_mid + part * kATileBytes, 0, t0, b);
+          if (p.has_out) tma_store_3d(&p.tmap_out[part], s_stage + part * kATileBytes, 0, p.out_row0 + t0, b);
+          else if (p.has_out2) tma_store_2d(&p.tmap_out2[part], s_stage + part * kATileBytes, 0, b * p.L + t0);
+        }
+        bulk_commit();
+      }
+    }
+    if (storer) bulk_wait_all();
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int C>
+static int launch(const RbParams& p, cudaStream_t stream) {
+  using Cfg = RbCfg<C>;
+  auto kern = resblock_kernel<C>;
+  static bool configured = false;
+  if (!configured) {
+    AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int max_ctas = num_sms() * Cfg::kCtasPerSm;
+  const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+  kern<<<grid, kRbThreads, Cfg::kSmemBytes, stream>>>(p);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace avc
+
+extern "C" int avc_resblock(const avc_resblock_desc* d, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(d != nullptr, "avc_resblock: null descriptor");
+  AVC_REQUIRE(d->C == 32 || d->C == 64, "avc_resblock: C=%d (32 or 64)", d->C);
+  AVC_REQUIRE(d->B > 0 && d->L > 0 && d->L % kBlockM == 0, "avc_resblock: B=%d L=%d (L must be a multiple of 128)",
+              d->B, d->L);
+  AVC_REQUIRE(d->dilation >= 1 && d->dilation <= 16, "avc_resblock: dilation %d (1..16)", d->dilation);
+  AVC_REQUIRE(d->xa && d->x && d->w && d->bias3 && d->bias1, "avc_resblock: missing buffer");
+  AVC_REQUIRE(d->xa_ld >= 2 * d->C && d->x_ld >= 2 * d->C, "avc_resblock: input row strides too small");
+  AVC_REQUIRE(d->out || d->out_raw || d->out2, "avc_resblock: no output requested");
+  AVC_REQUIRE(!(d->out && d->out2), "avc_resblock: out and out2 are exclusive");
+  AVC_REQUIRE((long long)d->B * d->L < (1LL << 31), "avc_resblock: B*L too large");
+  const int C = d->C, P = C == 64 ? 2 : 1;
+  const uint64_t B = (uint64_t)d->B, L = (uint64_t)d->L;
+  RbParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t win_rows = L + 2 * d->dilation;
+  for (int part = 0; part < P; ++part) {
+    const __nv_bfloat16* xa = static_cast<const __nv_bfloat16*>(d->xa) + part * 64;
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(d->x) + part * 64;
+    if (!encode_tmap_3d(&p.tmap_win[part], 2, xa, 64, win_rows, B, (uint64_t)d->xa_ld * 2, win_rows * d->xa_ld * 2, 64,
+                        kBlockM + 2 * d->dilation, 1))
+      return -3;
+    if (!encode_tmap_3d(&p.tmap_xr[part], 2, x, 64, L, B, (uint64_t)d->x_ld * 2, L * d->x_ld * 2, 64, kBlockM, 1))
+      return -3;
+    if (d->out) {
+      AVC_REQUIRE(d->out_ld >= 2 * C && d->out_row0 >= d->out_reflect && d->out_reflect >= 0 && d->out_reflect <= 16 &&
+                      d->out_rows_per_utt >= d->out_row0 + d->L + d->out_reflect,
+                  "avc_resblock: bad out geometry (ld %lld rows %d row0 %d reflect %d)", d->out_ld,
+                  d->out_rows_per_utt, d->out_row0, d->out_reflect);
+      const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(d->out) + part * 64;
+      if (!encode_tmap_3d(&p.tmap_out[part], 2, o, 64, (uint64_t)d->out_rows_per_utt, B, (uint64_t)d->out_ld * 2,
+                          (uint64_t)d->out_rows_per_utt * d->out_ld * 2, 64, kBlockM, 1))
+        return -3;
+    }
+    if (d->out_raw) {
+      AVC_REQUIRE(d->out_raw_ld >= 2 * C, "avc_resblock: out_raw_ld too small");
+      const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(d->out_raw) + part * 64;
+      if (!encode_tmap_3d(&p.tmap_raw[part], 2, o, 64, L, B, (uint64_t)d->out_raw_ld * 2, L * d->out_raw_ld * 2, 64,
+                          kBlockM, 1))
+        return -3;
+    }
+    if (d->out2) {
+      AVC_REQUIRE(d->out2_ld >= C, "avc_resblock: out2_ld too small");
+      if (!encode_tmap_2d(&p.tmap_out2[part], 4, d->out2 + part * 32, 32, B * L, (uint64_t)d->out2_ld * 4, 32, kBlockM))
+        return -3;
+    }
+  }
+  p.w = static_cast<const uint4*>(d->w);
+  p.bias3 = d->bias3;
+  p.bias1 = d->bias1;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_ld = d->out_ld;
+  p.out_rows_per_utt = d->out_rows_per_utt;
+  p.out_row0 = d->out_row0;
+  p.out_reflect = d->out ? d->out_reflect : 0;
+  p.has_out = d->out != nullptr;
+  p.has_raw = d->out_raw != nullptr;
+  p.has_out2 = d->out2 != nullptr;
+  p.B = d->B;
+  p.L = d->L;
+  p.dilation = d->dilation;
+  p.tiles_per_utt = d->L / kBlockM;
+  p.n_tiles = d->B * p.tiles_per_utt;
+  return C == 64 ? launch<64>(p, stream) : launch<32>(p, stream);
+}

@@ -9,9 +9,13 @@ The module tree only HOLDS parameters under the reference's state_dict names (``
                                        epilogue writes both x (for the shortcut) and LeakyReLU(x) with the reflected
                                        halo rows the next dilated conv needs
   ResnetBlock                       -> [k3 dilated conv + LeakyReLU] then ONE GEMM over the K-concatenated pair
-                                       (block output, shortcut input) x [W_k1 | W_shortcut]
+                                       (block output, shortcut input) x [W_k1 | W_shortcut]; the narrow, long stages
+                                       (C = 64 / 32) run each block as ONE fused kernel (avc_resblock) with the
+                                       intermediate in shared memory and the weights resident
   LeakyReLU + ReflectionPad1d(3) + WNConv1d(32 -> 1, k7) + Tanh -> avc_conv_to_mono_tanh
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -65,7 +69,12 @@ class _Plan:
                 k1 = ops.ConvGemm(*packing.pack_conv_sources([W(p + ".block.4"), W(p + ".shortcut")],
                                                              b(p + ".block.4") + b(p + ".shortcut"), precision),
                                   tap_t0=[0, 0], act="lrelu", tag="melgan_conv")
-                blocks.append((d, c3, k1))
+                fused = None
+                if precision == "fp32" and c_out in packing.RESBLOCK_CHANNELS:
+                    fused = ops.Resblock(*packing.pack_resblock(W(p + ".block.2"), b(p + ".block.2"), W(p + ".block.4"),
+                                                                b(p + ".block.4"), W(p + ".shortcut"),
+                                                                b(p + ".shortcut")), dilation=d)
+                blocks.append((d, c3, k1, fused))
             self.stages.append((r, c_out, up, blocks))
             idx += 2 + gen.n_residual_layers
         wf = W(f"model.{idx + 2}")                                        # (1, ngf, 7)
@@ -161,6 +170,8 @@ class Generator(nn.Module):
         self.precision = "fp32"
         self.collect_taps = False
         self.taps = {}
+        # AVC_MELGAN_FUSED=0 (profiling aid): run every ResnetBlock as two avc_conv_gemm launches
+        self.fuse_resblocks = os.environ.get("AVC_MELGAN_FUSED", "1") != "0"
         self._cache = layers.PlanCache()
 
     def _plan(self):
@@ -192,25 +203,31 @@ class Generator(nn.Module):
             up(cur, B, L, out=xa, out_row0=d0, reflect=d0, out_raw=x_raw, phases=r)     # ConvTranspose1d
             if taps is not None:
                 taps[f"up{si}"] = packing.act_to_float(x_raw, prec)
-            for j, (d, c3, k1) in enumerate(blocks):
-                h1 = ops.alloc_act(B, Lr, C, prec, dev)
-                c3(xa, B, Lr, out=h1)                                     # block.0-3
+            fuse = self.fuse_resblocks and ops.Resblock.eligible(C, Lr, prec)
+            for j, (d, c3, k1, fused) in enumerate(blocks):
+                if fuse and fused is not None:
+                    # block.0-4 + shortcut in one kernel (intermediate in shared memory)
+                    run = lambda _f=fused, _xa=xa, _x=x_raw, **kw: _f(_xa, _x, B, Lr, **kw)
+                else:
+                    h1 = ops.alloc_act(B, Lr, C, prec, dev)
+                    c3(xa, B, Lr, out=h1)                                 # block.0-3
+                    run = lambda _k1=k1, _h1=h1, _x=x_raw, **kw: _k1([_h1, _x], B, Lr, **kw)   # block.4 + shortcut
                 if j + 1 < len(blocks):
                     dn = blocks[j + 1][0]
                     y_raw = ops.alloc_act(B, Lr, C, prec, dev)
                     ya = ops.alloc_act(B, Lr + 2 * dn, C, prec, dev)
-                    k1([h1, x_raw], B, Lr, out=ya, out_row0=dn, reflect=dn, out_raw=y_raw)   # block.4 + shortcut
+                    run(out=ya, out_row0=dn, reflect=dn, out_raw=y_raw)
                     x_raw, xa = y_raw, ya
                 elif si + 1 < n_stage:
                     cur = ops.alloc_act(B, Lr, C, prec, dev)
                     raw = ops.alloc_act(B, Lr, C, prec, dev) if taps is not None else None
-                    k1([h1, x_raw], B, Lr, out=cur, out_raw=raw)
+                    run(out=cur, out_raw=raw)
                     if taps is not None:
                         taps[f"stage{si}"] = packing.act_to_float(raw, prec)
                 else:
                     final = torch.empty(B * Lr, C, dtype=torch.float32, device=dev)
                     raw = ops.alloc_act(B, Lr, C, prec, dev) if taps is not None else None
-                    k1([h1, x_raw], B, Lr, out2=final, out_raw=raw)
+                    run(out2=final, out_raw=raw)
                     if taps is not None:
                         taps[f"stage{si}"] = packing.act_to_float(raw, prec)
             L = Lr

@@ -373,6 +373,57 @@ def conv_to_mono_tanh(x, w, bias):
     return out
 
 
+class Resblock:
+    """One MelGAN ResnetBlock bound to the fused kernel avc_resblock (split-bf16 precision, C = 32 / 64).
+
+    ``w``/``bias3``/``bias1`` come from ``packing.pack_resblock``."""
+
+    def __init__(self, w, bias3, bias1, dilation, tag="melgan_res"):
+        self.w, self.bias3, self.bias1 = w, bias3, bias1
+        self.C = w.shape[1] // 2
+        self.dilation = dilation
+        self.tag = tag
+
+    @staticmethod
+    def eligible(C, L, precision):
+        return precision == "fp32" and C in packing.RESBLOCK_CHANNELS and L % 128 == 0
+
+    def to(self, device):
+        self.w, self.bias3, self.bias1 = self.w.to(device), self.bias3.to(device), self.bias1.to(device)
+        return self
+
+    def __call__(self, xa, x, B, L, out=None, out_row0=0, reflect=0, out_raw=None, out2=None):
+        """xa [B][L + 2d][2C] LeakyReLU(x) with reflected halo rows, x [B][L][2C] (split bf16).
+        out: LeakyReLU(y) [B][rows][2C] at rows out_row0 + t (+ `reflect` mirrored halo rows); out_raw: y [B][L][2C];
+        out2: LeakyReLU(y) as exact fp32 [B*L][C]."""
+        lib = _lib.load()
+        C, d = self.C, self.dilation
+        _require_cuda(self.w, xa, x)
+        for a, rows in ((xa, L + 2 * d), (x, L)):
+            assert a.dtype == torch.bfloat16 and a.dim() == 3 and a.shape == (B, rows, 2 * C), (a.shape, (B, rows, 2 * C))
+            assert a.stride(2) == 1 and a.stride(0) == rows * a.stride(1)
+        desc = _lib.ResblockDesc()
+        desc.xa, desc.xa_ld = xa.data_ptr(), xa.stride(1)
+        desc.x, desc.x_ld = x.data_ptr(), x.stride(1)
+        desc.w, desc.bias3, desc.bias1 = self.w.data_ptr(), self.bias3.data_ptr(), self.bias1.data_ptr()
+        desc.B, desc.L, desc.C, desc.dilation = B, L, C, d
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.bfloat16 and out.dim() == 3 and out.shape[0] == B
+            assert out.shape[2] == 2 * C and out.stride(2) == 1 and out.stride(0) == out.shape[1] * out.stride(1)
+            desc.out, desc.out_ld = out.data_ptr(), out.stride(1)
+            desc.out_rows_per_utt, desc.out_row0, desc.out_reflect = out.shape[1], out_row0, reflect
+        if out_raw is not None:
+            assert out_raw.is_cuda and out_raw.dtype == torch.bfloat16 and out_raw.shape == (B, L, 2 * C)
+            assert out_raw.is_contiguous()
+            desc.out_raw, desc.out_raw_ld = out_raw.data_ptr(), out_raw.stride(1)
+        if out2 is not None:
+            assert out2.is_cuda and out2.dtype == torch.float32 and out2.shape == (B * L, C) and out2.is_contiguous()
+            desc.out2, desc.out2_ld = out2.data_ptr(), out2.stride(0)
+        with PROFILER.span(self.tag, flops=2.0 * 5 * C * C * B * L):
+            _lib.check(lib.avc_resblock(ctypes.byref(desc), _stream()), "avc_resblock")
+        return out if out is not None else (out2 if out2 is not None else out_raw)
+
+
 # ------------------------------------------------------------------------------------------------ Meta glue
 def _ptr(t):
     return t.data_ptr() if t is not None else None

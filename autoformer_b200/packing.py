@@ -136,6 +136,30 @@ def pack_linear(weight, bias, precision, block_n=None):
     return pack_conv_sources([weight.unsqueeze(-1)], bias, precision, block_n)
 
 
+RESBLOCK_CHANNELS = (32, 64)      # widths the fused ResnetBlock kernel (avc_resblock) is built for
+
+
+def pack_resblock(w3, b3, w1, b1, wsc, bsc):
+    """Weights of one MelGAN ResnetBlock (melgan/modules.py:72-85, weight norm already folded) for avc_resblock.
+
+    w3 (C, C, 3) dilated conv, w1 / wsc (C, C, 1) block.4 / shortcut.  Returns (W [5][2C][64] bf16, bias3 [C], bias1 [C])
+    with tiles W3 tap 0..2, W1, Wsc in the split-bf16 tile layouts of include/avc_b200.h:
+      C = 64: rows [w_hi (64) ; w_lo (64)];   C = 32: rows [[w_hi | w_hi] (32) ; [w_lo | 0] (32)]."""
+    c = w3.shape[0]
+    assert c in RESBLOCK_CHANNELS and w3.shape == (c, c, 3) and w1.shape == (c, c, 1) and wsc.shape == (c, c, 1)
+    mats = [w3[:, :, 0], w3[:, :, 1], w3[:, :, 2], w1[:, :, 0], wsc[:, :, 0]]
+    tiles = []
+    for m in mats:
+        hi, lo = split_bf16(m)
+        if c == 64:
+            tiles.append(torch.cat([hi, lo], dim=0))
+        else:
+            tiles.append(torch.cat([torch.cat([hi, hi], dim=1), torch.cat([lo, torch.zeros_like(lo)], dim=1)], dim=0))
+    w = torch.stack(tiles).contiguous()
+    assert w.shape == (5, 2 * c, 64) and w.dtype == torch.bfloat16
+    return w, b3.float().contiguous(), (b1.float() + bsc.float()).contiguous()
+
+
 def gate_permutation(hidden: int, group: int, device=None) -> torch.Tensor:
     """index[p] = PyTorch gate row (g*H + u) stored at packed position p = (u//G)*4G + g*G + u%G."""
     assert hidden % group == 0

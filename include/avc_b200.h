@@ -111,6 +111,47 @@ typedef struct avc_gemm_desc {
 int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
 
 /*
+ * Fused MelGAN ResnetBlock (melgan/modules.py:72-85) for the narrow stages, split-bf16 precision (dtype 2):
+ *
+ *   y = W_sc x + W_1 LeakyReLU( W_3 *_d LeakyReLU(ReflectionPad_d(x)) + b_3 ) + (b_1 + b_sc)
+ *
+ * One kernel: the dilated k3 convolution, the LeakyReLU between, the k1 convolution and the k1 shortcut; the
+ * intermediate stays in shared memory / tensor memory, the block's weights stay resident in shared memory, and each
+ * input row is loaded once (the three taps read one shared-memory window through row-shifted descriptors).
+ * Same results as the two avc_conv_gemm launches it replaces (up to fp32 summation order).
+ *   xa      [B][L + 2*dilation][xa_ld]  LeakyReLU(x) in split bf16 ([hi(C) | lo(C)]), time t at row t + dilation, the
+ *           halo rows hold the reflected samples (written by the producer: out / out_row0 / out_reflect below)
+ *   x       [B][L][x_ld]                x in split bf16 (the shortcut input)
+ *   w       [5][2C][64] bf16: tiles W3 tap 0, 1, 2, W1 (block.4), Wsc (shortcut).  C = 64: tile rows [w_hi (64) ; w_lo (64)]
+ *           over the 64 input channels; C = 32: rows [ [w_hi | w_hi] (32) ; [w_lo | 0] (32) ]  (packing.pack_resblock)
+ *   bias3   [C] fp32 (block.2);  bias1 [C] fp32 (block.4 bias + shortcut bias)
+ *   out     LeakyReLU(y), split bf16 [B][out_rows_per_utt][out_ld] at row out_row0 + t, plus out_reflect mirrored halo
+ *           rows each side (the next block's ReflectionPad1d)           -- optional
+ *   out_raw y, split bf16 [B][L][out_raw_ld]                            -- optional
+ *   out2    LeakyReLU(y), exact fp32 [B*L][out2_ld]                      -- optional, exclusive with out
+ * C is 32 or 64, L a multiple of 128, 1 <= dilation <= 16.
+ */
+typedef struct avc_resblock_desc {
+  const void* xa;
+  long long xa_ld;
+  const void* x;
+  long long x_ld;
+  const void* w;
+  const float* bias3;
+  const float* bias1;
+  int B, L, C, dilation;
+  void* out;
+  long long out_ld;
+  int out_rows_per_utt, out_row0, out_reflect;
+  void* out_raw;
+  long long out_raw_ld;
+  float* out2;
+  long long out2_ld;
+} avc_resblock_desc;
+
+int avc_resblock(const avc_resblock_desc* d, void* stream);
+
+/*
  * Recurrence of one uni-directional LSTM layer with hidden size H (multiple of gate_group, >= 64):
  * for t = 0..T-1:  z = xproj[b,t,:] + W_hh h_{t-1}   (xproj = W_ih x_t + b_ih + b_hh, precomputed or fused);  c = s(z_f) c + s(z_i) tanh(z_g);  h = s(z_o) tanh(c)
  * (nn.LSTM semantics, gate order i,f,g,o, zero initial state; factory/AutoVC.py:77,96,103,110;

@@ -16,9 +16,11 @@ plan = gen._plan()
 plan.stem.tag = "stem 80->512 k7"
 for si, (r, C, up, blocks) in enumerate(plan.stages):
     up.tag = f"s{si} up x{r} ->{C}"
-    for j, (d, c3, k1) in enumerate(blocks):
+    for j, (d, c3, k1, fused) in enumerate(blocks):
         c3.tag = f"s{si} b{j} k3 d{d} C{C}"
         k1.tag = f"s{si} b{j} k1+sc C{C}"
+        if fused is not None:
+            fused.tag = f"s{si} b{j} fused d{d} C{C}"
 ops.PROFILER.reset(); ops.PROFILER.enabled = True
 gen(mel)
 torch.cuda.synchronize()

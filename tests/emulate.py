@@ -276,7 +276,37 @@ def _emu_complex_mag(spec, bins, bins_pad, precision):
     return packing.to_act(mag.float().unsqueeze(0), precision)
 
 
+def _emu_resblock_call(self, xa, x, B, L, out=None, out_row0=0, reflect=0, out_raw=None, out2=None):
+    """Mirror of avc_resblock: reads the PACKED tiles (so packing.pack_resblock is what gets validated), the halo
+    window of LeakyReLU(x) with row-shifted taps, the split intermediate, and the three output forms."""
+    C, d = self.C, self.dilation
+    assert xa.shape == (B, L + 2 * d, 2 * C) and x.shape == (B, L, 2 * C) and L % 128 == 0
+    w = self.w.double()
+    if C == 64:
+        mats = [w[i, :64] + w[i, 64:] for i in range(5)]
+    else:
+        assert torch.equal(w[:, :32, :32], w[:, :32, 32:]) and not w[:, 32:, 32:].any()
+        mats = [w[i, :32, :32] + w[i, 32:, :32] for i in range(5)]
+    a = packing.act_to_float(xa, "fp32").double()
+    mid = self.bias3.double().view(1, 1, C).expand(B, L, C).clone()
+    for tap in range(3):
+        mid = mid + a[:, tap * d:tap * d + L] @ mats[tap].t()
+    mid = packing.act_to_float(packing.to_act(F.leaky_relu(mid, 0.2).float(), "fp32"), "fp32").double()
+    y = mid @ mats[3].t() + packing.act_to_float(x, "fp32").double() @ mats[4].t() + self.bias1.double()
+    if out_raw is not None:
+        out_raw[:] = packing.to_act(y.float(), "fp32")
+    ya = F.leaky_relu(y, 0.2)
+    if out is not None:
+        assert out2 is None and out.shape[1] >= out_row0 + L + reflect and out_row0 >= reflect
+        full = F.pad(ya.transpose(1, 2), (reflect, reflect), mode="reflect").transpose(1, 2) if reflect else ya
+        out[:, out_row0 - reflect:out_row0 + L + reflect] = packing.to_act(full.float(), "fp32")
+    if out2 is not None:
+        out2[:] = ya.float().reshape(B * L, C)
+    return out if out is not None else (out2 if out2 is not None else out_raw)
+
+
 def install_cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops.Resblock, "__call__", _emu_resblock_call)
     monkeypatch.setattr(ops, "audio_frames", _emu_audio_frames)
     monkeypatch.setattr(ops, "complex_mag", _emu_complex_mag)
     monkeypatch.setattr(ops, "global_stats", _emu_global_stats)

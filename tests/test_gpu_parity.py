@@ -277,6 +277,62 @@ def test_melgan_parity_and_golden(precision, tol, name):
         assert ((c - r.mean()) - (r - r.mean())).norm() / (r - r.mean()).norm() < 1e-3
 
 
+@pytest.mark.parametrize("C,d,B,L", [(64, 1, 2, 256), (64, 9, 1, 384), (32, 3, 3, 128), (32, 9, 2, 640), (64, 3, 150, 128)])
+def test_fused_resblock_matches_torch(C, d, B, L):
+    """avc_resblock (melgan/modules.py:72-85 in one kernel) against torch fp64 on the same split-bf16 inputs: all three
+    output forms, the reflected halo rows of the next block, more tiles than CTAs (B = 150)."""
+    from autoformer_b200 import ops, packing
+    torch.manual_seed(100 * C + d)
+    w3, w1, wsc = torch.randn(C, C, 3) / (3 * C) ** 0.5, torch.randn(C, C, 1) / C ** 0.5, torch.randn(C, C, 1) / C ** 0.5
+    b3, b1, bsc = torch.randn(C), torch.randn(C), torch.randn(C)
+    x = torch.randn(B, L, C)
+    x_op = packing.to_act(x, "fp32")
+    xs = packing.act_to_float(x_op, "fp32").double()                       # what the kernel actually reads
+    xa = F.pad(F.leaky_relu(xs, 0.2).transpose(1, 2), (d, d), mode="reflect").transpose(1, 2)
+    xa_op = packing.to_act(xa.float(), "fp32")
+    xas = packing.act_to_float(xa_op, "fp32").double()
+    mid = F.leaky_relu(F.conv1d(xas.transpose(1, 2), w3.double(), b3.double(), dilation=d), 0.2)
+    y = (F.conv1d(mid, w1.double(), b1.double()) + F.conv1d(xs.transpose(1, 2), wsc.double(), bsc.double())).transpose(1, 2)
+    ya = F.leaky_relu(y, 0.2)
+    blk = ops.Resblock(*packing.pack_resblock(w3, b3, w1, b1, wsc, bsc), dilation=d).to("cuda")
+    R = 9
+    out = torch.zeros(B, L + 2 * R, 2 * C, dtype=torch.bfloat16, device="cuda")
+    raw = torch.zeros(B, L, 2 * C, dtype=torch.bfloat16, device="cuda")
+    blk(xa_op.cuda(), x_op.cuda(), B, L, out=out, out_row0=R, reflect=R, out_raw=raw)
+    out2 = torch.zeros(B * L, C, device="cuda")
+    blk(xa_op.cuda(), x_op.cuda(), B, L, out2=out2)
+    only = torch.zeros(B, L, 2 * C, dtype=torch.bfloat16, device="cuda")
+    blk(xa_op.cuda(), x_op.cuda(), B, L, out=only)
+    torch.cuda.synchronize()
+    assert rel_l2(packing.act_to_float(raw, "fp32"), y) < 3e-5
+    assert rel_l2(out2.view(B, L, C), ya) < 3e-5
+    padded = F.pad(ya.transpose(1, 2), (R, R), mode="reflect").transpose(1, 2)
+    assert rel_l2(packing.act_to_float(out, "fp32"), padded) < 3e-5
+    assert torch.equal(only, out[:, R:R + L])
+
+
+def test_melgan_fused_resblocks_match_layerwise():
+    """The fused ResnetBlock path and the two-launch path are the same arithmetic up to fp32 summation order."""
+    import warnings
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    from autoformer_b200 import _lib
+    from autoformer_b200.melgan.modules import Generator
+    sd = seeded_state_dict(templates.melgan_template(), 9)
+    mel = synthetic_mel(2, 23, 3).transpose(1, 2).contiguous().cuda()
+    gen = Generator(80, 32, 3)
+    gen.load_state_dict(sd)
+    gen = gen.cuda().eval()
+    n0 = _lib.launch_count()
+    gen.fuse_resblocks = True
+    a = gen(mel)
+    n1 = _lib.launch_count()
+    gen.fuse_resblocks = False
+    b = gen(mel)
+    n2 = _lib.launch_count()
+    assert (n1 - n0) == (n2 - n1) - 6            # six blocks (C = 64 and C = 32 stages) run as one launch instead of two
+    assert rel_l2(a, b) < 2e-5
+
+
 def test_full_pipeline_embed_convert_vocode():
     """BASELINE config 4 at test size: LstmDV(src), LstmDV(tgt) -> AutoVC with pad/convert/trim -> MelGAN."""
     import warnings
