@@ -54,7 +54,7 @@ static bool encode(CUtensorMap* map, int elem_bytes, const void* base, int rank,
       return false;
     }
   }
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -74,6 +74,14 @@ bool encode_tmap_3d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {box0, box1, box2};
   return encode(map, elem_bytes, base, 3, dims, strides, box);
+}
+
+bool encode_tmap_4d(CUtensorMap* map, int elem_bytes, const void* base, const uint64_t (&d)[4],
+                    const uint64_t (&stride_bytes)[3], const uint32_t (&b)[4]) {
+  cuuint64_t dims[4] = {d[0], d[1], d[2], d[3]};
+  cuuint64_t strides[3] = {stride_bytes[0], stride_bytes[1], stride_bytes[2]};
+  cuuint32_t box[4] = {b[0], b[1], b[2], b[3]};
+  return encode(map, elem_bytes, base, 4, dims, strides, box);
 }
 
 bool encode_tmap_2d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,

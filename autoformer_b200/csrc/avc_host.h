@@ -17,6 +17,9 @@ void count_launch(long long n = 1);
 // elem_bytes = 4 (fp32 read as TF32) or 2 (bf16).  Box = {box0, box1, box2} elements; box0*elem_bytes == 128.
 bool encode_tmap_3d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                     uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+// 4-D variant: dims d[0] (contiguous) .. d[3], stride_bytes[i] = byte stride of dim i + 1, box b[0..3].
+bool encode_tmap_4d(CUtensorMap* map, int elem_bytes, const void* base, const uint64_t (&d)[4],
+                    const uint64_t (&stride_bytes)[3], const uint32_t (&b)[4]);
 // 2-D variant over [d1][d0].
 bool encode_tmap_2d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
                     uint64_t stride1_bytes, uint32_t box0, uint32_t box1);

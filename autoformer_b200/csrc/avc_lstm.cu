@@ -33,11 +33,13 @@
 namespace avc {
 
 struct alignas(64) LstmParams {
-  CUtensorMap tmap_h[2];   // hseq as (H, T, B), box {kc, 1, 128}; [1] = the lo half in split mode
-  CUtensorMap tmap_w[2];   // w_hh as (H, 4H), box {kc, BN / CTAS}; [1] = the lo half in split mode
+  // One TMA op loads the hi AND lo tiles of a stage (the part is a tensor dimension): a TMA op costs ~100-170 cycles
+  // of issue bandwidth whatever its size (scripts/ubench/tma_ops.cu), which is what bounds small-batch frames.
+  CUtensorMap tmap_h;      // hseq as (H, B, part, T), box {kc, a_rows, PARTS, 1} -> [a_hi tile][a_lo tile]
+  CUtensorMap tmap_w;      // w_hh as (H, 4H, part), box {kc, BN / CTAS, PARTS} -> [W_hi tile][W_lo tile]
   CUtensorMap tmap_x;      // xproj as (4H, T, B) fp32, box {32, 1, 128}
-  CUtensorMap tmap_xi[2];  // fused input projection: input sequence as (C_in, T, B), box {kc, 1, 128}; [1] = lo half
-  CUtensorMap tmap_wi[2];  // fused input projection: w_ih as (K_in, 4H), box {kc, BN / CTAS}; [1] = lo half
+  CUtensorMap tmap_xi;     // fused input projection: input sequence as (C_in, B, part, T), box as tmap_h
+  CUtensorMap tmap_wi;     // fused input projection: w_ih as (K_in, 4H, part), box as tmap_w
   const float* bias;       // fused input projection: b_ih + b_hh [4H], packed gate order
   int num_kx;              // fused input projection: k-blocks of the input part
   const float* xproj;
@@ -51,6 +53,11 @@ struct alignas(64) LstmParams {
   int num_kb, kc_elems;
   int n_tiles;
   int t_begin, t_end;
+  int a_rows;             // rows of an activation box: 128, or B rounded up to 8 when one CTA owns the whole batch
+  int a_tile;             // bytes of one activation tile of a stage (a_rows * 128)
+  int stage_bytes;        // {activation tile(s), W tile(s)}
+  uint32_t stages;        // ring depth: as many stages as the shared-memory ring holds, at most kMaxStages
+  uint32_t stage_tx;      // bytes one CTA's loads of a stage credit to the full barrier
 };
 
 // Accumulator layout of the split-bf16 mode.  Wide MMA (N = 2 * BN): B rows = this CTA's [W_hi tile ; W_lo tile], so with
@@ -66,16 +73,27 @@ struct SplitAcc {
   __device__ static constexpr int second(int c) { return first(c) + kHalf; }
 };
 
-// The MMAs of one landed stage (a_hi at `a_hi`, W tile(s) at `w_hi`) into the accumulator at `acc`.
+// The MMAs of one landed stage (activation tiles at `a_hi` / `a_lo`, W tile(s) at `w_hi`) into the accumulator at `acc`.
 template <int BN, int MODE, int CTAS>
-__device__ __forceinline__ void issue_stage(uint32_t a_hi, uint32_t w_hi, uint32_t acc, bool first) {
+__device__ __forceinline__ void issue_stage(uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t acc, bool first) {
   constexpr bool BF16 = MODE != 0;
   if (MODE == 2) {
     issue_pair<2 * BN, BF16, CTAS>(a_hi, w_hi, acc, first);                                        // a_hi * [W_hi | W_lo]
-    issue_pair<BN, BF16, CTAS>(a_hi + kATileBytes, w_hi, acc + SplitAcc<BN, CTAS, true>::kLoOffset, false);  // a_lo * W_hi
+    issue_pair<BN, BF16, CTAS>(a_lo, w_hi, acc + SplitAcc<BN, CTAS, true>::kLoOffset, false);                 // a_lo * W_hi
   } else {
     issue_pair<BN, BF16, CTAS>(a_hi, w_hi, acc, first);
   }
+}
+
+// Activation tile(s) of a stage: channels [kc0, kc0 + kc) of utterances [b0, b0 + a_rows) at frame t, both parts.
+template <int CTAS>
+__device__ __forceinline__ void load_act(void* dst, const CUtensorMap* map, uint64_t* bar, int kc0, int b0, int t) {
+  if (CTAS == 2) tma_load_4d_2sm(dst, map, bar, kc0, b0, 0, t); else tma_load_4d(dst, map, bar, kc0, b0, 0, t);
+}
+// Weight tile(s) of a stage: channels [kc0, kc0 + kc) of rows [n, n + BN / CTAS), both parts.
+template <int CTAS>
+__device__ __forceinline__ void load_w(void* dst, const CUtensorMap* map, uint64_t* bar, int kc0, int n) {
+  if (CTAS == 2) tma_load_3d_2sm(dst, map, bar, kc0, n, 0); else tma_load_3d(dst, map, bar, kc0, n, 0);
 }
 
 // Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
@@ -181,13 +199,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
   const int nb0 = n0 + cta_rank * (BN / CTAS);              // first W_hh row staged by this CTA
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&p.tmap_h[0]);
-    prefetch_tmap(&p.tmap_w[0]);
+    prefetch_tmap(&p.tmap_h);
+    prefetch_tmap(&p.tmap_w);
     prefetch_tmap(&p.tmap_x);
-    if (PARTS == 2) {
-      prefetch_tmap(&p.tmap_h[1]);
-      prefetch_tmap(&p.tmap_w[1]);
-    }
   }
   const uint32_t tmem_base = pipe_setup<C>(s);
 
@@ -213,29 +227,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
         // frame, so the first `pre` stages of frame t+1 get their W loads (and the full barrier's byte count) BEFORE
         // the grid barrier, while the cell epilogue of frame t is still running; only the h loads wait for it.
         auto issue = [&](int kb, int frame, bool want_w, bool want_h, uint32_t stage) {
-          uint8_t* st = s.base + stage * C::kStageBytes;
-          uint8_t* wst = st + PARTS * kATileBytes;
+          uint8_t* st = s.base + stage * p.stage_bytes;
+          uint8_t* wst = st + PARTS * p.a_tile;
           const int kc0 = kb * p.kc_elems;
           if (want_w) {
-            if (CTAS == 2) {
-              if (leader) mbar_arrive_expect_tx(&s.full[stage], 2 * C::kStageBytes);
-              tma_load_2d_2sm(wst, &p.tmap_w[0], &s.full[stage], kc0, nb0);
-              if (PARTS == 2) tma_load_2d_2sm(wst + C::kBTileBytes, &p.tmap_w[1], &s.full[stage], kc0, nb0);
-            } else {
-              mbar_arrive_expect_tx(&s.full[stage], C::kStageBytes);
-              tma_load_2d(wst, &p.tmap_w[0], &s.full[stage], kc0, nb0);
-              if (PARTS == 2) tma_load_2d(wst + C::kBTileBytes, &p.tmap_w[1], &s.full[stage], kc0, nb0);
-            }
+            if (CTAS == 1 || leader) mbar_arrive_expect_tx(&s.full[stage], CTAS * p.stage_tx);
+            load_w<CTAS>(wst, &p.tmap_w, &s.full[stage], kc0, nb0);
           }
-          if (want_h) {
-            if (CTAS == 2) {
-              tma_load_3d_2sm(st, &p.tmap_h[0], &s.full[stage], kc0, frame - 1, b0);
-              if (PARTS == 2) tma_load_3d_2sm(st + kATileBytes, &p.tmap_h[1], &s.full[stage], kc0, frame - 1, b0);
-            } else {
-              tma_load_3d(st, &p.tmap_h[0], &s.full[stage], kc0, frame - 1, b0);
-              if (PARTS == 2) tma_load_3d(st + kATileBytes, &p.tmap_h[1], &s.full[stage], kc0, frame - 1, b0);
-            }
-          }
+          if (want_h) load_act<CTAS>(st, &p.tmap_h, &s.full[stage], kc0, b0, frame - 1);
         };
         auto issue_x = [&]() {     // this frame's xproj tile (independent of h): consumed by the cell warps
           mbar_arrive_expect_tx(s.extra_bar, kXBytes);
@@ -249,24 +248,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           RingState hs = rs;         // stages whose W tiles were pre-issued: add the h tiles
           for (int kb = 0; kb < pre_issued; ++kb) {
             issue(kb, t, false, true, hs.stage);
-            hs.advance<C::kStages>();
+            hs.advance(p.stages);
           }
-          for (int kb = 0; kb < pre_issued; ++kb) rs.advance<C::kStages>();
+          for (int kb = 0; kb < pre_issued; ++kb) rs.advance(p.stages);
           issue_x();                 // after the h tiles of the first stages: those are on the critical path
           for (int kb = pre_issued; kb < p.num_kb; ++kb) {
             mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
             issue(kb, t, true, true, rs.stage);
-            rs.advance<C::kStages>();
+            rs.advance(p.stages);
           }
           pre_issued = 0;
         }
         if (t + 1 < p.t_end) {     // persistent mode: W tiles of the next frame's first stages
           RingState ws = rs;
-          const int pre = p.num_kb < C::kStages ? p.num_kb : C::kStages;
+          const int pre = p.num_kb < p.stages ? p.num_kb : p.stages;
           for (int kb = 0; kb < pre; ++kb) {
             mbar_wait(&s.empty[ws.stage], ws.phase ^ 1u);
             issue(kb, t + 1, true, false, ws.stage);
-            ws.advance<C::kStages>();
+            ws.advance(p.stages);
           }
           pre_issued = pre;
           // the next frame's h tiles need every CTA's h_t: wait for this CTA's cell warps, then for the whole grid
@@ -285,11 +284,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           mbar_wait(&s.full[rs.stage], rs.phase);
           if (dbg && kb == 0) dbg[1] = clock64();                          // first stage landed
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(s.base + rs.stage * C::kStageBytes);
-          const uint32_t w_hi = a_hi + PARTS * kATileBytes;
-          issue_stage<BN, MODE, CTAS>(a_hi, w_hi, tmem_base, kb == 0);
+          const uint32_t a_hi = smem_u32(s.base + rs.stage * p.stage_bytes);
+          const uint32_t w_hi = a_hi + PARTS * p.a_tile;
+          issue_stage<BN, MODE, CTAS>(a_hi, a_hi + p.a_tile, w_hi, tmem_base, kb == 0);
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
-          rs.advance<C::kStages>();
+          rs.advance(p.stages);
         }
         if (CTAS == 2) umma_commit_2sm(s.tmem_full, 0x3); else umma_commit(s.tmem_full);
         if (dbg) dbg[2] = clock64();                                       // all MMAs issued
@@ -417,13 +416,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
   const int nb0 = n0 + cta_rank * (BN / CTAS);
 
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int part = 0; part < PARTS; ++part) {
-      prefetch_tmap(&p.tmap_h[part]);
-      prefetch_tmap(&p.tmap_w[part]);
-      prefetch_tmap(&p.tmap_xi[part]);
-      prefetch_tmap(&p.tmap_wi[part]);
-    }
+    prefetch_tmap(&p.tmap_h);
+    prefetch_tmap(&p.tmap_w);
+    prefetch_tmap(&p.tmap_xi);
+    prefetch_tmap(&p.tmap_wi);
   }
   float* sbias = reinterpret_cast<float*>(s.extra);
   // Recurrent stages whose slot the static producer has claimed (empty barrier observed, W tiles in flight).  The h
@@ -442,36 +438,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
       // and loads everything except the h tiles
       auto stage_static = [&](const CUtensorMap* tw, int kb, const CUtensorMap* ta, int frame) {
         mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
-        uint8_t* st = s.base + rs.stage * C::kStageBytes;
-        uint8_t* wst = st + PARTS * kATileBytes;
+        uint8_t* st = s.base + rs.stage * p.stage_bytes;
+        uint8_t* wst = st + PARTS * p.a_tile;
         const int kc0 = kb * p.kc_elems;
-        if (CTAS == 2) {
-          if (leader) mbar_arrive_expect_tx(&s.full[rs.stage], 2 * C::kStageBytes);
-          tma_load_2d_2sm(wst, &tw[0], &s.full[rs.stage], kc0, nb0);
-          if (PARTS == 2) tma_load_2d_2sm(wst + C::kBTileBytes, &tw[1], &s.full[rs.stage], kc0, nb0);
-          if (ta) {
-            tma_load_3d_2sm(st, &ta[0], &s.full[rs.stage], kc0, frame, b0);
-            if (PARTS == 2) tma_load_3d_2sm(st + kATileBytes, &ta[1], &s.full[rs.stage], kc0, frame, b0);
-          }
-        } else {
-          mbar_arrive_expect_tx(&s.full[rs.stage], C::kStageBytes);
-          tma_load_2d(wst, &tw[0], &s.full[rs.stage], kc0, nb0);
-          if (PARTS == 2) tma_load_2d(wst + C::kBTileBytes, &tw[1], &s.full[rs.stage], kc0, nb0);
-          if (ta) {
-            tma_load_3d(st, &ta[0], &s.full[rs.stage], kc0, frame, b0);
-            if (PARTS == 2) tma_load_3d(st + kATileBytes, &ta[1], &s.full[rs.stage], kc0, frame, b0);
-          }
-        }
+        if (CTAS == 1 || leader) mbar_arrive_expect_tx(&s.full[rs.stage], CTAS * p.stage_tx);
+        load_w<CTAS>(wst, tw, &s.full[rs.stage], kc0, nb0);
+        if (ta) load_act<CTAS>(st, ta, &s.full[rs.stage], kc0, b0, frame);
         if (!ta) {
           ++h_claimed;
           asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(h_ready)), "r"(h_claimed) : "memory");
         }
-        rs.advance<C::kStages>();
+        rs.advance(p.stages);
       };
       for (int t = p.t_begin; t < p.t_end; ++t) {
-        for (int kb = 0; kb < p.num_kx; ++kb) stage_static(p.tmap_wi, kb, p.tmap_xi, t);
+        for (int kb = 0; kb < p.num_kx; ++kb) stage_static(&p.tmap_wi, kb, &p.tmap_xi, t);
         if (t > 0)
-          for (int kb = 0; kb < p.num_kb; ++kb) stage_static(p.tmap_w, kb, nullptr, 0);
+          for (int kb = 0; kb < p.num_kb; ++kb) stage_static(&p.tmap_w, kb, nullptr, 0);
       }
     }
     __syncwarp();
@@ -487,11 +469,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
           mbar_wait(&s.full[rs.stage], rs.phase);
           if (dbg && i == p.num_kx) dbg[1] = clock64();                    // first recurrent stage landed
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(s.base + rs.stage * C::kStageBytes);
-          const uint32_t w_hi = a_hi + PARTS * kATileBytes;
-          issue_stage<BN, MODE, CTAS>(a_hi, w_hi, acc, i == 0);
+          const uint32_t a_hi = smem_u32(s.base + rs.stage * p.stage_bytes);
+          const uint32_t w_hi = a_hi + PARTS * p.a_tile;
+          issue_stage<BN, MODE, CTAS>(a_hi, a_hi + p.a_tile, w_hi, acc, i == 0);
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
-          rs.advance<C::kStages>();
+          rs.advance(p.stages);
         }
         if (CTAS == 2) umma_commit_2sm(&s.tmem_full[t & 1], 0x3); else umma_commit(&s.tmem_full[t & 1]);
         if (dbg) dbg[2] = clock64();                                       // all MMAs of the frame issued
@@ -506,7 +488,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
       unsigned int sync_count = 0;
       for (int t = p.t_begin; t < p.t_end; ++t) {
         long long* dbg = p.debug_clk ? p.debug_clk + ((long long)t * gridDim.x + blockIdx.x) * 8 : nullptr;
-        for (int kb = 0; kb < p.num_kx; ++kb) rs.advance<C::kStages>();
+        for (int kb = 0; kb < p.num_kx; ++kb) rs.advance(p.stages);
         if (t == 0) continue;
         if (t > p.t_begin) {
           // h_{t-1} comes from this launch: wait for this CTA's cell warps, then for every CTA that owns the same
@@ -533,16 +515,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
               }
             } while (seen < h_issued);
           }
-          uint8_t* st = s.base + rs.stage * C::kStageBytes;
+          uint8_t* st = s.base + rs.stage * p.stage_bytes;
           const int kc0 = kb * p.kc_elems;
-          if (CTAS == 2) {
-            tma_load_3d_2sm(st, &p.tmap_h[0], &s.full[rs.stage], kc0, t - 1, b0);
-            if (PARTS == 2) tma_load_3d_2sm(st + kATileBytes, &p.tmap_h[1], &s.full[rs.stage], kc0, t - 1, b0);
-          } else {
-            tma_load_3d(st, &p.tmap_h[0], &s.full[rs.stage], kc0, t - 1, b0);
-            if (PARTS == 2) tma_load_3d(st + kATileBytes, &p.tmap_h[1], &s.full[rs.stage], kc0, t - 1, b0);
-          }
-          rs.advance<C::kStages>();
+          load_act<CTAS>(st, &p.tmap_h, &s.full[rs.stage], kc0, b0, t - 1);
+          rs.advance(p.stages);
         }
       }
     }
@@ -632,6 +608,10 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
   using C = std::conditional_t<FUSED, PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, kBiasBytes, 2, kAccCols>,
                                PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes, 1, kAccCols>>;
   constexpr int kThreads = FUSED ? kFusedThreads : kNumThreads;
+  // small batches shrink the stage (a_rows < 128): the same ring memory then holds more, shallower stages, which is what
+  // a latency-bound frame wants (a TMA round trip costs ~3 K cycles whatever the tile size)
+  const int fit = C::kStages * C::kStageBytes / p.stage_bytes;
+  p.stages = (uint32_t)(fit < kMaxStages ? fit : kMaxStages);
   static bool configured = false;
   if (!configured) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
@@ -729,16 +709,20 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   const uint64_t ld = split ? 2 * H : H;     // elements per row of hseq and of the packed W_hh ([hi | lo] when split)
   const int m_tiles = (d->B + kBlockM - 1) / kBlockM;
   const int ctas = (m_tiles >= 2 && lstm_cta_group() == 2) ? 2 : 1;
+  // A small batch owned by one CTA loads only its real rows (rounded up to 8): the MMA still spans 128 rows, but the
+  // rows past the batch are never stored and every accumulator row depends on its own operand row only, so whatever
+  // those shared-memory rows hold is harmless -- and the stage shrinks from 32 KB to a few KB of activations.
+  const int a_rows = m_tiles == 1 ? (d->B + 7) / 8 * 8 : kBlockM;
 
   LstmParams p;
   memset(&p, 0, sizeof(p));
-  for (int part = 0; part < (split ? 2 : 1); ++part) {
-    const char* hb = static_cast<const char*>(d->hseq) + (size_t)part * H * es;
-    const char* wb = static_cast<const char*>(d->w_hh) + (size_t)part * H * es;
-    if (!encode_tmap_3d(&p.tmap_h[part], es, hb, H, (uint64_t)d->T, (uint64_t)d->B, ld * es, (uint64_t)d->T * ld * es, kc,
-                        1, kBlockM))
-      return -3;
-    if (!encode_tmap_2d(&p.tmap_w[part], es, wb, H, 4 * H, ld * es, kc, bn / ctas)) return -3;
+  const uint32_t parts = split ? 2 : 1;
+  {
+    const uint64_t dh[4] = {H, (uint64_t)d->B, parts, (uint64_t)d->T};
+    const uint64_t sh[3] = {(uint64_t)d->T * ld * es, H * es, ld * es};
+    const uint32_t bh[4] = {(uint32_t)kc, (uint32_t)a_rows, parts, 1};
+    if (!encode_tmap_4d(&p.tmap_h, es, d->hseq, dh, sh, bh)) return -3;
+    if (!encode_tmap_3d(&p.tmap_w, es, d->w_hh, H, 4 * H, parts, ld * es, H * es, kc, bn / ctas, parts)) return -3;
   }
   if (fused) {
     // input sequence [B][T][xin_ld] holding xin_channels logical channels ([hi | lo] halves when split); channels past
@@ -749,14 +733,11 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
     p.num_kx = (int)((cin + kc - 1) / kc);
     const uint64_t kpad = (uint64_t)p.num_kx * kc;
     const uint64_t ldw = split ? 2 * kpad : kpad;
-    for (int part = 0; part < (split ? 2 : 1); ++part) {
-      const char* xb = static_cast<const char*>(d->xin) + (size_t)part * cin * es;
-      const char* wb = static_cast<const char*>(d->w_ih) + (size_t)part * kpad * es;
-      if (!encode_tmap_3d(&p.tmap_xi[part], es, xb, cin, (uint64_t)d->T, (uint64_t)d->B, (uint64_t)d->xin_ld * es,
-                          (uint64_t)d->T * d->xin_ld * es, kc, 1, kBlockM))
-        return -3;
-      if (!encode_tmap_2d(&p.tmap_wi[part], es, wb, kpad, 4 * H, ldw * es, kc, bn / ctas)) return -3;
-    }
+    const uint64_t dx[4] = {cin, (uint64_t)d->B, parts, (uint64_t)d->T};
+    const uint64_t sx[3] = {(uint64_t)d->T * d->xin_ld * es, cin * es, (uint64_t)d->xin_ld * es};
+    const uint32_t bx[4] = {(uint32_t)kc, (uint32_t)a_rows, parts, 1};
+    if (!encode_tmap_4d(&p.tmap_xi, es, d->xin, dx, sx, bx)) return -3;
+    if (!encode_tmap_3d(&p.tmap_wi, es, d->w_ih, kpad, 4 * H, parts, ldw * es, kpad * es, kc, bn / ctas, parts)) return -3;
     p.bias = d->bias;
   } else {
     if (!encode_tmap_3d(&p.tmap_x, 4, d->xproj, 4 * H, (uint64_t)d->T, (uint64_t)d->B, 4 * H * 4,
@@ -776,6 +757,10 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   p.kc_elems = kc;
   p.num_kb = d->H / kc;
   p.n_tiles = 4 * d->H / bn;
+  p.a_rows = a_rows;
+  p.a_tile = a_rows * kRowBytes;
+  p.stage_bytes = (split ? 2 : 1) * (p.a_tile + bn / ctas * kRowBytes);
+  p.stage_tx = (uint32_t)p.stage_bytes;
 #define AVC_LSTM_DISPATCH3(BN_, MODE_, CTAS_) \
   return fused ? run<BN_, MODE_, CTAS_, true>(p, d, m_tiles, stream) : run<BN_, MODE_, CTAS_, false>(p, d, m_tiles, stream);
 #define AVC_LSTM_DISPATCH2(BN_, MODE_) \

@@ -12,6 +12,7 @@ namespace avc {
 constexpr int kBlockM = 128;
 constexpr int kRowBytes = 128;                 // one swizzle row = one k-block of one row
 constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KB
+constexpr int kMaxStages = 8;                   // barrier slots reserved for the ring (a kernel may run fewer stages)
 constexpr int kEpiWarps = 8;                   // two epilogue warps per TMEM lane quarter (= per SM sub-partition)
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;   // TMA warp + MMA warp + epilogue warps
 constexpr int kSmemBudget = 186 * 1024;
@@ -34,13 +35,13 @@ struct PipeCfg {
   static constexpr int kBTileBytes = BN / CTAS * kRowBytes;
   static constexpr int kStageBytes = PARTS * (kATileBytes + kBTileBytes);
   static constexpr int kBudget = (STAGING ? kSmemBudget : kSmemBudget + kStagingBytes + 8 * 1024) - EXTRA;
-  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kStages = (kBudget / kStageBytes) > kMaxStages ? kMaxStages : (kBudget / kStageBytes);
   // per-epilogue-warp staging tile used to transpose 32 rows x 32 columns so that global stores are coalesced
   static constexpr int kExtraOffset = kStages * kStageBytes;
   static constexpr int kStagingOffset = kExtraOffset + EXTRA;
   static constexpr int kBarOffset = kStagingOffset + (STAGING ? kStagingBytes : 0);
-  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], extra barrier, epilogue-done barrier, TMEM address word
-  static constexpr int kSmemBytes = kBarOffset + (2 * kStages + 6) * 8 + 16 + 1024 /* alignment slack */;
+  // full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], extra barrier, epilogue-done barrier, TMEM address word
+  static constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 6) * 8 + 16 + 1024 /* alignment slack */;
   static constexpr int kAccCols = ACCW;
   static constexpr uint32_t kTmemCols = ACCW * ACC < 32 ? 32 : ACCW * ACC;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two, at most 512");
@@ -68,8 +69,8 @@ __device__ __forceinline__ PipeSmem carve_smem(uint8_t* raw) {
   s.base = raw + ((1024u - (addr & 1023u)) & 1023u);
   s.staging = reinterpret_cast<float*>(s.base + C::kStagingOffset);
   s.full = reinterpret_cast<uint64_t*>(s.base + C::kBarOffset);
-  s.empty = s.full + C::kStages;
-  s.tmem_full = s.empty + C::kStages;
+  s.empty = s.full + kMaxStages;
+  s.tmem_full = s.empty + kMaxStages;
   s.tmem_empty = s.tmem_full + 2;
   s.extra_bar = s.tmem_empty + 2;
   s.epi_done = s.extra_bar + 1;
@@ -83,7 +84,7 @@ template <class C>
 __device__ __forceinline__ uint32_t pipe_setup(const PipeSmem& s) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&s.full[i], 1);
       mbar_init(&s.empty[i], 1);
     }
@@ -136,6 +137,12 @@ struct RingState {
   template <int STAGES>
   __device__ __forceinline__ void advance() {
     if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+  __device__ __forceinline__ void advance(uint32_t stages) {   // ring depth chosen at launch
+    if (++stage == stages) {
       stage = 0;
       phase ^= 1u;
     }

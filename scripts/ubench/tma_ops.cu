@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(64, 1) ops_kernel(const __grid_constant__ Para
 }
 
 static void run(const char* label, void* buf, long long buf_rows, int pitch_bytes, std::vector<int> rows_op,
-                int region_rows, bool dram, int grid = 148) {
+                int region_rows, bool dram, int grid = 148, bool shared_region = false, int max_stages = 8) {
   Params p;
   memset(&p, 0, sizeof(p));
   p.n_ops = (int)rows_op.size();
@@ -84,11 +84,12 @@ static void run(const char* label, void* buf, long long buf_rows, int pitch_byte
     }
   }
   p.stages = kRing / p.stage_bytes;
-  if (p.stages > 8) p.stages = 8;
+  if (p.stages > max_stages) p.stages = max_stages;
   p.iters = 3000;
   p.region_rows = region_rows;
   p.cta_stride_rows = dram ? buf_rows / grid : region_rows;
   if (dram) p.region_rows = (int)(buf_rows / grid);
+  if (shared_region) p.cta_stride_rows = 0;      // every CTA walks the same rows
   cudaMalloc(&p.cycles, grid * sizeof(long long));
   const int smem = kRing + 2 * 64 * 8 + 1024;
   cudaFuncSetAttribute(ops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -131,5 +132,24 @@ int main() {
   run("2 ops 16KB + 4KB, DRAM stream", buf, rows128, 128, {128, 32}, 0, true);
   run("1 x 16KB, pitch 128B, L2, 74 CTAs", buf, rows128, 128, {128}, L2rows, false, 74);
   run("1 x 16KB, pitch 128B, DRAM stream, 74 CTAs", buf, rows128, 128, {128}, 0, true, 74);
+  // rows of one box far apart in memory, as the recurrent-state tiles of the LSTM are (one row per utterance,
+  // utterances T * H * 4 bytes apart): does the number of distinct pages a box touches matter?
+  const long long rows512k = bytes / (512 << 10);
+  run("1 x 16KB (128 rows), pitch 512KB, L2", buf, rows512k, 512 << 10, {128}, 1024, false, 148, true);
+  run("1 x 4KB (32 rows), pitch 512KB, L2", buf, rows512k, 512 << 10, {32}, 1024, false, 148, true);
+  run("2 x 4KB (32 rows), pitch 512KB, L2", buf, rows512k, 512 << 10, {32, 32}, 1024, false, 148, true);
+  run("1 x 16KB (128 rows), pitch 2KB, shared region", buf, rows2k, 2048, {128}, 1024, false, 148, true);
+  run("2 x 4KB (32 rows), pitch 2KB, shared region", buf, rows2k, 2048, {32, 32}, 1024, false, 148, true);
+  // latency or throughput?  the same single 4 KB op with 2 .. 32 stages in flight
+  for (int st : {2, 4, 8, 16, 32}) {
+    char label[64];
+    snprintf(label, sizeof(label), "1 x 4KB, pitch 128B, L2, ring of %d", st);
+    run(label, buf, rows128, 128, {32}, L2rows, false, 148, false, st);
+  }
+  for (int st : {2, 4, 8}) {
+    char label[64];
+    snprintf(label, sizeof(label), "4 x 4KB, pitch 128B, L2, ring of %d", st);
+    run(label, buf, rows128, 128, {32, 32, 32, 32}, L2rows, false, 148, false, st);
+  }
   return 0;
 }
