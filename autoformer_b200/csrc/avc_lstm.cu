@@ -96,24 +96,6 @@ __device__ __forceinline__ void load_w(void* dst, const CUtensorMap* map, uint64
   if (CTAS == 2) tma_load_3d_2sm(dst, map, bar, kc0, n, 0); else tma_load_3d(dst, map, bar, kc0, n, 0);
 }
 
-// Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
-// has already synchronised with this thread through the epi_done mbarrier.
-__device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target, long long* stamp = nullptr) {
-  // release: everything this thread has observed (the cell warps' h stores, via epi_done) becomes visible to whoever
-  // acquires the counter; the acquire load orders the TMA issue that follows.
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-  const long long t0 = clock64();
-  if (stamp) *stamp = t0;                                                  // arrival issued (after the release fence)
-  unsigned int seen;
-  do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
-    if (seen < target && clock64() - t0 > 4000000000LL) {
-      printf("avc: grid barrier timeout block %d seen %u target %u\n", (int)blockIdx.x, seen, target);
-      __trap();
-    }
-  } while (seen < target);
-}
-
 // Pre-activations (without bias / xproj) of hidden units j*8 .. j*8+7 of the tile for the four gates, from the
 // accumulator row this thread owns; in split mode the sum of the two column blocks of SplitAcc.
 template <class SA, int G>

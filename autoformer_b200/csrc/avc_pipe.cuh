@@ -180,6 +180,24 @@ __device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, 
   issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, tmem_acc, first);
 }
 
+// Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
+// has already synchronised with this thread through the epi_done mbarrier.
+__device__ __forceinline__ void grid_arrive_wait(unsigned int* bar, unsigned int target, long long* stamp = nullptr) {
+  // release: everything this thread has observed (the cell warps' h stores, via epi_done) becomes visible to whoever
+  // acquires the counter; the acquire load orders the TMA issue that follows.
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+  const long long t0 = clock64();
+  if (stamp) *stamp = t0;                                                  // arrival issued (after the release fence)
+  unsigned int seen;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    if (seen < target && clock64() - t0 > 4000000000LL) {
+      printf("avc: grid barrier timeout block %d seen %u target %u\n", (int)blockIdx.x, seen, target);
+      __trap();
+    }
+  } while (seen < target);
+}
+
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // tanh with ~1e-7 absolute error (tanh.approx is only good to 2^-11, too coarse for a 1e-3 end-to-end gate).
 __device__ __forceinline__ float tanh_fast(float x) {

@@ -48,7 +48,7 @@ class Adjust(nn.Module):
         self.lstm = nn.LSTM(512, hidden_size=dim_cell, num_layers=3, batch_first=True)
         self.embedding = LinearNorm(dim_cell, 256)
         self.precision = "fp32"
-        self.persistent_lstm = False
+        self.persistent_lstm = True
         self._cache = layers.PlanCache()
 
     def _plan(self):

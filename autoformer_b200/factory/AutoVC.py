@@ -81,7 +81,7 @@ class AutoVC(nn.Module):
         self.postnet = Postnet()
         self.dim_neck, self.dim_emb, self.dim_pre, self.freq = dim_neck, dim_emb, dim_pre, freq
         self.precision = "fp32"
-        self.persistent_lstm = False
+        self.persistent_lstm = True
         self.collect_taps = False
         self.taps = {}
         self._cache = layers.PlanCache()

@@ -18,7 +18,7 @@ class LstmDV(nn.Module):
         self.embedding = nn.Linear(dim_cell, dim_emb)
         self.num_layers, self.dim_cell = num_layers, dim_cell
         self.precision = "fp32"
-        self.persistent_lstm = False
+        self.persistent_lstm = True
         self._cache = layers.PlanCache()
 
     def _plan(self):

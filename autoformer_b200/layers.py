@@ -36,6 +36,11 @@ def conv_bn_layer(sd, prefix, precision, act):
     return ops.ConvGemm(*packing.pack_conv(w, b, precision), act=act, tag="conv")
 
 
+def lstm_ws_default():
+    """AVC_LSTM_WS=0 keeps small batches on the batched recurrence kernel (A/B timing)."""
+    return os.environ.get("AVC_LSTM_WS", "1") != "0"
+
+
 def lstm_fused_default():
     """AVC_LSTM_FUSED=0 selects the two-kernel form (dense input projection, then the recurrence) for A/B timing."""
     return os.environ.get("AVC_LSTM_FUSED", "1") != "0"
@@ -52,6 +57,7 @@ class LstmLayer:
         self.H = w_hh.shape[1]
         self.C_in = w_ih.shape[1]
         self.fused = lstm_fused_default() if fused is None else fused
+        self.ws = lstm_ws_default()
         self._packs = {}
         self._fused_packs = {}
 
@@ -88,6 +94,15 @@ class LstmLayer:
                 self(x[b0:b1], b1 - b0, T, hseq_f32=hseq_f32[b0:b1] if hseq_f32 is not None else None,
                      h_last=h_last[b0:b1] if h_last is not None else None, persistent=True, hseq=out[b0:b1])
             return out
+        if persistent and self.ws and ops.ws_supported(B, self.H, self.precision):
+            # small batch: dense input projection, then the recurrence with W_hh resident in shared memory
+            ih, hh = self.packs(packing.WS_GROUP)
+            xp = torch.empty(B * T, 4 * self.H, dtype=torch.float32, device=x.device)
+            ih(x, B, T, out2=xp)
+            out = ops.lstm_seq_ws(xp, hh, B, T, self.H, hseq=hseq, hseq_f32=hseq_f32, h_last=h_last)
+            if out is not None:
+                return out
+            self.ws = False             # the device cannot hold the grid: batched kernel from now on
         group = ops.choose_gate_group(B, self.H, persistent)
         if self.use_fused(B):
             wih, bias, hh = self.fused_packs(group)

@@ -288,6 +288,55 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
     return hseq
 
 
+WS_MAX_BATCH = 64
+
+
+def ws_supported(B, H, precision, n_sm=148):
+    """Shapes the weight-stationary recurrence (avc_lstm_seq_ws) takes: split precision, B <= 64, the 4H/128 row
+    blocks x 4 K-slices within one wave (8 slices are used when the device can hold them), W slice + h slice +
+    reduction buffer within 227 KB of shared memory."""
+    if precision != "fp32" or B < 1 or B > WS_MAX_BATCH or H % 256 or 4 * H // 128 * 4 > n_sm:
+        return False
+    ar = 16 if B <= 16 else (32 if B <= 32 else 64)
+    chunks = H // 4 // 64
+    red = (128 * (ar + 4) * 4 + 1023) // 1024 * 1024
+    stage = (ar * 8 * 4 + 1023) // 1024 * 1024
+    return chunks * (32768 + 2 * ar * 128) + red + stage + 1152 <= 227 * 1024
+
+
+def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, debug_clk=None):
+    """Small-batch recurrence with W_hh resident in shared memory (split precision).  xproj [B*T][4H] fp32 and w_hh
+    [4H][2H] bf16 in the packing.WS_GROUP gate order.  Returns hseq, or None when the device cannot hold the grid
+    (nothing was launched; the caller uses lstm_seq)."""
+    lib = _lib.load()
+    _require_cuda(xproj, w_hh)
+    dev = w_hh.device
+    assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
+    assert w_hh.dtype == torch.bfloat16 and w_hh.shape == (4 * H, 2 * H) and w_hh.is_contiguous()
+    if hseq is None:
+        hseq = alloc_act(B, T, H, "fp32", dev)
+    assert hseq.is_contiguous() and hseq.shape == (B, T, 2 * H) and hseq.dtype == torch.bfloat16
+    d = _lib.LstmWsDesc()
+    d.xproj, d.w_hh, d.hseq = xproj.data_ptr(), w_hh.data_ptr(), hseq.data_ptr()
+    if hseq_f32 is not None:
+        assert hseq_f32.is_contiguous() and hseq_f32.shape == (B, T, H) and hseq_f32.dtype == torch.float32
+        d.hseq_f32 = hseq_f32.data_ptr()
+    if h_last is not None:
+        assert h_last.is_contiguous() and h_last.shape == (B, H) and h_last.dtype == torch.float32
+        d.h_last = h_last.data_ptr()
+    bar = torch.empty(32, dtype=torch.int32, device=dev)              # zeroed by the library
+    d.grid_barrier = bar.data_ptr()
+    d.B, d.T, d.H = B, T, H
+    if debug_clk is not None:
+        d.debug_clk = debug_clk.data_ptr()
+    with PROFILER.span("lstm_ws", flops=2.0 * 4 * H * H * B * T, launches=1):
+        rc = lib.avc_lstm_seq_ws(ctypes.byref(d), _stream())
+    if rc == _lib.ERR_NOT_RESIDENT:
+        return None
+    _lib.check(rc, "avc_lstm_seq_ws")
+    return hseq
+
+
 def bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=True, split=False):
     """xproj [B*T][8H] fp32; w_hh [2][4H][H] fp32; out [B][T][2H] (fp32/bf16; split: [B][T][4H] bf16) and/or
     codes [B][T/freq][2H] fp32."""

@@ -160,10 +160,17 @@ def pack_resblock(w3, b3, w1, b1, wsc, bsc):
     return w, b3.float().contiguous(), (b1.float() + bsc.float()).contiguous()
 
 
-def gate_permutation(hidden: int, group: int, device=None) -> torch.Tensor:
-    """index[p] = PyTorch gate row (g*H + u) stored at packed position p = (u//G)*4G + g*G + u%G."""
-    assert hidden % group == 0
+WS_GROUP = "ws"     # gate packing of the weight-stationary small-batch recurrence (avc_lstm_seq_ws)
+
+
+def gate_permutation(hidden: int, group, device=None) -> torch.Tensor:
+    """index[p] = PyTorch gate row (g*H + u) stored at packed position p = (u//G)*4G + g*G + u%G; for
+    group == WS_GROUP the four gates of a unit are adjacent: p = 128 (u//32) + 4 (u%32) + g."""
     p = torch.arange(4 * hidden, device=device)
+    if group == WS_GROUP:
+        assert hidden % 32 == 0
+        return (p % 4) * hidden + (p // 128) * 32 + (p % 128) // 4
+    assert hidden % group == 0
     blk = p // (4 * group)
     g = (p % (4 * group)) // group
     u = blk * group + p % group

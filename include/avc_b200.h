@@ -188,6 +188,27 @@ typedef struct avc_lstm_desc {
 int avc_lstm_seq(const avc_lstm_desc* d, void* stream);
 
 /*
+ * Small-batch form of the same recurrence (B <= 64, split-bf16 precision only): the recurrent weights stay in
+ * shared memory for the whole sequence (4H/128 row blocks x S K-slices, one thread-block cluster per row block
+ * reducing its partial sums through distributed shared memory), so a frame moves only h_{t-1}.
+ * Same semantics and references as avc_lstm_seq (factory/AutoVC.py:77,96,103,110; factory/LstmDV.py:12,20).
+ * Gate rows of w_hh and columns of xproj are packed  p = 128 (u / 32) + 4 (u % 32) + gate.
+ * Returns AVC_ERR_NOT_RESIDENT (nothing launched) when the grid cannot be co-resident.
+ */
+typedef struct avc_lstm_ws_desc {
+  const float* xproj;         /* [B*T][4H] fp32, packed column order, biases included */
+  const void* w_hh;           /* [4H][2H] = [w_hi | w_lo] bf16, packed row order */
+  void* hseq;                 /* [B][T][2H] split bf16: output sequence and recurrent operand */
+  float* hseq_f32;            /* optional exact fp32 copy (may be NULL) */
+  float* h_last;              /* optional [B][H] fp32: h_{T-1} only (may be NULL) */
+  unsigned int* grid_barrier; /* one counter; zeroed by the library */
+  int B, T, H;
+  long long* debug_clk;       /* optional device buffer, 8 x int64 per (frame, CTA): clock64 stamps (profiling aid) */
+} avc_lstm_ws_desc;
+
+int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream);
+
+/*
  * Bidirectional small-H LSTM layer (H <= 64) with the recurrent weights held in shared memory, one warp
  * per (utterance, direction); optionally emits only the down-sampled content code
  * code_j = [h_fwd[jF+F-1] || h_bwd[jF]]  (factory/AutoVC.py:43,54-66).

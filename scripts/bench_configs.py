@@ -77,6 +77,8 @@ def full_pipeline(precision, B, T=1000):
     ms, _ = timed(lambda: gen(mel), steps=2, warmup=1)
     res["melgan_ms"] = round(ms, 2)
     families(); gen(mel); res["melgan_families"] = fam_summary()
+    families(); dv(src); res["lstmdv_families"] = fam_summary()
+    families(); pipeline.convert(vc, src, eo, et); res["autovc_families"] = fam_summary()
     ms, launches = timed(lambda: pipeline.convert_and_vocode(dv, vc, gen, src, trg), steps=2, warmup=1)
     res.update(config=f"LstmDV x2 + AutoVC(pad 1000->1024, trim) + MelGAN, B={B} T={T} {precision}", ms=round(ms, 2),
                frames_per_s=round(B * T / ms * 1e3), launches=launches,
@@ -87,11 +89,12 @@ def full_pipeline(precision, B, T=1000):
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["meta", "pipe"]
+    precs = os.environ.get("AVC_BENCH_PRECS", "fp32,bf16").split(",")
     if "pipe" in what:
-        for prec in ("fp32", "bf16"):
+        for prec in precs:
             for B in (1, 32):
                 full_pipeline(prec, B)
     if "meta" in what:
-        for prec in ("fp32", "bf16"):
+        for prec in precs:
             meta(MetaPool, "MetaPool", 53.441e9, prec, 512)
             meta(MetaConv, "MetaConv", 55.727e9, prec, 512)

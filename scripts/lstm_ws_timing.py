@@ -1,0 +1,50 @@
+"""Per-frame clock64 breakdown of the weight-stationary small-batch LSTM recurrence (avc_lstm_seq_ws; profiling aid).
+Stamps per (frame, CTA): 0 own cell warps done (producer), 1 grid barrier passed, 2 h slice landed (MMA thread),
+3 accumulator ready (cell warps), 4 partial sums pushed + arrival issued, 5 all partial sums of the owned rows
+arrived, 6 cell update done, 7 h stored."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from autoformer_b200 import ops, packing
+
+
+def run(B=32, T=256, H=1024):
+    torch.manual_seed(0)
+    w_hh = torch.randn(4 * H, H) * 0.03
+    hh = packing.pack_lstm_hh(w_hh, "fp32", packing.WS_GROUP).cuda()
+    xp = (torch.randn(B * T, 4 * H) * 0.5).cuda()
+    for _ in range(2):
+        assert ops.lstm_seq_ws(xp, hh, B, T, H) is not None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.lstm_seq_ws(xp, hh, B, T, H); e1.record()
+    torch.cuda.synchronize()
+    plain = e0.elapsed_time(e1) * 1e3 / T
+    grid_max = 4 * H // 128 * 8
+    dbg = torch.zeros(T * grid_max * 8, dtype=torch.int64, device="cuda")
+    ops.lstm_seq_ws(xp, hh, B, T, H, debug_clk=dbg)
+    torch.cuda.synchronize()
+    flat = dbg.cpu()
+    # the grid is R x S with S = 8 or 4: find it from the stamps written for frame 1
+    for S in (8, 4):
+        grid = 4 * H // 128 * S
+        d = flat[:T * grid * 8].view(T, grid, 8).double()
+        if (d[1:, :, 1] > 0).all() and (flat[T * grid * 8:] == 0).all():
+            break
+    cur, nxt = d[10:T - 1], d[11:T]
+    f = lambda a: f"{a.mean():.0f}"
+    print(f"ws B={B} H={H} S={S} grid={grid}: {plain:.2f} us/frame = {plain * 1.965e3:.0f} cycles @1965 MHz; cycles: "
+          f"barrier (own cells done -> passed) {f(cur[..., 1] - cur[..., 0])}, "
+          f"passed -> h slice landed {f(cur[..., 2] - cur[..., 1])}, "
+          f"MMAs -> accumulator ready {f(cur[..., 3] - cur[..., 2])}, "
+          f"tmem ld + push {f(cur[..., 4] - cur[..., 3])}, "
+          f"wait for the cluster's sums {f(cur[..., 5] - cur[..., 4])}, "
+          f"cell {f(cur[..., 6] - cur[..., 5])}, "
+          f"h store + fence {f(cur[..., 7] - cur[..., 6])}, "
+          f"stored -> producer sees epi_done {f(nxt[..., 0] - cur[..., 7])}, "
+          f"frame {f(nxt[..., 1] - cur[..., 1])}; "
+          f"slowest CTA's barrier arrival {f(cur[..., 0].max(dim=1).values.unsqueeze(1) - cur[..., 0])} after the mean")
+
+
+if __name__ == "__main__":
+    for B, H in ((32, 1024), (32, 768), (32, 512), (1, 1024), (64, 768)):
+        run(B=B, H=H)

@@ -137,6 +137,33 @@ def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=No
     return hseq
 
 
+def _emu_lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None):
+    """Mirror of lstm_ws_kernel: gate rows packed p = 128 (u//32) + 4 (u%32) + gate; split-bf16 operands."""
+    assert ops.ws_supported(B, H, "fp32")
+    w = w_hh[:, :H].double() + w_hh[:, H:].double()
+    xp = xproj.double().reshape(B, T, 4 * H)
+    h = torch.zeros(B, H, dtype=torch.float64)
+    c = torch.zeros(B, H, dtype=torch.float64)
+    outs = torch.zeros(B, T, H, dtype=torch.float64)
+    u = torch.arange(H)
+    base = 128 * (u // 32) + 4 * (u % 32)
+    for t in range(T):
+        hq = packing.act_to_float(packing.to_act(h.float(), "fp32"), "fp32").double()
+        z = xp[:, t] + hq @ w.t()
+        zi, zf, zg, zo = (z[:, base + g] for g in range(4))
+        c = torch.sigmoid(zf) * c + torch.sigmoid(zi) * torch.tanh(zg)
+        h = torch.sigmoid(zo) * torch.tanh(c)
+        outs[:, t] = h
+    if hseq is None:
+        hseq = torch.empty(B, T, 2 * H, dtype=torch.bfloat16)
+    hseq.copy_(packing.to_act(outs.float(), "fp32"))
+    if hseq_f32 is not None:
+        hseq_f32.copy_(outs.float())
+    if h_last is not None:
+        h_last.copy_(outs[:, -1].float())
+    return hseq
+
+
 def _emu_bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=True, split=False):
     xp = xproj.double().view(B, T, 8 * H)
     res = torch.zeros(B, T, 2 * H, dtype=torch.float64)
@@ -321,6 +348,7 @@ def install_cpu_kernels(monkeypatch):
     monkeypatch.setattr(ops, "_require_cuda", lambda *a: None)
     monkeypatch.setattr(ops.ConvGemm, "__call__", _emu_convgemm_call)
     monkeypatch.setattr(ops, "lstm_seq", _emu_lstm_seq)
+    monkeypatch.setattr(ops, "lstm_seq_ws", _emu_lstm_seq_ws)
     monkeypatch.setattr(ops, "bilstm_small", _emu_bilstm_small)
     monkeypatch.setattr(ops, "concat_bcast", _emu_concat_bcast)
     monkeypatch.setattr(ops, "to_act", lambda x, precision, round_tf32=True: _emu_concat_bcast(x, None, x.shape[1], 1, precision))

@@ -161,6 +161,32 @@ def test_adain_models_host_logic(cpu_kernels, name, kind):
         m(i["x"], i["c_org"], None, [[0.0, 1.0]] * 3)      # the reference dereferences c_trg here
 
 
+@pytest.mark.parametrize("B,H", [(2, 512), (32, 1024), (64, 768)])
+def test_lstm_layer_small_batch_takes_weight_stationary_packing(cpu_kernels, B, H):
+    """B <= 64 in split precision: dense projection + avc_lstm_seq_ws with the gates of a unit adjacent
+    (p = 128 (u//32) + 4 (u%32) + gate); the packing of W_ih, the biases and W_hh must agree with that order."""
+    from autoformer_b200 import layers, ops, packing
+    from oracle.layers import lstm_explicit
+    assert ops.ws_supported(B, H, "fp32") and not ops.ws_supported(65, H, "fp32") and not ops.ws_supported(B, H, "bf16")
+    assert not ops.ws_supported(64, 1024, "fp32")          # W slice + 64-row h slice + reduction buffer > 227 KB
+    perm = packing.gate_permutation(H, packing.WS_GROUP)
+    assert sorted(perm.tolist()) == list(range(4 * H))
+    assert perm[:8].tolist() == [0, H, 2 * H, 3 * H, 1, H + 1, 2 * H + 1, 3 * H + 1] and perm[128].item() == 32
+    torch.manual_seed(B)
+    T, I = 4, 80
+    k = 1.0 / H ** 0.5
+    w_ih, w_hh = (torch.rand(4 * H, I) * 2 - 1) * k, (torch.rand(4 * H, H) * 2 - 1) * k
+    b_ih, b_hh = (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
+    x = torch.randn(B, T, I)
+    ref = lstm_explicit(x.double(), w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
+    layer = layers.LstmLayer(w_ih, w_hh, b_ih, b_hh, "fp32")
+    f32 = torch.full((B, T, H), float("nan"))
+    last = torch.full((B, H), float("nan"))
+    layer(packing.to_act(x, "fp32"), B, T, hseq_f32=f32, h_last=last, persistent=True)
+    assert packing.WS_GROUP in layer._packs and not layer._fused_packs
+    assert rel_l2(f32, ref) < 1e-4 and rel_l2(last, ref[:, -1]) < 1e-4
+
+
 def test_lstm_layer_sub_batches_when_persistent_grid_exceeds_one_wave(cpu_kernels):
     """B = 600 at H = 1024 needs 192 CTAs > 148 SMs: the layer must split the batch (utterances are independent) and
     still fill every output the caller asked for."""
