@@ -10,13 +10,16 @@
 // CTA loads only its K-slice of h_{t-1} (B rows: a few KB), issues
 //   W_hi x [h_hi ; h_lo]   (one MMA of width N = 2 B')      and      W_lo x h_hi   (N = B')
 // into a 128 x 2B' accumulator, and the S CTAs of a row block -- one thread-block CLUSTER -- reduce their partial sums
-// through distributed shared memory: every accumulator row is pushed (st.shared::cluster) to the CTA that owns it,
-// followed by a release-arrive on the owner's mbarrier.  Gate rows are packed  p = 128 (u / 32) + 4 (u % 32) + gate,
-// so the 128 / S rows an owner finalises are whole hidden units: it adds xproj, runs the cell (c stays in registers
-// for all T frames), writes h_t in the split operand format, and the frame ends with the same release/acquire grid
-// barrier as the batched kernel (every CTA needs all of h_t).
+// through distributed shared memory: every accumulator row is pushed to the CTA that owns it with st.async, which
+// credits the bytes to the owner's mbarrier (no fence, no separate arrival).  Gate rows are packed
+// p = 128 (u / 32) + 4 (u % 32) + gate, so the 128 / S rows an owner finalises are whole hidden units: it adds xproj,
+// runs the cell (c stays in registers for all T frames) and writes h_t in the split operand format.
+// The frame ends with the same release/acquire grid barrier as the batched kernel (every CTA needs all of h_t).  (A
+// variant without the barrier -- per-CTA progress flags, each consumer polling only the R CTAs that produce its
+// K-slice -- measured slower: 10.9 K instead of 8.8 K cycles per frame; the skew it allows between the CTAs of a
+// cluster comes back as waiting time in the reduction.)
 //
-// Warp roles: 0 = h_{t-1} producer + grid barrier, 1 = MMA issuer, 2..5 = reduction + cell.
+// Warp roles: 0 = grid barrier + h_{t-1} producer, 1 = MMA issuer, 2..5 = reduction + cell (warp 2 stores h_t).
 #include <cuda_bf16.h>
 #include <cstdlib>
 
@@ -31,7 +34,8 @@ constexpr int kWsCellWarps = 4;
 constexpr int kWChunkBytes = 2 * kATileBytes;        // W_hi tile + W_lo tile of one 64-channel chunk
 
 struct alignas(64) WsParams {
-  CUtensorMap tmap_w;     // w_hh as (H, 4H, part), box {64, 128, 2}
+  CUtensorMap tmap_w;     // w_hh as (H, 4H, part), box {64, 128, 2}  (weights in shared memory)
+  const __nv_bfloat16* w; // w_hh [4H][2H]                            (weights in tensor memory)
   CUtensorMap tmap_h;     // hseq as (H, B, part, T), box {64, AR, 2, 1}
   const float* xproj;
   __nv_bfloat16* hseq;
@@ -47,13 +51,21 @@ template <int AR, int S>
 struct WsCfg {
   static constexpr int kRowsOwn = kBlockM / S;        // gate rows each CTA of the cluster finalises
   static constexpr int kUnitsOwn = kRowsOwn / 4;
-  static constexpr int kRedLd = AR + 4;               // floats per reduction-buffer row (16-byte multiple)
+  // reduction buffer of an owner: [source rank s][utterance n][owned row] fp32 -- for one utterance the rows of a
+  // warp are consecutive, so every remote store instruction of the push is one contiguous 128-byte segment
   static constexpr int kHTile = AR * kRowBytes;       // one part of one chunk
-  static constexpr int kRedBytes = (S * kRowsOwn * kRedLd * 4 + 1023) / 1024 * 1024;
+  static constexpr int kRedFrameBytes = S * AR * kRowsOwn * 4;       // what one frame pushes into an owner
+  static constexpr int kRedBytes = (kRedFrameBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = (AR * kUnitsOwn * 4 + 1023) / 1024 * 1024;
-  static constexpr uint32_t kTmemCols = 2 * AR < 32 ? 32 : 2 * AR;
-  static int smem_bytes(int chunks) {
-    return chunks * (kWChunkBytes + 2 * kHTile) + kRedBytes + kStageBytes + 128 + 1024 /* alignment slack */;
+  static constexpr uint32_t kAccCols = 2 * AR < 32 ? 32 : 2 * AR;
+  // tensor memory: the accumulator, then (WT) this CTA's W slice as the A operand: [hi: 32 chunks columns | lo]
+  __host__ __device__ static uint32_t tmem_cols(int chunks, bool wt) {
+    uint32_t need = kAccCols + (wt ? 64u * chunks : 0u), c = 32;
+    while (c < need) c *= 2;
+    return c;
+  }
+  static int smem_bytes(int chunks, bool wt) {
+    return chunks * ((wt ? 0 : kWChunkBytes) + 2 * kHTile) + kRedBytes + kStageBytes + 128 + 1024 /* alignment slack */;
   }
 };
 
@@ -62,13 +74,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+// 16-byte store into a cluster peer's shared memory that credits its bytes to the peer's mbarrier on completion
+__device__ __forceinline__ void st_async_f4(uint32_t addr, uint32_t mbar, float4 v) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
                : "memory");
-}
-// release at cluster scope: this thread's earlier st.shared::cluster are visible to whoever acquires the barrier
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
@@ -89,22 +99,22 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
-template <int AR, int S>
+template <int AR, int S, bool WT>
 __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_constant__ WsParams p) {
   using Cfg = WsCfg<AR, S>;
   constexpr int NQ = AR / 4;                         // groups of 4 utterances
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = base;
-  uint8_t* s_h = s_w + p.chunks * kWChunkBytes;
+  uint8_t* s_h = s_w + (WT ? 0 : p.chunks * kWChunkBytes);
   float* s_red = reinterpret_cast<float*>(s_h + p.chunks * 2 * Cfg::kHTile);
   float* s_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_red) + Cfg::kRedBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stage) + Cfg::kStageBytes);
   uint64_t* w_full = bars + 0;
-  uint64_t* h_full = bars + 1;
-  uint64_t* d_full = bars + 2;
-  uint64_t* red_full = bars + 3;      // all 128 rows this CTA owns have been pushed by the S CTAs of the cluster
-  uint64_t* epi_done = bars + 4;      // this CTA's cell warps have stored h_t
+  uint64_t* d_full = bars + 1;        // the frame's MMAs have completed (accumulator ready)
+  uint64_t* red_full = bars + 2;      // all partial sums of the rows this CTA owns have landed
+  uint64_t* epi_done = bars + 3;      // this CTA's h_t is stored (and the accumulator drained)
+  uint64_t* h_full = bars + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,36 +127,41 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
   if (clk) clk[((long long)(t_) * n_ctas + blockIdx.x) * 8 + (i_)] = clock64()
 
   if (threadIdx.x == 0) {
-    mbar_init(w_full, 1);
+    mbar_init(w_full, WT ? kWsCellWarps : 1);
     mbar_init(h_full, 1);
     mbar_init(d_full, 1);
-    mbar_init(red_full, kBlockM);
-    mbar_init(epi_done, kWsCellWarps);
+    mbar_init(red_full, 1);
+    mbar_init(epi_done, 1);
     fence_mbar_init();
-    prefetch_tmap(&p.tmap_w);
+    if (!WT) prefetch_tmap(&p.tmap_w);
     prefetch_tmap(&p.tmap_h);
   }
+  const uint32_t tmem_cols = Cfg::tmem_cols(p.chunks, WT);
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_alloc(tmem_ptr, tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
-  cluster_sync_all();                 // peers arrive on this CTA's red_full: its init must be visible cluster-wide
+  cluster_sync_all();                 // peers credit bytes to this CTA's red_full: its init must be visible cluster-wide
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
+  const uint32_t tmem_w = tmem_base + Cfg::kAccCols;        // WT: W_hi at columns [0, 32 chunks), W_lo behind it
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (!WT && lane == 0) {
       mbar_arrive_expect_tx(w_full, p.chunks * kWChunkBytes);
       for (int c = 0; c < p.chunks; ++c)
         tma_load_3d(s_w + c * kWChunkBytes, &p.tmap_w, w_full, k0 + c * 64, r * kBlockM, 0);
+    }
+    if (lane == 0) {
       for (int t = 1; t < p.T; ++t) {
-        // h_{t-1}: this CTA's cell warps, then every CTA of the grid
+        // h_{t-1}: this CTA's part is stored, then every CTA's
         mbar_wait(epi_done, (t - 1) & 1);
         AVC_WS_STAMP(t, 0);
         grid_arrive_wait(p.grid_barrier, (unsigned)t * n_ctas);
         AVC_WS_STAMP(t, 1);
         fence_proxy_async_global();     // h_{t-1} was written with generic stores
+        // (one mbarrier per chunk, so that the MMAs start on the first chunk, measured slower: +430 cycles per frame)
         mbar_arrive_expect_tx(h_full, p.chunks * 2 * Cfg::kHTile);
         for (int c = 0; c < p.chunks; ++c)
           tma_load_4d(s_h + c * 2 * Cfg::kHTile, &p.tmap_h, h_full, k0 + c * 64, 0, 0, t - 1);
@@ -157,20 +172,32 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
     if (lane == 0) {
       constexpr uint32_t wide = umma_idesc(kBlockM, 2 * AR, false), narrow = umma_idesc(kBlockM, AR, false);
       mbar_wait(w_full, 0);
+      tc_fence_after();
       for (int t = 1; t < p.T; ++t) {
+        // (the accumulator is free: h_{t-1} exists only after this CTA's cell warps drained frame t - 1)
         mbar_wait(h_full, (t - 1) & 1);
         AVC_WS_STAMP(t, 2);
-        tc_fence_after();
+        tc_fence_after();               // orders the cell warps' accumulator reads of frame t - 1 before these MMAs
         for (int c = 0; c < p.chunks; ++c) {
-          const uint32_t w_hi = smem_u32(s_w + c * kWChunkBytes), w_lo = w_hi + kATileBytes;
           const uint32_t h = smem_u32(s_h + c * 2 * Cfg::kHTile);            // [h_hi rows ; h_lo rows]
+          if (WT) {
+            const uint32_t w_hi = tmem_w + c * 32, w_lo = w_hi + p.chunks * 32;   // 8 columns per K = 16
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, umma_desc_sw128(w_hi + k * 32), umma_desc_sw128(h + k * 32), wide,
-                      (c == 0 && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem_base, w_hi + k * 8, umma_desc_sw128(h + k * 32), wide, (c == 0 && k == 0) ? 0u : 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, umma_desc_sw128(w_lo + k * 32), umma_desc_sw128(h + k * 32), narrow, 1u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem_base, w_lo + k * 8, umma_desc_sw128(h + k * 32), narrow, 1u);
+          } else {
+            const uint32_t w_hi = smem_u32(s_w + c * kWChunkBytes), w_lo = w_hi + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, umma_desc_sw128(w_hi + k * 32), umma_desc_sw128(h + k * 32), wide,
+                        (c == 0 && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, umma_desc_sw128(w_lo + k * 32), umma_desc_sw128(h + k * 32), narrow, 1u);
+          }
         }
         umma_commit(d_full);
       }
@@ -180,12 +207,34 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
     const int q = warp & 3;                           // TMEM lane quarter
     const int row = q * 32 + lane;                    // accumulator row = packed gate row within the row block
     const int e = (warp - 2) * 32 + lane;             // owner-phase index
-    const int n4 = e % NQ, u_own = e / NQ;
-    const bool active = u_own < Cfg::kUnitsOwn;
+    const int u_own = e % Cfg::kUnitsOwn, n4 = e / Cfg::kUnitsOwn;   // adjacent lanes: adjacent units (contiguous reads)
+    const bool active = n4 < NQ;
+    // reduction buffer of an owner: [source rank][group of 4 utterances][gate][owned unit][4] fp32 -- a warp's
+    // 16-byte stores of one group fill one contiguous 512-byte run, and the cell threads of adjacent units read
+    // adjacent float4 (no bank conflicts)
     const uint32_t owner = row / Cfg::kRowsOwn;
-    const uint32_t push_addr =
-        map_to_cta(smem_u32(s_red + ((int)rank * Cfg::kRowsOwn + row % Cfg::kRowsOwn) * Cfg::kRedLd), owner);
+    const int slot = (row & 3) * Cfg::kUnitsOwn + (row % Cfg::kRowsOwn) / 4;
+    const uint32_t push_addr = map_to_cta(smem_u32(s_red + ((int)rank * NQ * Cfg::kRowsOwn + slot) * 4), owner);
     const uint32_t owner_bar = map_to_cta(smem_u32(red_full), owner);
+    if (WT) {
+      // this thread's W row -> its TMEM lane, once: 32 bf16 (16 columns) per store, hi half then lo half
+      const uint4* src = reinterpret_cast<const uint4*>(p.w + ((long long)r * kBlockM + row) * (2LL * p.H) + k0);
+      const uint32_t lane_base = tmem_w + (static_cast<uint32_t>(q * 32) << 16);
+      for (int part = 0; part < 2; ++part)
+        for (int g = 0; g < 2 * p.chunks; ++g) {
+          uint32_t v[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 u = __ldg(src + part * (p.H / 8) + g * 4 + i);
+            v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
+          }
+          tmem_st_32x16(lane_base + part * p.chunks * 32 + g * 16, v);
+        }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_full);
+    }
     float c_state[4] = {0.f, 0.f, 0.f, 0.f};
     const long long H4 = 4LL * p.H;
     for (int t = 0; t < p.T; ++t) {
@@ -205,6 +254,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
         z[j][0] = xp[j].x; z[j][1] = xp[j].y; z[j][2] = xp[j].z; z[j][3] = xp[j].w;
       }
       if (t > 0) {
+        if (threadIdx.x == 64) mbar_arrive_expect_tx(red_full, Cfg::kRedFrameBytes);
         mbar_wait(d_full, (t - 1) & 1);
         if (threadIdx.x == 64) AVC_WS_STAMP(t, 3);
         tc_fence_after();
@@ -217,24 +267,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            st_cluster_f4(push_addr + (j * 16 + i * 4) * 4,
-                          make_float4(__uint_as_float(a[i * 4]) + __uint_as_float(b[i * 4]),
-                                      __uint_as_float(a[i * 4 + 1]) + __uint_as_float(b[i * 4 + 1]),
-                                      __uint_as_float(a[i * 4 + 2]) + __uint_as_float(b[i * 4 + 2]),
-                                      __uint_as_float(a[i * 4 + 3]) + __uint_as_float(b[i * 4 + 3])));
+            st_async_f4(push_addr + (j * 4 + i) * Cfg::kRowsOwn * 16, owner_bar,
+                        make_float4(__uint_as_float(a[i * 4]) + __uint_as_float(b[i * 4]),
+                                    __uint_as_float(a[i * 4 + 1]) + __uint_as_float(b[i * 4 + 1]),
+                                    __uint_as_float(a[i * 4 + 2]) + __uint_as_float(b[i * 4 + 2]),
+                                    __uint_as_float(a[i * 4 + 3]) + __uint_as_float(b[i * 4 + 3])));
         }
         tc_fence_before();              // accumulator reads before the next frame's MMAs (via epi_done -> h_full)
-        mbar_arrive_remote(owner_bar);
         if (threadIdx.x == 64) AVC_WS_STAMP(t, 4);
         mbar_wait_cluster(red_full, (t - 1) & 1);
         if (threadIdx.x == 64) AVC_WS_STAMP(t, 5);
         if (active) {
+          const float* red = s_red;
 #pragma unroll
           for (int s = 0; s < S; ++s)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const float4 v = *reinterpret_cast<const float4*>(
-                  s_red + (s * Cfg::kRowsOwn + 4 * u_own + g) * Cfg::kRedLd + 4 * n4);
+                  red + ((s * NQ + n4) * Cfg::kRowsOwn + g * Cfg::kUnitsOwn + u_own) * 4);   // gate g, utterances 4 n4 .. + 3
               z[0][g] += v.x; z[1][g] += v.y; z[2][g] += v.z; z[3][g] += v.w;
             }
         }
@@ -250,28 +300,32 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsCellWarps) : "memory");
       if (threadIdx.x == 64) AVC_WS_STAMP(t, 6);
-      // utterance n = e: the kUnitsOwn units this CTA finalised, as whole 8-byte groups of the split operand format
-      if (e < AR && e < p.B) {
-        const long long orow = (long long)e * p.T + t;
-        const int ug = r * 32 + (int)rank * Cfg::kUnitsOwn;
+      if (warp == 2) {
+        // utterance n: the kUnitsOwn units this CTA finalised, as whole 8-byte groups of the split operand format
+        for (int n = lane; n < AR && n < p.B; n += 32) {
+          const long long orow = (long long)n * p.T + t;
+          const int ug = r * 32 + (int)rank * Cfg::kUnitsOwn;
 #pragma unroll
-        for (int i = 0; i < Cfg::kUnitsOwn / 4; ++i) {
-          const float4 h = *reinterpret_cast<const float4*>(s_stage + e * Cfg::kUnitsOwn + i * 4);
-          const float lx = h.x - __bfloat162float(__float2bfloat16_rn(h.x));
-          const float ly = h.y - __bfloat162float(__float2bfloat16_rn(h.y));
-          const float lz = h.z - __bfloat162float(__float2bfloat16_rn(h.z));
-          const float lw = h.w - __bfloat162float(__float2bfloat16_rn(h.w));
-          __nv_bfloat16* o = p.hseq + orow * (2LL * p.H) + ug + i * 4;
-          *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
-          *reinterpret_cast<uint2*>(o + p.H) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
-          if (p.hseq_f32) *reinterpret_cast<float4*>(p.hseq_f32 + orow * p.H + ug + i * 4) = h;
-          if (p.h_last && t == p.T - 1) *reinterpret_cast<float4*>(p.h_last + (long long)e * p.H + ug + i * 4) = h;
+          for (int i = 0; i < Cfg::kUnitsOwn / 4; ++i) {
+            const float4 h = *reinterpret_cast<const float4*>(s_stage + n * Cfg::kUnitsOwn + i * 4);
+            const float lx = h.x - __bfloat162float(__float2bfloat16_rn(h.x));
+            const float ly = h.y - __bfloat162float(__float2bfloat16_rn(h.y));
+            const float lz = h.z - __bfloat162float(__float2bfloat16_rn(h.z));
+            const float lw = h.w - __bfloat162float(__float2bfloat16_rn(h.w));
+            __nv_bfloat16* o = p.hseq + orow * (2LL * p.H) + ug + i * 4;
+            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
+            *reinterpret_cast<uint2*>(o + p.H) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+            if (p.hseq_f32) *reinterpret_cast<float4*>(p.hseq_f32 + orow * p.H + ug + i * 4) = h;
+            if (p.h_last && t == p.T - 1) *reinterpret_cast<float4*>(p.h_last + (long long)n * p.H + ug + i * 4) = h;
+          }
+          fence_proxy_async_global();   // order the h stores before later async-proxy (TMA) reads
         }
-        fence_proxy_async_global();     // order the h stores before later async-proxy (TMA) reads
+        __syncwarp();
+        if (lane == 0) {
+          AVC_WS_STAMP(t, 7);
+          mbar_arrive(epi_done);        // after bar.sync 1: every cell warp has drained the accumulator too
+        }
       }
-      __syncwarp();
-      if (threadIdx.x == 64) AVC_WS_STAMP(t, 7);
-      if (lane == 0) mbar_arrive(epi_done);
     }
   }
   __syncwarp();
@@ -279,15 +333,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
   cluster_sync_all();                   // no CTA may exit while a peer can still push into its shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
-template <int AR, int S>
+template <int AR, int S, bool WT>
 static int launch_ws(WsParams p, const avc_lstm_ws_desc* d, cudaStream_t stream) {
   using Cfg = WsCfg<AR, S>;
-  auto kern = lstm_ws_kernel<AR, S>;
-  const int smem = Cfg::smem_bytes(p.chunks);
+  auto kern = lstm_ws_kernel<AR, S, WT>;
+  const int smem = Cfg::smem_bytes(p.chunks, WT);
   AVC_REQUIRE(smem <= 227 * 1024, "avc_lstm_seq_ws: H=%d B=%d needs %d bytes of shared memory", d->H, d->B, smem);
   static int configured = 0;
   if (configured < smem) {
@@ -346,6 +400,9 @@ extern "C" int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream_v) {
   const uint64_t sh[3] = {(uint64_t)d->T * 2 * H * 2, H * 2, 2 * H * 2};
   const uint32_t bh[4] = {64, (uint32_t)ar, 2, 1};
   if (!encode_tmap_4d(&p.tmap_h, 2, d->hseq, dh, sh, bh)) return -3;
+  // the W slice lives in tensor memory as the MMA's A operand (AVC_WS_W_SMEM=1: in shared memory, for A/B timing)
+  static const bool wt = getenv("AVC_WS_W_SMEM") == nullptr;
+  p.w = static_cast<const __nv_bfloat16*>(d->w_hh);
   p.xproj = d->xproj;
   p.hseq = static_cast<__nv_bfloat16*>(d->hseq);
   p.hseq_f32 = d->hseq_f32;
@@ -361,9 +418,12 @@ extern "C" int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream_v) {
 #define AVC_WS_DISPATCH(S_)                                                                     \
   if (d->H % (64 * S_) == 0 && R * S_ <= num_sms()) {                                           \
     p.chunks = d->H / S_ / 64;                                                                  \
-    const int rc = ar == 16   ? launch_ws<16, S_>(p, d, stream)                                 \
-                   : ar == 32 ? launch_ws<32, S_>(p, d, stream)                                 \
-                              : launch_ws<64, S_>(p, d, stream);                                \
+    const int rc = wt ? (ar == 16   ? launch_ws<16, S_, true>(p, d, stream)                     \
+                         : ar == 32 ? launch_ws<32, S_, true>(p, d, stream)                     \
+                                    : launch_ws<64, S_, true>(p, d, stream))                    \
+                      : (ar == 16   ? launch_ws<16, S_, false>(p, d, stream)                    \
+                         : ar == 32 ? launch_ws<32, S_, false>(p, d, stream)                    \
+                                    : launch_ws<64, S_, false>(p, d, stream));                  \
     if (rc != AVC_ERR_NOT_RESIDENT) return rc;                                                  \
   }
   AVC_WS_DISPATCH(8)

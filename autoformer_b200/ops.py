@@ -299,7 +299,7 @@ def ws_supported(B, H, precision, n_sm=148):
         return False
     ar = 16 if B <= 16 else (32 if B <= 32 else 64)
     chunks = H // 4 // 64
-    red = (128 * (ar + 4) * 4 + 1023) // 1024 * 1024
+    red = (128 * ar * 4 + 1023) // 1024 * 1024
     stage = (ar * 8 * 4 + 1023) // 1024 * 1024
     return chunks * (32768 + 2 * ar * 128) + red + stage + 1152 <= 227 * 1024
 
@@ -324,7 +324,7 @@ def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, deb
     if h_last is not None:
         assert h_last.is_contiguous() and h_last.shape == (B, H) and h_last.dtype == torch.float32
         d.h_last = h_last.data_ptr()
-    bar = torch.empty(32, dtype=torch.int32, device=dev)              # zeroed by the library
+    bar = torch.empty(256, dtype=torch.int32, device=dev)             # zeroed by the library
     d.grid_barrier = bar.data_ptr()
     d.B, d.T, d.H = B, T, H
     if debug_clk is not None:

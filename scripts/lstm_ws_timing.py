@@ -1,7 +1,7 @@
 """Per-frame clock64 breakdown of the weight-stationary small-batch LSTM recurrence (avc_lstm_seq_ws; profiling aid).
-Stamps per (frame, CTA): 0 own cell warps done (producer), 1 grid barrier passed, 2 h slice landed (MMA thread),
-3 accumulator ready (cell warps), 4 partial sums pushed + arrival issued, 5 all partial sums of the owned rows
-arrived, 6 cell update done, 7 h stored."""
+Stamps per (frame, CTA): 0 own h stored (seen by the producer thread), 1 grid barrier passed, 2 h slice landed
+(MMA thread), 3 accumulator ready (cell warps), 4 partial sums pushed, 5 all partial sums of the owned
+rows landed, 6 cell update done, 7 h stored.  clock64 is per SM: only differences within one CTA are meaningful."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -33,16 +33,14 @@ def run(B=32, T=256, H=1024):
     cur, nxt = d[10:T - 1], d[11:T]
     f = lambda a: f"{a.mean():.0f}"
     print(f"ws B={B} H={H} S={S} grid={grid}: {plain:.2f} us/frame = {plain * 1.965e3:.0f} cycles @1965 MHz; cycles: "
-          f"barrier (own cells done -> passed) {f(cur[..., 1] - cur[..., 0])}, "
+          f"h stored -> barrier passed {f(nxt[..., 1] - cur[..., 7])} (of which after the producer saw it {f(nxt[..., 1] - nxt[..., 0])}), "
           f"passed -> h slice landed {f(cur[..., 2] - cur[..., 1])}, "
           f"MMAs -> accumulator ready {f(cur[..., 3] - cur[..., 2])}, "
           f"tmem ld + push {f(cur[..., 4] - cur[..., 3])}, "
           f"wait for the cluster's sums {f(cur[..., 5] - cur[..., 4])}, "
           f"cell {f(cur[..., 6] - cur[..., 5])}, "
-          f"h store + fence {f(cur[..., 7] - cur[..., 6])}, "
-          f"stored -> producer sees epi_done {f(nxt[..., 0] - cur[..., 7])}, "
-          f"frame {f(nxt[..., 1] - cur[..., 1])}; "
-          f"slowest CTA's barrier arrival {f(cur[..., 0].max(dim=1).values.unsqueeze(1) - cur[..., 0])} after the mean")
+          f"h store {f(cur[..., 7] - cur[..., 6])}, "
+          f"frame {f(nxt[..., 1] - cur[..., 1])}")
 
 
 if __name__ == "__main__":
