@@ -14,10 +14,14 @@
 // credits the bytes to the owner's mbarrier (no fence, no separate arrival).  Gate rows are packed
 // p = 128 (u / 32) + 4 (u % 32) + gate, so the 128 / S rows an owner finalises are whole hidden units: it adds xproj,
 // runs the cell (c stays in registers for all T frames) and writes h_t in the split operand format.
-// The frame ends with the same release/acquire grid barrier as the batched kernel (every CTA needs all of h_t).  (A
-// variant without the barrier -- per-CTA progress flags, each consumer polling only the R CTAs that produce its
-// K-slice -- measured slower: 10.9 K instead of 8.8 K cycles per frame; the skew it allows between the CTAs of a
-// cluster comes back as waiting time in the reduction.)
+// The frame ends with the same release/acquire grid barrier as the batched kernel (every CTA needs all of h_t).
+// Two barrier-free variants were built and measured slower (B = 32, H = 1024, cycles per frame; barrier: 8.1 K):
+//  - per-CTA progress flags, each consumer polling only the H / 32 CTAs that produce its K-slice: 10.9 K;
+//  - h_t exchanged in a flag-carrying format (8-byte words {2 bf16, frame tag}, no fence, no counter, consumers poll
+//    the data itself): 26.7 K at B = 32 (every CTA re-reads 64 KB of tagged words per poll round), 7.4 K at B = 1
+//    against 7.2 K with the barrier.
+// Without the barrier the CTAs of a cluster drift up to one frame apart and the time comes back as waiting in the
+// reduction and before the MMAs; the slowest of the producers sets the pace either way.
 //
 // Warp roles: 0 = grid barrier + h_{t-1} producer, 1 = MMA issuer, 2..5 = reduction + cell (warp 2 stores h_t).
 #include <cuda_bf16.h>
@@ -157,8 +161,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
       for (int t = 1; t < p.T; ++t) {
         // h_{t-1}: this CTA's part is stored, then every CTA's
         mbar_wait(epi_done, (t - 1) & 1);
-        AVC_WS_STAMP(t, 0);
-        grid_arrive_wait(p.grid_barrier, (unsigned)t * n_ctas);
+        grid_arrive_wait(p.grid_barrier, (unsigned)t * n_ctas,
+                         clk ? clk + ((long long)t * n_ctas + blockIdx.x) * 8 : nullptr);   // stamp 0: arrival issued
         AVC_WS_STAMP(t, 1);
         fence_proxy_async_global();     // h_{t-1} was written with generic stores
         // (one mbarrier per chunk, so that the MMAs start on the first chunk, measured slower: +430 cycles per frame)

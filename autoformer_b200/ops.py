@@ -293,15 +293,16 @@ WS_MAX_BATCH = 64
 
 def ws_supported(B, H, precision, n_sm=148):
     """Shapes the weight-stationary recurrence (avc_lstm_seq_ws) takes: split precision, B <= 64, the 4H/128 row
-    blocks x 4 K-slices within one wave (8 slices are used when the device can hold them), W slice + h slice +
-    reduction buffer within 227 KB of shared memory."""
+    blocks x 4 K-slices within one wave (8 slices are used when the device can hold them); the W slice lives in
+    tensor memory (<= 256 of the 512 columns, beside the accumulator), the h slice and the reduction buffer in
+    shared memory."""
     if precision != "fp32" or B < 1 or B > WS_MAX_BATCH or H % 256 or 4 * H // 128 * 4 > n_sm:
         return False
     ar = 16 if B <= 16 else (32 if B <= 32 else 64)
     chunks = H // 4 // 64
     red = (128 * ar * 4 + 1023) // 1024 * 1024
     stage = (ar * 8 * 4 + 1023) // 1024 * 1024
-    return chunks * (32768 + 2 * ar * 128) + red + stage + 1152 <= 227 * 1024
+    return chunks * 2 * ar * 128 + red + stage + 1152 <= 227 * 1024 and 2 * ar + 64 * chunks <= 512
 
 
 def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, debug_clk=None):

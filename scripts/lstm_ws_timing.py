@@ -1,5 +1,5 @@
 """Per-frame clock64 breakdown of the weight-stationary small-batch LSTM recurrence (avc_lstm_seq_ws; profiling aid).
-Stamps per (frame, CTA): 0 own h stored (seen by the producer thread), 1 grid barrier passed, 2 h slice landed
+Stamps per (frame, CTA): 0 barrier arrival issued (own h stored, membar done), 1 grid barrier passed, 2 h slice landed
 (MMA thread), 3 accumulator ready (cell warps), 4 partial sums pushed, 5 all partial sums of the owned
 rows landed, 6 cell update done, 7 h stored.  clock64 is per SM: only differences within one CTA are meaningful."""
 import os, sys
@@ -33,7 +33,7 @@ def run(B=32, T=256, H=1024):
     cur, nxt = d[10:T - 1], d[11:T]
     f = lambda a: f"{a.mean():.0f}"
     print(f"ws B={B} H={H} S={S} grid={grid}: {plain:.2f} us/frame = {plain * 1.965e3:.0f} cycles @1965 MHz; cycles: "
-          f"h stored -> barrier passed {f(nxt[..., 1] - cur[..., 7])} (of which after the producer saw it {f(nxt[..., 1] - nxt[..., 0])}), "
+          f"h stored -> barrier passed {f(nxt[..., 1] - cur[..., 7])} (of which after the arrival was issued {f(nxt[..., 1] - nxt[..., 0])}), "
           f"passed -> h slice landed {f(cur[..., 2] - cur[..., 1])}, "
           f"MMAs -> accumulator ready {f(cur[..., 3] - cur[..., 2])}, "
           f"tmem ld + push {f(cur[..., 4] - cur[..., 3])}, "

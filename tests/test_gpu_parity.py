@@ -110,7 +110,8 @@ def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent, fused
 
 
 @pytest.mark.parametrize("B,T,I,H", [(1, 5, 80, 512), (2, 40, 320, 512), (16, 7, 80, 768), (17, 9, 512, 1024),
-                                     (32, 30, 1024, 1024), (33, 6, 768, 768), (64, 12, 80, 768), (64, 5, 320, 512)])
+                                     (32, 30, 1024, 1024), (33, 6, 768, 768), (64, 12, 80, 768), (64, 5, 320, 512),
+                                     (64, 6, 512, 1024)])
 def test_lstm_ws_matches_explicit_lstm(B, T, I, H):
     """Small-batch recurrence with W_hh resident in shared memory (avc_lstm_seq_ws): every activation-row variant
     (16 / 32 / 64), both cluster sizes (H = 512: 8 K-slices; 768 / 1024: 4), ragged batches."""
