@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libavc_b200.so")
 ERR_NOT_RESIDENT = -4
 DTYPE_TF32 = 0
 DTYPE_BF16 = 1
+DTYPE_F16 = 3
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_LRELU, ACT_GELU, ACT_LOG10_CLAMP = 0, 1, 2, 3, 4, 5
 ACTS = {"none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH, "lrelu": ACT_LRELU, "gelu": ACT_GELU,
         "log10_clamp": ACT_LOG10_CLAMP}

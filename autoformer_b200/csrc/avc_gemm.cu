@@ -37,7 +37,8 @@ struct alignas(64) GemmParams {
   int phases, cs;        // N = phases * cs; output time = phases * t + n / cs
   void* out;
   long long out_ld;
-  int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16
+  int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16, 3 fp16
+  uint32_t fmt_xor;       // kIdescF16Xor when the 16-bit operands are fp16
   void* out_raw;
   long long out_raw_ld;
   float* out2;
@@ -71,6 +72,9 @@ __device__ __forceinline__ void store4(void* base, int mode, int round, long lon
   } else if (mode == 1) {
     uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + row * ld + c) = pk;
+  } else if (mode == 3) {
+    uint2 pk = make_uint2(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]));
+    *reinterpret_cast<uint2*>(static_cast<__half*>(base) + row * ld + c) = pk;
   } else {
     float4 o = round ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
                      : make_float4(v[0], v[1], v[2], v[3]);
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           if (ud && kb == 0) ud[4] = clock64();                            // first k-block landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(s.base + rs.stage * C::kStageBytes);
-          issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, acc, kb == 0);
+          issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, acc, kb == 0, p.fmt_xor);
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
           rs.advance<C::kStages>();
@@ -366,12 +370,13 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   using namespace avc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(d != nullptr, "avc_conv_gemm: null descriptor");
-  AVC_REQUIRE(d->dtype == AVC_DTYPE_TF32 || d->dtype == AVC_DTYPE_BF16, "avc_conv_gemm: bad dtype %d", d->dtype);
+  AVC_REQUIRE(d->dtype == AVC_DTYPE_TF32 || d->dtype == AVC_DTYPE_BF16 || d->dtype == AVC_DTYPE_F16,
+              "avc_conv_gemm: bad dtype %d", d->dtype);
   AVC_REQUIRE(d->B > 0 && d->T > 0 && d->N > 0 && d->N % 4 == 0, "avc_conv_gemm: bad shape B=%d T=%d N=%d", d->B,
               d->T, d->N);
   AVC_REQUIRE(d->a_taps[0] > 0 && d->a_ptr[0] && d->w_ptr && d->bias, "avc_conv_gemm: missing operand");
   AVC_REQUIRE(d->out || d->out2 || d->out_raw, "avc_conv_gemm: no output");
-  const int es = d->dtype == AVC_DTYPE_BF16 ? 2 : 4;
+  const int es = d->dtype == AVC_DTYPE_TF32 ? 4 : 2;
   const int kc = kRowBytes / es;
 
   int bn = d->block_n;
@@ -447,7 +452,8 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   p.out_rows_per_utt = d->out_rows_per_utt;
   p.out_row0 = d->out_row0;
   p.out_mode = d->out_dtype;
-  AVC_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 2, "avc_conv_gemm: out_dtype %d", d->out_dtype);
+  AVC_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 3, "avc_conv_gemm: out_dtype %d", d->out_dtype);
+  p.fmt_xor = d->dtype == AVC_DTYPE_F16 ? kIdescF16Xor : 0u;
   const long long min_ld = d->out_dtype == 2 ? 2LL * p.cs : p.cs;
   p.out_round = d->out_round_tf32;
   p.out_reflect = d->out_reflect;
@@ -470,7 +476,7 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   if (d->out2) AVC_REQUIRE(d->out2_ld % 4 == 0 && d->out2_ld >= p.cs, "avc_conv_gemm: out2_ld");
   if (d->residual) AVC_REQUIRE(d->res_ld % 4 == 0 && d->res_ld >= p.cs, "avc_conv_gemm: res_ld");
 
-  const bool bf16 = d->dtype == AVC_DTYPE_BF16;
+  const bool bf16 = d->dtype != AVC_DTYPE_TF32;      // 16-bit operands (bf16 or fp16)
   switch (bn) {
     case 64: return bf16 ? launch<64, true>(p, m_tiles, ctas, stream) : launch<64, false>(p, m_tiles, ctas, stream);
     case 128: return bf16 ? launch<128, true>(p, m_tiles, ctas, stream) : launch<128, false>(p, m_tiles, ctas, stream);

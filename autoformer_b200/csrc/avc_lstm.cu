@@ -80,6 +80,8 @@ __device__ __forceinline__ void issue_stage(uint32_t a_hi, uint32_t a_lo, uint32
   if (MODE == 2) {
     issue_pair<2 * BN, BF16, CTAS>(a_hi, w_hi, acc, first);                                        // a_hi * [W_hi | W_lo]
     issue_pair<BN, BF16, CTAS>(a_lo, w_hi, acc + SplitAcc<BN, CTAS, true>::kLoOffset, false);                 // a_lo * W_hi
+  } else if (MODE == 3) {
+    issue_pair<2 * BN, BF16, CTAS>(a_hi, w_hi, acc, first, kIdescF16Xor);                          // a * [W_hi | W_lo], fp16
   } else {
     issue_pair<BN, BF16, CTAS>(a_hi, w_hi, acc, first);
   }
@@ -139,6 +141,10 @@ __device__ __forceinline__ void store_h8(const LstmParams& p, long long row, int
     uint4 pk = make_uint4(pack_bf16(hn[0], hn[1]), pack_bf16(hn[2], hn[3]), pack_bf16(hn[4], hn[5]),
                           pack_bf16(hn[6], hn[7]));
     *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.hseq) + hoff) = pk;
+  } else if (MODE == 3) {
+    uint4 pk = make_uint4(pack_f16(hn[0], hn[1]), pack_f16(hn[2], hn[3]), pack_f16(hn[4], hn[5]),
+                          pack_f16(hn[6], hn[7]));
+    *reinterpret_cast<uint4*>(static_cast<__half*>(p.hseq) + hoff) = pk;
   } else {
     float* hp = static_cast<float*>(p.hseq) + hoff;
     *reinterpret_cast<float4*>(hp) =
@@ -158,13 +164,15 @@ __device__ __forceinline__ void store_h8(const LstmParams& p, long long row, int
   }
 }
 
-// MODE: 0 = tf32, 1 = bf16, 2 = split bf16 (three bf16 products per fp32 product, operands staged once)
+// MODE: 0 = tf32, 1 = bf16, 2 = split bf16 (three bf16 products per fp32 product, operands staged once),
+//       3 = fp16 activations x [W_hi | W_lo] fp16 weights (one wide MMA per stage: two products per fp32 product)
 template <int BN, int MODE, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_constant__ LstmParams p) {
-  constexpr int PARTS = MODE == 2 ? 2 : 1;
+  constexpr int PARTS = MODE >= 2 ? 2 : 1;       // weight tiles per stage (ring sizing)
+  constexpr int APARTS = MODE == 2 ? 2 : 1;      // activation tiles per stage
   constexpr int kXSlabs = BN / 32;                         // xproj tile = BN/32 swizzled slabs of 128 rows x 128 B
   constexpr int kXBytes = kXSlabs * kATileBytes;
-  using SA = SplitAcc<BN, CTAS, MODE == 2>;
+  using SA = SplitAcc<BN, CTAS, MODE >= 2>;
   using C = PipeCfg<BN, CTAS, PARTS, false, kXBytes, 1, SA::kCols>;
   constexpr int G = BN / 4;
   extern __shared__ uint8_t smem_raw[];
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
         // the grid barrier, while the cell epilogue of frame t is still running; only the h loads wait for it.
         auto issue = [&](int kb, int frame, bool want_w, bool want_h, uint32_t stage) {
           uint8_t* st = s.base + stage * p.stage_bytes;
-          uint8_t* wst = st + PARTS * p.a_tile;
+          uint8_t* wst = st + APARTS * p.a_tile;
           const int kc0 = kb * p.kc_elems;
           if (want_w) {
             if (CTAS == 1 || leader) mbar_arrive_expect_tx(&s.full[stage], CTAS * p.stage_tx);
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) lstm_step_kernel(const __grid_
           if (dbg && kb == 0) dbg[1] = clock64();                          // first stage landed
           tc_fence_after();
           const uint32_t a_hi = smem_u32(s.base + rs.stage * p.stage_bytes);
-          const uint32_t w_hi = a_hi + PARTS * p.a_tile;
+          const uint32_t w_hi = a_hi + APARTS * p.a_tile;
           issue_stage<BN, MODE, CTAS>(a_hi, a_hi + p.a_tile, w_hi, tmem_base, kb == 0);
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
           rs.advance(p.stages);
@@ -379,8 +387,9 @@ constexpr int kBiasBytes = 1024;
 
 template <int BN, int MODE, int CTAS>
 __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __grid_constant__ LstmParams p) {
-  constexpr int PARTS = MODE == 2 ? 2 : 1;
-  using SA = SplitAcc<BN, CTAS, MODE == 2>;
+  constexpr int PARTS = MODE >= 2 ? 2 : 1;       // weight tiles per stage (ring sizing)
+  constexpr int APARTS = MODE == 2 ? 2 : 1;      // activation tiles per stage
+  using SA = SplitAcc<BN, CTAS, MODE >= 2>;
   using C = PipeCfg<BN, CTAS, PARTS, false, kBiasBytes, 2, SA::kCols>;
   constexpr int G = BN / 4;
   static_assert(BN * 4 <= kBiasBytes - 16, "bias tile + the h_ready counter");
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
       auto stage_static = [&](const CUtensorMap* tw, int kb, const CUtensorMap* ta, int frame) {
         mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
         uint8_t* st = s.base + rs.stage * p.stage_bytes;
-        uint8_t* wst = st + PARTS * p.a_tile;
+        uint8_t* wst = st + APARTS * p.a_tile;
         const int kc0 = kb * p.kc_elems;
         if (CTAS == 1 || leader) mbar_arrive_expect_tx(&s.full[rs.stage], CTAS * p.stage_tx);
         load_w<CTAS>(wst, tw, &s.full[rs.stage], kc0, nb0);
@@ -452,7 +461,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
           if (dbg && i == p.num_kx) dbg[1] = clock64();                    // first recurrent stage landed
           tc_fence_after();
           const uint32_t a_hi = smem_u32(s.base + rs.stage * p.stage_bytes);
-          const uint32_t w_hi = a_hi + PARTS * p.a_tile;
+          const uint32_t w_hi = a_hi + APARTS * p.a_tile;
           issue_stage<BN, MODE, CTAS>(a_hi, a_hi + p.a_tile, w_hi, acc, i == 0);
           if (CTAS == 2) umma_commit_2sm(&s.empty[rs.stage], 0x3); else umma_commit(&s.empty[rs.stage]);
           rs.advance(p.stages);
@@ -586,9 +595,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) lstm_fused_kernel(const __gr
 template <int BN, int MODE, int CTAS, bool FUSED>
 static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t stream) {
   auto kern = FUSED ? lstm_fused_kernel<BN, MODE, CTAS> : lstm_step_kernel<BN, MODE, CTAS>;
-  constexpr int kAccCols = SplitAcc<BN, CTAS, MODE == 2>::kCols;
-  using C = std::conditional_t<FUSED, PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, kBiasBytes, 2, kAccCols>,
-                               PipeCfg<BN, CTAS, MODE == 2 ? 2 : 1, false, BN / 32 * kATileBytes, 1, kAccCols>>;
+  constexpr int kAccCols = SplitAcc<BN, CTAS, MODE >= 2>::kCols;
+  using C = std::conditional_t<FUSED, PipeCfg<BN, CTAS, MODE >= 2 ? 2 : 1, false, kBiasBytes, 2, kAccCols>,
+                               PipeCfg<BN, CTAS, MODE >= 2 ? 2 : 1, false, BN / 32 * kATileBytes, 1, kAccCols>>;
   constexpr int kThreads = FUSED ? kFusedThreads : kNumThreads;
   // small batches shrink the stage (a_rows < 128): the same ring memory then holds more, shallower stages, which is what
   // a latency-bound frame wants (a TMA round trip costs ~3 K cycles whatever the tile size)
@@ -674,7 +683,7 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   using namespace avc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(d != nullptr, "avc_lstm_seq: null descriptor");
-  AVC_REQUIRE(d->dtype >= AVC_DTYPE_TF32 && d->dtype <= AVC_DTYPE_BF16X3, "avc_lstm_seq: bad dtype %d", d->dtype);
+  AVC_REQUIRE(d->dtype >= AVC_DTYPE_TF32 && d->dtype <= AVC_DTYPE_F16, "avc_lstm_seq: bad dtype %d", d->dtype);
   AVC_REQUIRE(d->gate_group == 16 || d->gate_group == 32, "avc_lstm_seq: gate_group %d (16 or 32)", d->gate_group);
   AVC_REQUIRE(d->B > 0 && d->T > 0 && d->H > 0 && d->H % d->gate_group == 0, "avc_lstm_seq: bad shape B=%d T=%d H=%d",
               d->B, d->T, d->H);
@@ -686,9 +695,11 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   const int kc = kRowBytes / es;
   AVC_REQUIRE(d->H % kc == 0, "avc_lstm_seq: H=%d must be a multiple of %d", d->H, kc);
   const int bn = 4 * d->gate_group;
-  const bool split = d->dtype == AVC_DTYPE_BF16X3;
+  const bool split = d->dtype == AVC_DTYPE_BF16X3;                      // activations as [hi | lo]
+  const bool w2 = split || d->dtype == AVC_DTYPE_F16;                   // weights as [w_hi | w_lo]
   const uint64_t H = (uint64_t)d->H;
-  const uint64_t ld = split ? 2 * H : H;     // elements per row of hseq and of the packed W_hh ([hi | lo] when split)
+  const uint64_t ld = split ? 2 * H : H;     // elements per row of hseq ([hi | lo] when split)
+  const uint64_t ldw_hh = w2 ? 2 * H : H;    // elements per row of the packed W_hh
   const int m_tiles = (d->B + kBlockM - 1) / kBlockM;
   const int ctas = (m_tiles >= 2 && lstm_cta_group() == 2) ? 2 : 1;
   // A small batch owned by one CTA loads only its real rows (rounded up to 8): the MMA still spans 128 rows, but the
@@ -698,13 +709,13 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
 
   LstmParams p;
   memset(&p, 0, sizeof(p));
-  const uint32_t parts = split ? 2 : 1;
+  const uint32_t parts = split ? 2 : 1, wparts = w2 ? 2 : 1;
   {
     const uint64_t dh[4] = {H, (uint64_t)d->B, parts, (uint64_t)d->T};
     const uint64_t sh[3] = {(uint64_t)d->T * ld * es, H * es, ld * es};
     const uint32_t bh[4] = {(uint32_t)kc, (uint32_t)a_rows, parts, 1};
     if (!encode_tmap_4d(&p.tmap_h, es, d->hseq, dh, sh, bh)) return -3;
-    if (!encode_tmap_3d(&p.tmap_w, es, d->w_hh, H, 4 * H, parts, ld * es, H * es, kc, bn / ctas, parts)) return -3;
+    if (!encode_tmap_3d(&p.tmap_w, es, d->w_hh, H, 4 * H, wparts, ldw_hh * es, H * es, kc, bn / ctas, wparts)) return -3;
   }
   if (fused) {
     // input sequence [B][T][xin_ld] holding xin_channels logical channels ([hi | lo] halves when split); channels past
@@ -714,12 +725,12 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
     AVC_REQUIRE(d->xin_ld >= (long long)(split ? 2 * cin : cin), "avc_lstm_seq: xin_ld=%lld too small", d->xin_ld);
     p.num_kx = (int)((cin + kc - 1) / kc);
     const uint64_t kpad = (uint64_t)p.num_kx * kc;
-    const uint64_t ldw = split ? 2 * kpad : kpad;
+    const uint64_t ldw = w2 ? 2 * kpad : kpad;
     const uint64_t dx[4] = {cin, (uint64_t)d->B, parts, (uint64_t)d->T};
     const uint64_t sx[3] = {(uint64_t)d->T * d->xin_ld * es, cin * es, (uint64_t)d->xin_ld * es};
     const uint32_t bx[4] = {(uint32_t)kc, (uint32_t)a_rows, parts, 1};
     if (!encode_tmap_4d(&p.tmap_xi, es, d->xin, dx, sx, bx)) return -3;
-    if (!encode_tmap_3d(&p.tmap_wi, es, d->w_ih, kpad, 4 * H, parts, ldw * es, kpad * es, kc, bn / ctas, parts)) return -3;
+    if (!encode_tmap_3d(&p.tmap_wi, es, d->w_ih, kpad, 4 * H, wparts, ldw * es, kpad * es, kc, bn / ctas, wparts)) return -3;
     p.bias = d->bias;
   } else {
     if (!encode_tmap_3d(&p.tmap_x, 4, d->xproj, 4 * H, (uint64_t)d->T, (uint64_t)d->B, 4 * H * 4,
@@ -741,7 +752,7 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   p.n_tiles = 4 * d->H / bn;
   p.a_rows = a_rows;
   p.a_tile = a_rows * kRowBytes;
-  p.stage_bytes = (split ? 2 : 1) * (p.a_tile + bn / ctas * kRowBytes);
+  p.stage_bytes = (int)parts * p.a_tile + (int)wparts * (bn / ctas * kRowBytes);
   p.stage_tx = (uint32_t)p.stage_bytes;
 #define AVC_LSTM_DISPATCH3(BN_, MODE_, CTAS_) \
   return fused ? run<BN_, MODE_, CTAS_, true>(p, d, m_tiles, stream) : run<BN_, MODE_, CTAS_, false>(p, d, m_tiles, stream);
@@ -751,6 +762,7 @@ extern "C" int avc_lstm_seq(const avc_lstm_desc* d, void* stream_v) {
   switch (d->dtype) {                                    \
     case AVC_DTYPE_TF32: AVC_LSTM_DISPATCH2(BN_, 0)      \
     case AVC_DTYPE_BF16: AVC_LSTM_DISPATCH2(BN_, 1)      \
+    case AVC_DTYPE_F16: AVC_LSTM_DISPATCH2(BN_, 3)       \
     default: AVC_LSTM_DISPATCH2(BN_, 2)                  \
   }
   switch (bn) {

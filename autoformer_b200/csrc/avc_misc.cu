@@ -11,7 +11,7 @@ namespace avc {
 // ---------------------------------------------------------------------------------------------
 // concat with broadcast: out[b,t,:] = [seq[b, t/div, :C1] || vec[b, :C2]], float4 granularity
 // ---------------------------------------------------------------------------------------------
-template <int MODE>   // 0 fp32 (optionally TF32-rounded), 1 bf16, 2 split bf16 [hi | lo]
+template <int MODE>   // 0 fp32 (optionally TF32-rounded), 1 bf16, 2 split bf16 [hi | lo], 3 fp16
 __global__ void __launch_bounds__(256) concat_bcast_kernel(const float* __restrict__ seq, const float* __restrict__ vec,
                                                            void* __restrict__ out, long long rows, int T, int C1,
                                                            int C2, int div, int round) {
@@ -41,6 +41,9 @@ __global__ void __launch_bounds__(256) concat_bcast_kernel(const float* __restri
     } else if (MODE == 1) {
       uint2 pk = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
       *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + r * (C1 + C2) + c) = pk;
+    } else if (MODE == 3) {
+      uint2 pk = make_uint2(pack_f16(v.x, v.y), pack_f16(v.z, v.w));
+      *reinterpret_cast<uint2*>(static_cast<__half*>(out) + r * (C1 + C2) + c) = pk;
     } else {
       if (round) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
       *reinterpret_cast<float4*>(static_cast<float*>(out) + r * (C1 + C2) + c) = v;
@@ -167,6 +170,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
             base[2 * H] = __float2bfloat16_rn(h[e] - __bfloat162float(hi));
           } else if (out_mode == 1)
             static_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(h[e]);
+          else if (out_mode == 3)
+            static_cast<__half*>(out)[o] = __float2half_rn(h[e]);
           else
             static_cast<float*>(out)[o] = round ? round_tf32(h[e]) : h[e];
         }
@@ -311,7 +316,10 @@ extern "C" int avc_concat_bcast(const float* seq, const float* vec, void* out, i
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  if (out_dtype == 2)
+  AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 3, "avc_concat_bcast: out_dtype %d", out_dtype);
+  if (out_dtype == 3)
+    concat_bcast_kernel<3><<<(int)blocks, 256, 0, stream>>>(seq, vec, out, rows, T, C1, C2, div, 0);
+  else if (out_dtype == 2)
     concat_bcast_kernel<2><<<(int)blocks, 256, 0, stream>>>(seq, vec, out, rows, T, C1, C2, div, 0);
   else if (out_dtype == 1)
     concat_bcast_kernel<1><<<(int)blocks, 256, 0, stream>>>(seq, vec, out, rows, T, C1, C2, div, 0);

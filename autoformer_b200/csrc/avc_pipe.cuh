@@ -150,9 +150,12 @@ struct RingState {
 };
 
 // Four MMAs (32 bytes of K each) over one 128-byte-wide operand pair: D (+)= A[128*CTAS x 128B] . B[BN x 128B]^T.
+// `fmt_xor` = kIdescF16Xor turns the 16-bit operand format from bf16 into fp16 (same instruction, same tiles).
+constexpr uint32_t kIdescF16Xor = (1u << 7) | (1u << 10);
 template <int BN, bool BF16, int CTAS>
-__device__ __forceinline__ void issue_pair(uint32_t a_addr, uint32_t b_addr, uint32_t tmem_acc, bool first) {
-  constexpr uint32_t idesc = umma_idesc(kBlockM * CTAS, BN, !BF16);
+__device__ __forceinline__ void issue_pair(uint32_t a_addr, uint32_t b_addr, uint32_t tmem_acc, bool first,
+                                           uint32_t fmt_xor = 0) {
+  const uint32_t idesc = umma_idesc(kBlockM * CTAS, BN, !BF16) ^ fmt_xor;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
@@ -174,10 +177,11 @@ __device__ __forceinline__ void issue_pair(uint32_t a_addr, uint32_t b_addr, uin
 
 // MMA issue for one k-block that has landed in `stage` of a PARTS = 1 pipeline.
 template <int BN, bool BF16, int CTAS = 1>
-__device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, uint32_t tmem_acc, bool first) {
+__device__ __forceinline__ void issue_kblock(const PipeSmem& s, uint32_t stage, uint32_t tmem_acc, bool first,
+                                             uint32_t fmt_xor = 0) {
   using C = PipeCfg<BN, CTAS>;
   const uint32_t a_addr = smem_u32(s.base + stage * C::kStageBytes);
-  issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, tmem_acc, first);
+  issue_pair<BN, BF16, CTAS>(a_addr, a_addr + kATileBytes, tmem_acc, first, fmt_xor);
 }
 
 // Grid barrier executed by ONE thread per CTA (the TMA producer): everything that must be ordered before it in this CTA
@@ -231,6 +235,10 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 

@@ -1,4 +1,4 @@
-// Element / 4-element stores into the three operand formats (fp32 [TF32-rounded], bf16, split bf16 [hi | lo]).
+// Element / 4-element stores into the operand formats: 0 fp32 [TF32-rounded], 1 bf16, 2 split bf16 [hi | lo], 3 fp16.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -16,6 +16,8 @@ __device__ __forceinline__ void store_op1(void* out, int mode, int round, long l
     p[C] = __float2bfloat16_rn(v - __bfloat162float(hi));
   } else if (mode == 1) {
     static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
+  } else if (mode == 3) {
+    static_cast<__half*>(out)[row * ld + c] = __float2half_rn(v);
   } else {
     static_cast<float*>(out)[row * ld + c] = round ? round_tf32(v) : v;
   }
@@ -35,6 +37,9 @@ __device__ __forceinline__ void store_op4(void* out, int mode, int round, long l
   } else if (mode == 1) {
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + row * ld + c) =
         make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  } else if (mode == 3) {
+    *reinterpret_cast<uint2*>(static_cast<__half*>(out) + row * ld + c) =
+        make_uint2(pack_f16(v.x, v.y), pack_f16(v.z, v.w));
   } else {
     if (round) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
     *reinterpret_cast<float4*>(static_cast<float*>(out) + row * ld + c) = v;

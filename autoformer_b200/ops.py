@@ -69,12 +69,20 @@ def _require_cuda(*tensors):
 
 
 def _dt(precision):
-    return {"tf32": _lib.DTYPE_TF32, "bf16": _lib.DTYPE_BF16, "fp32": 2}[precision]
+    return {"tf32": _lib.DTYPE_TF32, "bf16": _lib.DTYPE_BF16, "fp32": 2, "fp16x2": 3}[precision]
 
 
 def alloc_act(B, rows, C, precision, device):
     """Activation buffer carrying C logical channels in the storage format of `precision`."""
     return torch.empty(B, rows, packing.act_channels(C, precision), dtype=TORCH_DTYPE[precision], device=device)
+
+
+def _out_dtype(t, split):
+    """C-ABI out_dtype code of an operand-format output buffer: 0 fp32, 1 bf16, 2 split bf16, 3 fp16."""
+    assert t.dtype in (torch.float32, torch.bfloat16, torch.float16)
+    if t.dtype == torch.float16:
+        return 3
+    return (2 if split else 1) if t.dtype == torch.bfloat16 else 0
 
 
 class ConvGemm:
@@ -87,13 +95,13 @@ class ConvGemm:
         self.w, self.bias, self.meta = w, bias, meta
         self.tag = tag
         # algorithmic MACs per output row: real channels x taps x real output channels
-        if meta.get("split"):
+        if meta.get("split") or meta.get("dup"):
             self.macs_per_row = sum(c * k for c, k in zip(meta["logical_channels"], meta["logical_taps"])) * meta["N"]
         else:
             self.macs_per_row = sum(c * k for c, k in zip(meta["channels"], meta["taps"])) * meta["N"]
         n_src = len(meta["taps"])
         # tap geometry is given per LOGICAL source; split precision duplicates it for the two physical sources
-        rep = 2 if meta.get("split") else 1
+        rep = 2 if (meta.get("split") or meta.get("dup")) else 1
         if tap_t0 is not None:
             self.tap_t0 = [v for v in tap_t0 for _ in range(rep)]
         else:
@@ -127,6 +135,9 @@ class ConvGemm:
                 assert a.shape[2] == 2 * c, (a.shape, c)
                 phys += [a, a[:, :, :c]]
             srcs = phys
+        elif meta.get("dup"):     # fp16x2: the same buffer against w_hi and against w_lo
+            assert len(srcs) == len(meta["logical_channels"])
+            srcs = [a for a in srcs for _ in range(2)]
         assert len(srcs) == len(meta["taps"])
         d = _lib.GemmDesc()
         want = TORCH_DTYPE[self.precision]
@@ -143,7 +154,7 @@ class ConvGemm:
             d.a_tap_dt[s] = self.tap_dt[s]
         d.w_ptr = self.w.data_ptr()
         d.n_pad, d.k_pad = meta["n_pad"], meta["k_pad"]
-        d.dtype = _lib.DTYPE_TF32 if self.precision == "tf32" else _lib.DTYPE_BF16
+        d.dtype = {"tf32": _lib.DTYPE_TF32, "fp16x2": _lib.DTYPE_F16}.get(self.precision, _lib.DTYPE_BF16)
         d.B, d.T, d.N = B, T, meta["N"]
         d.bias = self.bias.data_ptr()
         d.act = self.act
@@ -157,8 +168,7 @@ class ConvGemm:
             d.out_ld = out.stride(1)
             d.out_rows_per_utt = out.shape[1]
             d.out_row0 = out_row0
-            d.out_dtype = (2 if split else 1) if out.dtype == torch.bfloat16 else 0
-            assert out.dtype in (torch.float32, torch.bfloat16)
+            d.out_dtype = _out_dtype(out, split)
             d.out_round_tf32 = 1 if (round_tf32 and out.dtype == torch.float32) else 0
             d.out_reflect = reflect
         if out_raw is not None:
@@ -167,7 +177,7 @@ class ConvGemm:
             assert out is None or out.dtype == out_raw.dtype
             d.out_raw = out_raw.data_ptr()
             d.out_raw_ld = out_raw.stride(-2)
-            d.out_dtype = (2 if split else 1) if out_raw.dtype == torch.bfloat16 else 0
+            d.out_dtype = _out_dtype(out_raw, split)
             d.out_round_tf32 = 1 if (round_tf32 and out_raw.dtype == torch.float32) else 0
         if out2 is not None:
             assert out2.is_cuda and out2.dtype == torch.float32 and out2.stride(-1) == 1
@@ -234,12 +244,12 @@ def lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h
         assert xin.shape[2] >= packing.act_channels(c_in, precision) and xin.stride(2) == 1
         assert xin.stride(0) == T * xin.stride(1) and c_in % 8 == 0
         assert w_ih.dtype == TORCH_DTYPE[precision] and w_ih.is_contiguous()
-        assert w_ih.shape == (4 * H, 2 * kp if precision == "fp32" else kp), (w_ih.shape, kp)
+        assert w_ih.shape == (4 * H, 2 * kp if precision in packing.TWO_TERM_WEIGHTS else kp), (w_ih.shape, kp)
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == 4 * H
         _require_cuda(w_ih, bias)
     else:
         assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
-    wk = 2 * H if precision == "fp32" else H
+    wk = 2 * H if precision in packing.TWO_TERM_WEIGHTS else H
     assert w_hh.dtype == TORCH_DTYPE[precision] and w_hh.shape == (4 * H, wk) and w_hh.is_contiguous()
     if hseq is None:
         hseq = alloc_act(B, T, H, precision, dev)
@@ -348,7 +358,7 @@ def bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=
     out_ptr, out_dtype = None, 0
     if out is not None:
         assert out.is_contiguous() and out.shape == (B, T, (4 if split else 2) * H)
-        out_ptr, out_dtype = out.data_ptr(), ((2 if split else 1) if out.dtype == torch.bfloat16 else 0)
+        out_ptr, out_dtype = out.data_ptr(), _out_dtype(out, split)
     codes_ptr = None
     if codes is not None:
         assert codes.is_contiguous() and codes.dtype == torch.float32 and codes.shape == (B, T // freq, 2 * H)

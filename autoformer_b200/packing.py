@@ -12,10 +12,14 @@ Everything here happens once per ``load_state_dict`` (not per forward):
 import torch
 
 # precision modes: "tf32" (fp32 storage, one TF32 pass), "bf16" (one bf16 pass),
-# "fp32" (split bf16: hi + lo channels, three bf16 products per fp32 product -- fp32-grade accuracy)
-KC = {"tf32": 32, "bf16": 64, "fp32": 64}
-TORCH_DTYPE = {"tf32": torch.float32, "bf16": torch.bfloat16, "fp32": torch.bfloat16}
-PRECISIONS = tuple(KC)
+# "fp32" (split bf16: hi + lo channels, three bf16 products per fp32 product -- fp32-grade accuracy),
+# "fp16x2" (fp16 activations, every weight as two fp16 terms w_hi + w_lo: two fp16 products per fp32 product; the
+# only rounding is the 2^-12 of the activations -- ~3e-4 end to end on AutoVC, scripts/precision_study.py)
+KC = {"tf32": 32, "bf16": 64, "fp32": 64, "fp16x2": 64, "f16": 64}      # "f16": single fp16 operand (internal)
+TORCH_DTYPE = {"tf32": torch.float32, "bf16": torch.bfloat16, "fp32": torch.bfloat16, "fp16x2": torch.float16,
+               "f16": torch.float16}
+TWO_TERM_WEIGHTS = ("fp32", "fp16x2")     # precisions whose packed LSTM weights are [w_hi | w_lo]
+PRECISIONS = ("tf32", "bf16", "fp32", "fp16x2")
 
 
 def act_channels(c: int, precision: str) -> int:
@@ -31,12 +35,26 @@ def split_bf16(t: torch.Tensor):
     return hi, lo
 
 
+def split_f16(t: torch.Tensor):
+    """v -> (hi, lo) fp16 with v ~ hi + lo to ~2^-22 relative (|v| well inside the fp16 range: weights)."""
+    t = t.float()
+    hi = t.to(torch.float16)
+    lo = (t - hi.float()).to(torch.float16)
+    return hi, lo
+
+
+def split_terms(t: torch.Tensor, precision: str):
+    return split_bf16(t) if precision == "fp32" else split_f16(t)
+
+
 def to_act(t: torch.Tensor, precision: str) -> torch.Tensor:
     """fp32 channels-last activation -> the buffer format of `precision` (tests / host-side staging)."""
     if precision == "tf32":
         return round_tf32(t.float())
     if precision == "bf16":
         return t.to(torch.bfloat16)
+    if precision in ("fp16x2", "f16"):
+        return t.to(torch.float16)
     hi, lo = split_bf16(t)
     return torch.cat([hi, lo], dim=-1).contiguous()
 
@@ -62,7 +80,9 @@ def to_operand(t: torch.Tensor, precision: str) -> torch.Tensor:
         return round_tf32(t.float())
     if precision == "bf16":
         return t.to(torch.bfloat16)
-    raise ValueError("split precision has no single-tensor operand form")
+    if precision == "f16":
+        return t.to(torch.float16)
+    raise ValueError("two-term precisions have no single-tensor operand form")
 
 
 def _ceil_to(x, m):
@@ -102,6 +122,17 @@ def pack_conv_sources(weights, bias, precision, block_n=None):
             phys += [torch.cat([hi, hi], dim=1).float(), lo.float()]
         w_p, b_p, meta = pack_conv_sources(phys, bias, "bf16", block_n)
         meta.update(precision="fp32", split=True, logical_channels=[w.shape[1] for w in weights],
+                    logical_taps=[w.shape[2] for w in weights])
+        return w_p, b_p, meta
+    if precision == "fp16x2":
+        # a*w = a*w_hi + a*w_lo: each logical source becomes two physical ones over the SAME channels
+        assert len(weights) <= 2, "at most two logical sources (four physical sources)"
+        phys = []
+        for w in weights:
+            hi, lo = split_f16(w)
+            phys += [hi.float(), lo.float()]
+        w_p, b_p, meta = pack_conv_sources(phys, bias, "f16", block_n)
+        meta.update(precision="fp16x2", dup=True, logical_channels=[w.shape[1] for w in weights],
                     logical_taps=[w.shape[2] for w in weights])
         return w_p, b_p, meta
     bn_tile = block_n or choose_block_n(n)
@@ -193,8 +224,8 @@ def pack_lstm_ih_fused(w_ih, b_ih, b_hh, precision, group):
     w = torch.zeros(4 * h, kpad, dtype=torch.float32, device=w_ih.device)
     w[:, :c_in] = w_ih[perm].float()
     bias = (b_ih.float() + b_hh.float())[perm].contiguous()
-    if precision == "fp32":
-        hi, lo = split_bf16(w)
+    if precision in TWO_TERM_WEIGHTS:
+        hi, lo = split_terms(w, precision)
         return torch.cat([hi, lo], dim=1).contiguous(), bias
     return to_operand(w, precision).contiguous(), bias
 
@@ -203,9 +234,10 @@ def pack_lstm_hh(w_hh, precision, group):
     h = w_hh.shape[1]
     perm = gate_permutation(h, group, w_hh.device)
     w = w_hh[perm].float()
-    if precision == "fp32":
-        hi, lo = split_bf16(w)
-        return torch.cat([hi, lo], dim=1).contiguous()          # [w_hi | w_lo]; the kernel forms hi*hi + lo*hi + hi*lo
+    if precision in TWO_TERM_WEIGHTS:
+        hi, lo = split_terms(w, precision)
+        # [w_hi | w_lo]; "fp32": the kernel forms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, "fp16x2": a*w_hi + a*w_lo
+        return torch.cat([hi, lo], dim=1).contiguous()
     return to_operand(w, precision).contiguous()
 
 

@@ -33,6 +33,11 @@ extern "C" {
 #define AVC_DTYPE_TF32 0
 #define AVC_DTYPE_BF16 1
 #define AVC_DTYPE_BF16X3 2
+#define AVC_DTYPE_F16 3 /* fp16 storage and operands, fp32 accumulate.  "fp16x2" precision: activations are single
+                           fp16 values (2^-12 relative), every weight is two fp16 terms w_hi + w_lo (exact to ~2^-22), and a
+                           product is a*w_hi + a*w_lo -- two MMA passes instead of the three of dtype 2, end-to-end
+                           error ~3e-4 on AutoVC (scripts/precision_study.py).  avc_conv_gemm: two sources over the
+                           same buffer against [w_hi | w_lo]; avc_lstm_seq: w = [w_hi | w_lo] like dtype 2. */
 
 #define AVC_ACT_NONE 0
 #define AVC_ACT_RELU 1
@@ -79,7 +84,7 @@ typedef struct avc_gemm_desc {
   int a_tap_dt[AVC_MAX_SOURCES];        /* row step between taps (dilation) */
   const void* w_ptr;         /* packed weights */
   int n_pad, k_pad;
-  int dtype;                 /* AVC_DTYPE_TF32 or AVC_DTYPE_BF16 (operand type of A and W) */
+  int dtype;                 /* AVC_DTYPE_TF32, AVC_DTYPE_BF16 or AVC_DTYPE_F16 (operand type of A and W) */
   int B, T;                  /* GEMM row space: B utterances x T frames */
   int N;                     /* real output columns (multiple of 4) */
   const float* bias;         /* [n_pad] fp32 */
@@ -88,7 +93,7 @@ typedef struct avc_gemm_desc {
   void* out;                 /* act(v): [B][out_rows_per_utt][out_ld], written at row out_row0 + time */
   long long out_ld;
   int out_rows_per_utt, out_row0;
-  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column c, lo at column Cs + c (out_ld >= 2Cs) */
+  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column c, lo at column Cs + c (out_ld >= 2Cs), 3 = fp16 */
   int out_round_tf32;        /* round fp32 outputs to TF32 (rna) so the next GEMM reads them exactly */
   int out_reflect;           /* also write `out_reflect` reflected halo rows each side (ReflectionPad1d,
                                 melgan/modules.py:77,96,121); needs out_row0 >= out_reflect */

@@ -71,6 +71,8 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
             assert a.shape[2] == 2 * c
             phys += [a, a[:, :, :c]]
         srcs = phys
+    elif meta.get("dup"):      # fp16x2: the same buffer against w_hi and against w_lo
+        srcs = [a for a in srcs for _ in range(2)]
     for a, c in zip(srcs, meta["channels"]):
         assert a.shape[2] == c and a.dtype == packing.TORCH_DTYPE[prec]
     v = emulate_conv_gemm(self.w, self.bias, meta, srcs, B, T, self.tap_t0, self.tap_dt)
@@ -100,7 +102,8 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
 
 def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=None, h_last=None, persistent=False,
                   xin=None, w_ih=None, bias=None, c_in=None):
-    if precision == "fp32":
+    two = precision in packing.TWO_TERM_WEIGHTS
+    if two:
         w = w_hh[:, :H].double() + w_hh[:, H:].double()
     else:
         w = w_hh.double()
@@ -108,8 +111,8 @@ def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=No
         assert xproj is None
         kc = KC[precision]
         kp = (c_in + kc - 1) // kc * kc
-        assert w_ih.shape == (4 * H, 2 * kp if precision == "fp32" else kp) and bias.shape == (4 * H,)
-        wi = (w_ih[:, :kp].double() + w_ih[:, kp:].double()) if precision == "fp32" else w_ih.double()
+        assert w_ih.shape == (4 * H, 2 * kp if two else kp) and bias.shape == (4 * H,)
+        wi = (w_ih[:, :kp].double() + w_ih[:, kp:].double()) if two else w_ih.double()
         assert float(wi[:, c_in:].abs().max()) == 0.0 if kp > c_in else True
         assert xin.shape[:2] == (B, T) and xin.dtype == packing.TORCH_DTYPE[precision]
         xa = packing.act_to_float(xin[..., :packing.act_channels(c_in, precision)], precision).double()

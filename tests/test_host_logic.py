@@ -22,7 +22,7 @@ def cpu_kernels(monkeypatch):
     install_cpu_kernels(monkeypatch)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 2e-2), ("fp16x2", 1e-3)])
 def test_autovc_host_logic(cpu_kernels, precision, tol):
     from autoformer_b200.factory.AutoVC import AutoVC
     args = (32, 256, 512, 32)
