@@ -69,8 +69,8 @@ class AutoVC(nn.Module):
     """AutoVC generator (Qian et al. 2019) -- B200 kernels behind the reference API (factory/AutoVC.py:182-211).
 
     Extra, optional attributes (not in the reference): ``precision`` ("fp32" default: split-bf16
-    three-product tensor-core arithmetic, ~3e-5 from the fp32 reference | "tf32": one TF32 pass, ~1e-3 |
-    "bf16": one bf16 pass, ~1e-2),
+    three-product tensor-core arithmetic, ~3e-5 from the fp32 reference | "fp16x2": fp16 activations x two-term
+    fp16 weights, two products, ~4e-4, 1.45x faster | "tf32": one TF32 pass, ~1e-3 | "bf16": one bf16 pass, ~1e-2),
     ``persistent_lstm`` (one cooperative launch per LSTM layer instead of one launch per frame),
     ``collect_taps`` (keep fp32 copies of every stage in ``self.taps`` for parity tests)."""
 
