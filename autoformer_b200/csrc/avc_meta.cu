@@ -352,7 +352,7 @@ extern "C" int avc_gn_pool_residual(const float* x, const float* stats, const fl
                                     void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(x && stats && gamma && (out_f32 || out_op), "avc_gn_pool_residual: null buffer");
-  AVC_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 2, "avc_gn_pool_residual: bad shape");
+  AVC_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 3, "avc_gn_pool_residual: bad shape");
   const long long total4 = (long long)B * L * (C / 4);
   gn_pool_kernel<<<grid_for(total4), 256, 0, stream>>>(x, stats, gamma, out_f32, out_op, out_dtype, out_round_tf32,
                                                        total4, L, C);
@@ -365,7 +365,7 @@ extern "C" int avc_gn_apply(const float* x, const float* stats, const float* gam
                             int out_dtype, int out_round_tf32, int B, int L, int C, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(x && stats && gamma && beta && out_op, "avc_gn_apply: null buffer");
-  AVC_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 2, "avc_gn_apply: bad shape");
+  AVC_REQUIRE(B > 0 && L > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 3, "avc_gn_apply: bad shape");
   const long long total4 = (long long)B * L * (C / 4);
   gn_apply_kernel<<<grid_for(total4), 256, 0, stream>>>(x, stats, gamma, beta, out_op, out_dtype, out_round_tf32,
                                                         total4, L, C);
@@ -379,7 +379,7 @@ extern "C" int avc_patchify(const float* a, const float* stats, const float* gam
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(a && out_op, "avc_patchify: null buffer");
   AVC_REQUIRE(B > 0 && S > 0 && p > 0 && S % p == 0 && S % 4 == 0 && (p * p) % 8 == 0 && out_dtype >= 0 &&
-                  out_dtype <= 2 && (!stats || (gamma && beta)),
+                  out_dtype <= 3 && (!stats || (gamma && beta)),
               "avc_patchify: bad arguments S=%d p=%d", S, p);
   const long long total4 = (long long)B * S * (S / 4);
   patchify_kernel<<<grid_for(total4), 256, 0, stream>>>(a, stats, gamma, beta, out_op, out_dtype, out_round_tf32,
@@ -394,7 +394,7 @@ extern "C" int avc_ln_transpose(const float* x, const float* gamma, const float*
                                 void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(x && (out_op || out_f32), "avc_ln_transpose: null buffer");
-  AVC_REQUIRE(B > 0 && B < 65536 && R > 0 && C > 0 && ln_axis >= 0 && ln_axis <= 2 && out_dtype >= 0 && out_dtype <= 2,
+  AVC_REQUIRE(B > 0 && B < 65536 && R > 0 && C > 0 && ln_axis >= 0 && ln_axis <= 2 && out_dtype >= 0 && out_dtype <= 3,
               "avc_ln_transpose: bad arguments");
   if (ln_axis) AVC_REQUIRE(gamma && beta && scratch, "avc_ln_transpose: LayerNorm needs gamma, beta and scratch");
   const int R_pad = (R + 7) / 8 * 8;
@@ -419,7 +419,7 @@ extern "C" int avc_meta_decoder_input(const float* codes, const float* c_trg, vo
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(codes && c_trg && out_op, "avc_meta_decoder_input: null buffer");
   AVC_REQUIRE(B > 0 && T > 0 && freq > 0 && T % freq == 0 && T % 8 == 0 && H2 > 0 && E > 0 && out_dtype >= 0 &&
-                  out_dtype <= 2,
+                  out_dtype <= 3,
               "avc_meta_decoder_input: bad shape");
   const long long total = (long long)B * (H2 + E) * T;
   meta_decoder_input_kernel<<<grid_for(total), 256, 0, stream>>>(codes, c_trg, out_op, out_dtype, out_round_tf32,
@@ -456,7 +456,7 @@ extern "C" int avc_adain(const float* x, const float* x_stats, const float* t_st
                          int out_dtype, int out_round_tf32, long long rows, int C, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(x && x_stats && t_stats && (out_f32 || out_op), "avc_adain: null buffer");
-  AVC_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 2, "avc_adain: bad shape");
+  AVC_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && out_dtype >= 0 && out_dtype <= 3, "avc_adain: bad shape");
   const long long total4 = rows * (C / 4);
   adain_kernel<<<grid_for(total4), 256, 0, stream>>>(x, x_stats, t_stats, out_f32, out_op, out_dtype, out_round_tf32,
                                                      total4, C);

@@ -234,6 +234,8 @@ __device__ __forceinline__ void store1(void* out, int mode, int round, long long
     p[C] = __float2bfloat16_rn(v - __bfloat162float(hi));
   } else if (mode == 1) {
     static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
+  } else if (mode == 3) {
+    static_cast<__half*>(out)[row * ld + c] = __float2half_rn(v);
   } else {
     static_cast<float*>(out)[row * ld + c] = round ? round_tf32(v) : v;
   }
@@ -379,7 +381,7 @@ extern "C" int avc_transpose_pad(const float* in, void* out, int B, int C, int L
   AVC_REQUIRE(in && out, "avc_transpose_pad: null buffer");
   AVC_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && L > pad && pad >= 0 && B < 65536, "avc_transpose_pad: bad shape B=%d C=%d L=%d pad=%d",
               B, C, L, pad);
-  AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 2, "avc_transpose_pad: out_dtype %d", out_dtype);
+  AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 3, "avc_transpose_pad: out_dtype %d", out_dtype);
   dim3 grid((L + 31) / 32, (C + 31) / 32, B);
   transpose_pad_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, C, L, pad, out_dtype, out_round_tf32);
   AVC_CHECK_CUDA(cudaGetLastError());
@@ -450,7 +452,7 @@ extern "C" int avc_audio_frames(const float* audio, void* out, int B, long long 
   using namespace avc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(audio && out, "avc_audio_frames: null buffer");
-  AVC_REQUIRE(B > 0 && L > pad && pad >= 0 && hop > 0 && hop % 8 == 0 && rows > 0 && out_dtype >= 0 && out_dtype <= 2,
+  AVC_REQUIRE(B > 0 && L > pad && pad >= 0 && hop > 0 && hop % 8 == 0 && rows > 0 && out_dtype >= 0 && out_dtype <= 3,
               "avc_audio_frames: bad shape B=%d L=%lld pad=%d hop=%d rows=%d", B, L, pad, hop, rows);
   const long long total4 = (long long)B * rows * (hop / 4);
   audio_frames_kernel<<<ew_grid(total4), 256, 0, stream>>>(audio, out, L, pad, hop, rows, out_dtype, out_round_tf32,
@@ -465,7 +467,7 @@ extern "C" int avc_complex_mag(const float* spec, void* mag, long long rows, int
   using namespace avc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(spec && mag, "avc_complex_mag: null buffer");
-  AVC_REQUIRE(rows > 0 && bins > 0 && bins_pad >= bins && bins_pad % 8 == 0 && out_dtype >= 0 && out_dtype <= 2,
+  AVC_REQUIRE(rows > 0 && bins > 0 && bins_pad >= bins && bins_pad % 8 == 0 && out_dtype >= 0 && out_dtype <= 3,
               "avc_complex_mag: bad shape rows=%lld bins=%d bins_pad=%d", rows, bins, bins_pad);
   const long long total4 = rows * (bins_pad / 4);
   complex_mag_kernel<<<ew_grid(total4), 256, 0, stream>>>(spec, mag, bins, bins_pad, out_dtype, out_round_tf32, total4);

@@ -262,7 +262,7 @@ def test_state_dict_roundtrip_and_repack_on_reload():
 
 
 # ------------------------------------------------------------------------------------------------ LstmDV / MelGAN / pipeline
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 2e-2), ("fp16x2", 5e-4)])
 def test_lstmdv_parity_and_golden(precision, tol):
     from autoformer_b200.factory.LstmDV import LstmDV
     from oracle.lstmdv import lstmdv_forward
@@ -283,7 +283,7 @@ def test_lstmdv_parity_and_golden(precision, tol):
     assert rel_l2(e_step, e) < 1e-5 if precision == "fp32" else torch.equal(e_step, e)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 5e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 5e-3), ("bf16", 5e-2), ("fp16x2", 2e-3)])
 @pytest.mark.parametrize("name", ["melgan_b1_t40", "melgan_b2_t17"])
 def test_melgan_parity_and_golden(precision, tol, name):
     import warnings
@@ -303,8 +303,11 @@ def test_melgan_parity_and_golden(precision, tol, name):
     gen.collect_taps = True
     wav = gen(mel.cuda())
     assert wav.shape == (B, 1, 256 * T)
+    # fp16x2 on MelGAN: waveform 5e-4 ... 1e-3 depending on the weights (pre-tanh stage 3 up to 1.5e-3) -- it does not
+    # keep a margin inside the 1e-3 gate there, which is why MelGAN's default stays the split format; stated separately
+    stage_tol = tol * (1.5 if precision == "fp16x2" else 1.0)
     for k in ("up0", "stage0", "up1", "stage1", "up2", "stage2", "up3", "stage3"):
-        assert rel_l2(gen.taps[k], rt[k].transpose(1, 2)) < tol, k
+        assert rel_l2(gen.taps[k], rt[k].transpose(1, 2)) < stage_tol, k
     assert rel_l2(wav, ref) < tol
     assert rel_l2(wav, torch.from_numpy(g["wav"])) < tol               # the unmodified reference's waveform
     if precision == "fp32":
@@ -444,7 +447,7 @@ def test_meta_glue_kernels_match_cpu_standins():
 
 
 @pytest.mark.parametrize("kind,name", [("pool", "metapool_b1_t176"), ("conv", "metaconv_b1_t176")])
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 5e-2), ("fp16x2", 1.5e-3)])
 def test_meta_parity_and_golden(kind, name, precision, tol):
     """BASELINE config 3 at test size: MetaPool / MetaConv (44,256,512,22), T=176, fp32-grade vs bf16 tolerance."""
     from autoformer_b200.factory.MetaConv import MetaConv
