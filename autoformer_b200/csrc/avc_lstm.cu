@@ -13,7 +13,9 @@
 //     three products hi*hi, lo*hi, hi*lo from them (4 tiles instead of the 6 a K-concatenated GEMM would load);
 //   * the W_hi and W_lo tiles of a stage are adjacent, so a_hi * [W_hi | W_lo] is ONE MMA of width 2 * BN into a
 //     2 * BN-column accumulator (the a_hi tile is read once for both products) and a_lo * W_hi a second MMA of width BN
-//     onto columns of the same gates; the cell warps add the two column blocks (SplitAcc below).
+//     onto columns of the same gates; the cell warps add the two column blocks (SplitAcc below);
+//   * "fp16x2" mode (fp16 activations, two-term fp16 weights) keeps only the wide MMA: {a, W_hi, W_lo} per stage, one
+//     activation tile instead of two -- 9.6 K instead of 13.1 K cycles per frame for the H = 1024 recurrent part.
 //
 // Two kernels:
 //   lstm_fused_kernel  (default) input projection and recurrence in one kernel, two TMEM accumulators: the x_t products

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
           } else if (out_mode == 1)
             static_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(h[e]);
           else if (out_mode == 3)
-            static_cast<__half*>(out)[o] = __float2half_rn(h[e]);
+            static_cast<__half*>(out)[o] = __float2half_rn(sat_f16(h[e]));
           else
             static_cast<float*>(out)[o] = round ? round_tf32(h[e]) : h[e];
         }
@@ -235,7 +235,7 @@ __device__ __forceinline__ void store1(void* out, int mode, int round, long long
   } else if (mode == 1) {
     static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
   } else if (mode == 3) {
-    static_cast<__half*>(out)[row * ld + c] = __float2half_rn(v);
+    static_cast<__half*>(out)[row * ld + c] = __float2half_rn(sat_f16(v));
   } else {
     static_cast<float*>(out)[row * ld + c] = round ? round_tf32(v) : v;
   }

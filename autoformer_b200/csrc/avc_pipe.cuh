@@ -237,8 +237,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// fp16 stores saturate at +-65504 instead of producing inf (an out-of-range activation then costs accuracy, not a
+// NaN-poisoned utterance; values on this path are O(1..100))
+__device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
+  __half2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
   return *reinterpret_cast<uint32_t*>(&v);
 }
 

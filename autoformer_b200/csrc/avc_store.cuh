@@ -17,7 +17,7 @@ __device__ __forceinline__ void store_op1(void* out, int mode, int round, long l
   } else if (mode == 1) {
     static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
   } else if (mode == 3) {
-    static_cast<__half*>(out)[row * ld + c] = __float2half_rn(v);
+    static_cast<__half*>(out)[row * ld + c] = __float2half_rn(sat_f16(v));
   } else {
     static_cast<float*>(out)[row * ld + c] = round ? round_tf32(v) : v;
   }

@@ -34,12 +34,22 @@ def frames_cost(T, n):
     return float(T * n)
 
 
-def autovc_cost(T, n):
-    """Measured cost model of one AutoVC conversion batch on a B200 (default precision), in microseconds: the LSTM
-    layers run one tile row per frame whatever the batch size up to 512 (47.5 us per frame, profiles/r01_bench_final_1gpu:
-    6.08 ms / 128 frames), everything else scales with utterances x frames (3.9 ms / 65,536).  A 212-utterance tail batch
-    therefore costs 77 % of a full one for 41 % of its frames, which a frames-only balance does not see."""
-    return float(T) * (47.5 + 0.0596 * n)
+# per precision: (microseconds per frame of the LSTM layers, microseconds per utterance-frame of everything else)
+_AUTOVC_COST = {"fp32": (47.5, 0.0596), "fp16x2": (29.8, 0.0421)}
+
+
+def autovc_cost(T, n, precision="fp32"):
+    """Measured cost model of one AutoVC conversion batch on a B200, in microseconds: the LSTM layers run one tile row
+    per frame whatever the batch size up to 512 (split format: 47.5 us per frame, profiles/r01_bench_final_1gpu:
+    6.08 ms / 128 frames; fp16x2: 29.8 us, profiles/r01_bench_fp16x2_1gpu: 3.82 ms / 128), everything else scales with
+    utterances x frames (3.9 ms resp. 2.76 ms / 65,536).  A 212-utterance tail batch therefore costs 77 % of a full
+    one for 41 % of its frames, which a frames-only balance does not see."""
+    per_frame, per_utt_frame = _AUTOVC_COST.get(precision, _AUTOVC_COST["fp32"])
+    return float(T) * (per_frame + per_utt_frame * n)
+
+
+def autovc_cost_for(precision):
+    return lambda T, n: autovc_cost(T, n, precision)
 
 
 def assign_batches(batches, world_size, cost=frames_cost):

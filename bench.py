@@ -450,7 +450,7 @@ def run_sweep(args):
     model.persistent_lstm = args.lstm != "per-step"
     rng = random.Random(1234)
     lengths = [rng.choice(range(128, 1025, 32)) for _ in range(args.utterances)]
-    mine = sharding.plan(lengths, world, args.batch, cost=sharding.autovc_cost)[rank]
+    mine = sharding.plan(lengths, world, args.batch, cost=sharding.autovc_cost_for(args.precision))[rank]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = {}
 
