@@ -256,42 +256,103 @@ __global__ void __launch_bounds__(256) ln_col_stats_kernel(const float* __restri
   stats[2 * ((long long)b * C + c) + 1] = rsqrtf(var + eps);
 }
 
-// x [B][R][C] -> out [B][C][R_pad] (transposed), optional normalisation; 32x32 tiles through shared memory.
+// x [B][R][C] -> out [B][C][R_pad] (transposed), optional normalisation.  64 x 64 tiles through shared memory: the
+// loads are float4 along C (a warp covers two 256-byte row segments), the stores are 8 consecutive r per thread --
+// one 16-byte store per 16-bit operand row (two for the split format, two float4 for fp32 / the raw fp32 copy).
+constexpr int kLnTile = 64;
 __global__ void __launch_bounds__(256) ln_transpose_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, int ln_axis,
                                                            void* __restrict__ out_op, int mode, int round,
                                                            float* __restrict__ out_f32, int R, int C, int R_pad) {
-  __shared__ float raw[32][33];
-  __shared__ float nrm[32][33];
+  __shared__ float raw[kLnTile][kLnTile + 1];
+  __shared__ float nrm[kLnTile][kLnTile + 1];
   const int b = blockIdx.z;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int r0 = blockIdx.y * kLnTile, c0 = blockIdx.x * kLnTile;
   const float* xb = x + (long long)b * R * C;
-  for (int i = threadIdx.y; i < 32; i += 8) {            // coalesced along C
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    float v = 0.f, n = 0.f;
-    if (r < R && c < C) {
-      v = __ldg(xb + (long long)r * C + c);
-      n = v;
-      if (ln_axis == 1) {
-        const float* st = stats + 2 * ((long long)b * R + r);
-        n = (v - st[0]) * st[1] * __ldg(gamma + c) + __ldg(beta + c);
-      } else if (ln_axis == 2) {
-        const float* st = stats + 2 * ((long long)b * C + c);
-        n = (v - st[0]) * st[1] * __ldg(gamma + r) + __ldg(beta + r);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool vec = (C & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < kLnTile / 16; ++i) {                 // coalesced along C
+    const int lr = ty + 16 * i, r = r0 + lr, c = c0 + 4 * tx;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      if (vec && c + 3 < C) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(xb + (long long)r * C + c));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < C) v[e] = __ldg(xb + (long long)r * C + c + e);
       }
     }
-    raw[i][threadIdx.x] = v;
-    nrm[i][threadIdx.x] = n;
+    float rm = 0.f, rs = 0.f;
+    if (ln_axis == 1 && r < R) {
+      const float* st = stats + 2 * ((long long)b * R + r);
+      rm = st[0];
+      rs = st[1];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float n = v[e];
+      if (r < R && c + e < C) {
+        if (ln_axis == 1) {
+          n = (v[e] - rm) * rs * __ldg(gamma + c + e) + __ldg(beta + c + e);
+        } else if (ln_axis == 2) {
+          const float* st = stats + 2 * ((long long)b * C + c + e);
+          n = (v[e] - st[0]) * st[1] * __ldg(gamma + r) + __ldg(beta + r);
+        }
+      }
+      raw[lr][4 * tx + e] = v[e];
+      nrm[lr][4 * tx + e] = n;
+    }
   }
   __syncthreads();
   const long long ld = op_ld(R_pad, mode);
-  for (int i = threadIdx.y; i < 32; i += 8) {            // coalesced along R (the output's contiguous axis)
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < R_pad) {                              // columns r in [R, R_pad) are written as zeros
-      const long long orow = (long long)b * C + c;
-      if (out_op) store_op1(out_op, mode, round, orow, ld, r, R_pad, nrm[threadIdx.x][i]);
-      if (out_f32) out_f32[orow * R_pad + r] = raw[threadIdx.x][i];
+  const int rg = threadIdx.x & 7;                          // group of 8 consecutive r (R_pad is a multiple of 8)
+  const int r = r0 + 8 * rg;
+  if (r >= R_pad) return;                                  // columns r in [R, R_pad) are written as zeros
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int lc = (threadIdx.x >> 3) + 32 * i, c = c0 + lc;
+    if (c >= C) continue;
+    const long long orow = (long long)b * C + c;
+    float n[8], w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      n[j] = nrm[8 * rg + j][lc];
+      w[j] = raw[8 * rg + j][lc];
+    }
+    if (out_op) {
+      if (mode == 2) {
+        float lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo[j] = n[j] - __bfloat162float(__float2bfloat16_rn(n[j]));
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_op) + orow * ld + r;
+        *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(n[0], n[1]), pack_bf16(n[2], n[3]), pack_bf16(n[4], n[5]),
+                                                  pack_bf16(n[6], n[7]));
+        *reinterpret_cast<uint4*>(o + R_pad) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]),
+                                                          pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+      } else if (mode == 1) {
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_op) + orow * ld + r) =
+            make_uint4(pack_bf16(n[0], n[1]), pack_bf16(n[2], n[3]), pack_bf16(n[4], n[5]), pack_bf16(n[6], n[7]));
+      } else if (mode == 3) {
+        *reinterpret_cast<uint4*>(static_cast<__half*>(out_op) + orow * ld + r) =
+            make_uint4(pack_f16(n[0], n[1]), pack_f16(n[2], n[3]), pack_f16(n[4], n[5]), pack_f16(n[6], n[7]));
+      } else {
+        float* o = static_cast<float*>(out_op) + orow * ld + r;
+        if (round) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) n[j] = round_tf32(n[j]);
+        }
+        *reinterpret_cast<float4*>(o) = make_float4(n[0], n[1], n[2], n[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(n[4], n[5], n[6], n[7]);
+      }
+    }
+    if (out_f32) {
+      float* o = out_f32 + orow * R_pad + r;
+      *reinterpret_cast<float4*>(o) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(w[4], w[5], w[6], w[7]);
     }
   }
 }
@@ -406,8 +467,8 @@ extern "C" int avc_ln_transpose(const float* x, const float* gamma, const float*
     ln_col_stats_kernel<<<dim3((C + 255) / 256, B), 256, 0, stream>>>(x, scratch, R, C, 1e-5f);
     count_launch();
   }
-  dim3 grid((C + 31) / 32, (R_pad + 31) / 32, B);
-  ln_transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, scratch, gamma, beta, ln_axis, out_op, out_dtype,
+  dim3 grid((C + kLnTile - 1) / kLnTile, (R_pad + kLnTile - 1) / kLnTile, B);
+  ln_transpose_kernel<<<grid, 256, 0, stream>>>(x, scratch, gamma, beta, ln_axis, out_op, out_dtype,
                                                          out_round_tf32, out_f32, R, C, R_pad);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();

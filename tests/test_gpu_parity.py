@@ -430,15 +430,17 @@ def test_meta_glue_kernels_match_cpu_standins():
             ref = E._emu_patchify(a, stats.cpu() if stats is not None else None, gs, bs, p, "fp32")
             assert tk.shape == ref.shape
             assert rel_l2(packing.act_to_float(tk, "fp32"), packing.act_to_float(ref, "fp32")) < 2e-5
-    for R, C2, ax in ((484, 176, 1), (176, 488, 2), (1849, 344, 1), (344, 1856, 2), (344, 88, 0), (88, 176, 0)):
+    for R, C2, ax in ((484, 176, 1), (176, 488, 2), (1849, 344, 1), (344, 1856, 2), (344, 88, 0), (88, 176, 0), (121, 176, 1),
+                      (70, 36, 0)):
         z = torch.randn(2, R, C2)
         n = C2 if ax == 1 else R
         gz, bz = torch.rand(n) + 0.5, torch.randn(n) * 0.2
-        o, f = ops.ln_transpose(z.cuda(), gz.cuda() if ax else None, bz.cuda() if ax else None, ax, "fp32", want_f32=True)
-        ro_, rf_ = E._emu_ln_transpose(z, gz, bz, ax, "fp32", want_f32=True)
-        assert o.shape == ro_.shape and f.shape == rf_.shape
-        assert rel_l2(packing.act_to_float(o, "fp32"), packing.act_to_float(ro_, "fp32")) < 3e-5, (R, C2, ax)
-        assert torch.equal(f.cpu(), rf_)
+        for prec, tol in (("fp32", 3e-5), ("fp16x2", 5e-4), ("bf16", 5e-3), ("tf32", 5e-4)):
+            o, f = ops.ln_transpose(z.cuda(), gz.cuda() if ax else None, bz.cuda() if ax else None, ax, prec, want_f32=True)
+            ro_, rf_ = E._emu_ln_transpose(z, gz, bz, ax, prec, want_f32=True)
+            assert o.shape == ro_.shape and f.shape == rf_.shape
+            assert rel_l2(packing.act_to_float(o, prec), packing.act_to_float(ro_, prec)) < tol, (R, C2, ax, prec)
+            assert torch.equal(f.cpu(), rf_)
     codes, spk = torch.randn(2, 8, 88), torch.randn(2, 256)
     di = ops.meta_decoder_input(codes.cuda(), spk.cuda(), 176, 22, "fp32")
     assert rel_l2(packing.act_to_float(di, "fp32"), packing.act_to_float(E._emu_meta_decoder_input(codes, spk, 176, 22, "fp32"), "fp32")) < 1e-6
