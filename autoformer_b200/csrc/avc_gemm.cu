@@ -54,7 +54,19 @@ __device__ __forceinline__ float apply_act(float v) {
   if (ACT == AVC_ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == AVC_ACT_TANH) return tanh_fast(v);
   if (ACT == AVC_ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
-  if (ACT == AVC_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+  if (ACT == AVC_ACT_GELU) {
+    // exact-erf GELU, 0.5 v (1 + erf(v / sqrt 2)), with erfc(|x|) = t (a1 + t (a2 + ... a5 t)) exp(-x^2), t = 1 / (1 + p |x|)
+    // (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- fp32 rounding level; two MUFU ops and no branch, where erff()
+    // costs the low-K mixer GEMMs more than their MMAs).  1 + erf(x) is formed without cancellation on the negative side.
+    const float x = fabsf(v) * 0.70710678118654752f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+    float q = fmaf(t, 1.061405429f, -1.453152027f);
+    q = fmaf(t, q, 1.421413741f);
+    q = fmaf(t, q, -0.284496736f);
+    q = fmaf(t, q, 0.254829592f);
+    q = q * t * __expf(-x * x);                       // erfc(|x|)
+    return 0.5f * v * (v < 0.0f ? q : 2.0f - q);
+  }
   if (ACT == AVC_ACT_LOG10_CLAMP) return log10f(fmaxf(v, 1e-5f));
   return v;
 }
@@ -114,6 +126,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
     return n < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   float4 bv_next = c_first < chunks ? load_bias(c_first) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // output shapes served by the branch-free row loops (see below); tiles with one real chunk keep the general loop
+  int simple = 0;
+  if (!split_rows && p.phases == 1 && p.out_reflect == 0 && !p.out_raw) {
+    if (p.out && !p.out2 && !has_res && p.out_mode != 0) simple = 1;
+    if (!p.out && p.out2 && !(has_res && res_after)) simple = 2;
+  }
   // The row loop is deliberately NOT fully unrolled: with 8 copies of the (mode x output x halo) store code the
   // epilogue was ~4000 instructions, and layers with few k-blocks per tile (MelGAN stages 2-3, 1x1 convolutions) spent
   // 7 K cycles per 32-column chunk fetching instructions (ncu: 20 % stall_no_inst; time per tile independent of K).
@@ -135,7 +153,50 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
     const int n = n0 + c32 * 32 + cl;
     const float4 bv = bv_next;
     if (c32 + kEpiWarps / 4 < chunks) bv_next = load_bias(c32 + kEpiWarps / 4);
-    if (n < p.N) {
+    if (n < p.N && simple != 0) {
+      // The two common output shapes without any per-row branching (the general loop below crosses ~10 branches per
+      // 4-element store; with two epilogue warps per scheduler nothing hides their latency, and layers with few
+      // k-blocks per tile were bound by it: 13.5 K cycles per 128 x 256 tile against 9 K cycles of MMAs).
+      //   simple 1: act(v) to `out` in a 16-bit operand format or the split format, nothing else
+      //   simple 2: act(v [+ residual]) to `out2` (fp32), nothing else
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {          // (simple excludes split_rows: all eight row groups are this warp's)
+        {
+          const int m = q * 32 + 4 * i + rsub;
+          const int b = b0 + (m >> p.tb_log2);
+          const int t = t0 + (m & (tb - 1));
+          const bool ok = b < p.B && t < p.T;
+          const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
+          float o[4] = {a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w};
+          if (simple == 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
+            const long long off = ((long long)b * p.out_rows_per_utt + p.out_row0 + t) * p.out_ld + n;
+            __nv_bfloat16* ptr = static_cast<__nv_bfloat16*>(p.out) + off;      // 2-byte elements in all three formats
+            const bool f16 = p.out_mode == 3;
+            const uint2 hi = f16 ? make_uint2(pack_f16(o[0], o[1]), pack_f16(o[2], o[3]))
+                                 : make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+            if (ok) *reinterpret_cast<uint2*>(ptr) = hi;
+            if (p.out_mode == 2) {
+              float lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) lo[e] = o[e] - __bfloat162float(__float2bfloat16_rn(o[e]));
+              if (ok) *reinterpret_cast<uint2*>(ptr + p.cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+            }
+          } else {
+            const long long lr = (long long)b * p.T + t;
+            if (has_res) {
+              float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) rv = __ldg(reinterpret_cast<const float4*>(p.residual + lr * p.res_ld + n));
+              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
+            if (ok) *reinterpret_cast<float4*>(p.out2 + lr * p.out2_ld + n) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    } else if (n < p.N) {
       const int phase = p.phases == 1 ? 0 : n / p.cs;
       const int c = n - phase * p.cs;
 #pragma unroll 2
