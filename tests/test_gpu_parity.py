@@ -485,24 +485,26 @@ def test_meta_parity_and_golden(kind, name, precision, tol):
 
 
 # ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
 @pytest.mark.parametrize("B,T", [(1, 32), (130, 32), (2, 1024), (257, 64)])
-def test_autovc_edge_shapes(B, T):
+def test_autovc_edge_shapes(B, T, precision):
     """Smallest utterance (one code), ragged batches that leave partial / masked tiles and CTA pairs with a phantom
     m-tile, and the longest BASELINE utterance length.  The oracle is evaluated on a few utterances only."""
     args = (32, 256, 512, 32)
     sd = seeded_state_dict(templates.autovc_template(*args), 5)
     x, c_org, c_trg = synthetic_mel(B, T, 31), synthetic_speaker(B, 31, "org"), synthetic_speaker(B, 31, "trg")
-    m = _model(args, sd)
+    m = _model(args, sd, precision)
     mel, post, codes = m(x.cuda(), c_org.cuda(), c_trg.cuda())
     assert mel.shape == (B, 1, T, 80) and post.shape == (B, 1, T, 80) and codes.shape == (B, 64 * (T // 32))
     assert torch.isfinite(post).all()
     pick = sorted({0, B // 2, B - 1})
     ref = autovc_forward(sd, x[pick], c_org[pick], c_trg[pick], 32, 32)
-    assert rel_l2(mel[pick], ref[0]) < 2e-4 and rel_l2(post[pick], ref[1]) < 2e-4 and rel_l2(codes[pick], ref[2]) < 2e-4
+    tol = TOL[precision]
+    assert rel_l2(mel[pick], ref[0]) < tol and rel_l2(post[pick], ref[1]) < tol and rel_l2(codes[pick], ref[2]) < tol
     m.persistent_lstm = True
     post_p = m(x.cuda(), c_org.cuda(), c_trg.cuda())[1]
-    # B <= 64: the persistent path is the weight-stationary kernel (other summation order); else bit-identical
-    assert rel_l2(post_p, post) < 1e-5 if B <= 64 else torch.equal(post_p, post)
+    # fp32 at B <= 64: the persistent path is the weight-stationary kernel (other summation order); else bit-identical
+    assert rel_l2(post_p, post) < 1e-5 if (B <= 64 and precision == "fp32") else torch.equal(post_p, post)
 
 
 def test_lstmdv_and_melgan_batch_independence():
