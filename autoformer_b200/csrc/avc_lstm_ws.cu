@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
     mbar_init(h_full, 1);
     mbar_init(d_full, 1);
     mbar_init(red_full, 1);
-    mbar_init(epi_done, 1);
+    mbar_init(epi_done, AR > 32 ? 2 : 1);     // one arrival per warp that stores h_t
     fence_mbar_init();
     if (!WT) prefetch_tmap(&p.tmap_w);
     prefetch_tmap(&p.tmap_h);
@@ -304,9 +304,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsCellWarps) : "memory");
       if (threadIdx.x == 64) AVC_WS_STAMP(t, 6);
-      if (warp == 2) {
+      if (warp == 2 || (AR > 32 && warp == 3)) {
         // utterance n: the kUnitsOwn units this CTA finalised, as whole 8-byte groups of the split operand format
-        for (int n = lane; n < AR && n < p.B; n += 32) {
+        // (one lane per utterance: warp 2 alone up to 32 utterances, warps 2 and 3 for 64)
+        for (int n = (warp - 2) * 32 + lane; n < AR && n < p.B; n += AR) {
           const long long orow = (long long)n * p.T + t;
           const int ug = r * 32 + (int)rank * Cfg::kUnitsOwn;
 #pragma unroll
