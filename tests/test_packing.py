@@ -54,6 +54,41 @@ def test_split_bf16_packing_is_fp32_grade(c_in, c_out, k):
     assert (ours - ref).norm() / ref.norm() < 3e-5
 
 
+@pytest.mark.parametrize("c_in,c_out,k", [(336, 512, 5), (80, 96, 5), (512, 80, 1)])
+def test_fp16x2_packing_rounds_only_the_activations(c_in, c_out, k):
+    """"fp16x2" mode: a x w_hi + a x w_lo over the SAME fp16 buffer -- the weights are exact to ~2^-22, so with
+    activations that are exactly representable in fp16 the product matches fp64 to fp32 rounding level, and with
+    general activations the error is the 2^-12 of their rounding."""
+    B, T = 2, 13
+    w = torch.randn(c_out, c_in, k)
+    b = torch.randn(c_out)
+    x = torch.randn(B, c_in, T)
+    wp, bp, meta = packing.pack_conv(w, b, "fp16x2")
+    assert meta["dup"] and not meta.get("split") and meta["channels"] == [c_in, c_in] and wp.dtype == torch.float16
+    assert meta["precision"] == "fp16x2" and meta["logical_channels"] == [c_in] and meta["logical_taps"] == [k]
+    hi, lo = packing.split_f16(w)
+    assert (hi.double() + lo.double() - w.double()).abs().max() < 2 ** -21 * w.abs().max()
+    buf = packing.to_act(_cl(x), "fp16x2")
+    assert buf.shape == (B, T, c_in) and buf.dtype == torch.float16 and packing.act_channels(c_in, "fp16x2") == c_in
+    ours = emulate_conv_gemm(wp, bp, meta, [buf, buf], B, T, [-(k // 2)] * 2, [1, 1])
+    ref = _cl(F.conv1d(x.double(), w.double(), b.double(), padding=k // 2))
+    ref_q = _cl(F.conv1d(x.half().double(), w.double(), b.double(), padding=k // 2))     # activations rounded, weights exact
+    assert (ours - ref_q).norm() / ref_q.norm() < 2e-6
+    assert 1e-5 < (ours - ref).norm() / ref.norm() < 5e-4
+
+
+def test_fp16x2_lstm_weight_layout():
+    H, G = 128, 32
+    w = torch.randn(4 * H, H) * 0.1
+    p = packing.pack_lstm_hh(w, "fp16x2", G)
+    assert p.shape == (4 * H, 2 * H) and p.dtype == torch.float16
+    perm = packing.gate_permutation(H, G)
+    assert ((p[:, :H].double() + p[:, H:].double()) - w[perm].double()).abs().max() < 2 ** -21 * w.abs().max()
+    wi, bias = packing.pack_lstm_ih_fused(torch.randn(4 * H, 80), torch.randn(4 * H), torch.randn(4 * H), "fp16x2", G)
+    assert wi.shape == (4 * H, 2 * 128) and wi.dtype == torch.float16 and bias.dtype == torch.float32
+    assert float(wi[:, 80:128].abs().max()) == 0.0 and float(wi[:, 128 + 80:].abs().max()) == 0.0   # K padding
+
+
 def test_split_lstm_hh_layout():
     H, G = 128, 32
     w = torch.randn(4 * H, H)
