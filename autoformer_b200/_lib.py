@@ -101,6 +101,7 @@ class LstmWsDesc(ctypes.Structure):
         ("T", ctypes.c_int),
         ("H", ctypes.c_int),
         ("debug_clk", ctypes.c_void_p),
+        ("dtype", ctypes.c_int),
     ]
 
 

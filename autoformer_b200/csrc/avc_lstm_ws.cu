@@ -68,8 +68,9 @@ struct WsCfg {
     while (c < need) c *= 2;
     return c;
   }
-  static int smem_bytes(int chunks, bool wt) {
-    return chunks * ((wt ? 0 : kWChunkBytes) + 2 * kHTile) + kRedBytes + kStageBytes + 128 + 1024 /* alignment slack */;
+  static int smem_bytes(int chunks, bool wt, bool f16) {
+    return chunks * ((wt ? 0 : kWChunkBytes) + (f16 ? 1 : 2) * kHTile) + kRedBytes + kStageBytes + 128 +
+           1024 /* alignment slack */;
   }
 };
 
@@ -103,15 +104,19 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
-template <int AR, int S, bool WT>
+// F16 ("fp16x2" precision, W in tensor memory only): h is one fp16 value per unit, the weights two fp16 terms; both
+// products W_hi x h and W_lo x h are N = AR MMAs onto the SAME accumulator columns.
+template <int AR, int S, bool WT, bool F16>
 __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_constant__ WsParams p) {
+  static_assert(!F16 || WT, "the fp16x2 form keeps W in tensor memory");
   using Cfg = WsCfg<AR, S>;
+  constexpr int HP = F16 ? 1 : 2;                    // tiles of h per 64-channel chunk (hi / lo halves)
   constexpr int NQ = AR / 4;                         // groups of 4 utterances
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = base;
   uint8_t* s_h = s_w + (WT ? 0 : p.chunks * kWChunkBytes);
-  float* s_red = reinterpret_cast<float*>(s_h + p.chunks * 2 * Cfg::kHTile);
+  float* s_red = reinterpret_cast<float*>(s_h + p.chunks * HP * Cfg::kHTile);
   float* s_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s_red) + Cfg::kRedBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_stage) + Cfg::kStageBytes);
   uint64_t* w_full = bars + 0;
@@ -166,9 +171,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
         AVC_WS_STAMP(t, 1);
         fence_proxy_async_global();     // h_{t-1} was written with generic stores
         // (one mbarrier per chunk, so that the MMAs start on the first chunk, measured slower: +430 cycles per frame)
-        mbar_arrive_expect_tx(h_full, p.chunks * 2 * Cfg::kHTile);
+        mbar_arrive_expect_tx(h_full, p.chunks * HP * Cfg::kHTile);
         for (int c = 0; c < p.chunks; ++c)
-          tma_load_4d(s_h + c * 2 * Cfg::kHTile, &p.tmap_h, h_full, k0 + c * 64, 0, 0, t - 1);
+          tma_load_4d(s_h + c * HP * Cfg::kHTile, &p.tmap_h, h_full, k0 + c * 64, 0, 0, t - 1);
       }
     }
     __syncwarp();
@@ -183,8 +188,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
         AVC_WS_STAMP(t, 2);
         tc_fence_after();               // orders the cell warps' accumulator reads of frame t - 1 before these MMAs
         for (int c = 0; c < p.chunks; ++c) {
-          const uint32_t h = smem_u32(s_h + c * 2 * Cfg::kHTile);            // [h_hi rows ; h_lo rows]
-          if (WT) {
+          const uint32_t h = smem_u32(s_h + c * HP * Cfg::kHTile);           // [h_hi rows ; h_lo rows] (F16: h rows)
+          if (F16) {
+            const uint32_t w_hi = tmem_w + c * 32, w_lo = w_hi + p.chunks * 32;   // 8 columns per K = 16
+            constexpr uint32_t idesc16 = umma_idesc(kBlockM, AR, false) ^ kIdescF16Xor;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem_base, w_hi + k * 8, umma_desc_sw128(h + k * 32), idesc16, (c == 0 && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(tmem_base, w_lo + k * 8, umma_desc_sw128(h + k * 32), idesc16, 1u);
+          } else if (WT) {
             const uint32_t w_hi = tmem_w + c * 32, w_lo = w_hi + p.chunks * 32;   // 8 columns per K = 16
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -267,8 +281,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
         for (int j = 0; j < AR / 16; ++j) {
           uint32_t a[16], b[16];
           tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 16, a);
-          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + AR + j * 16, b);
+          if (!F16) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + AR + j * 16, b);
           tmem_ld_wait();
+          if (F16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) b[i] = 0u;       // +0.0f: one accumulator block only
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             st_async_f4(push_addr + (j * 4 + i) * Cfg::kRowsOwn * 16, owner_bar,
@@ -317,9 +335,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
             const float ly = h.y - __bfloat162float(__float2bfloat16_rn(h.y));
             const float lz = h.z - __bfloat162float(__float2bfloat16_rn(h.z));
             const float lw = h.w - __bfloat162float(__float2bfloat16_rn(h.w));
-            __nv_bfloat16* o = p.hseq + orow * (2LL * p.H) + ug + i * 4;
-            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
-            *reinterpret_cast<uint2*>(o + p.H) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+            if (F16) {
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.hseq) + orow * p.H + ug + i * 4) =
+                  make_uint2(pack_f16(h.x, h.y), pack_f16(h.z, h.w));
+            } else {
+              __nv_bfloat16* o = p.hseq + orow * (2LL * p.H) + ug + i * 4;
+              *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(h.x, h.y), pack_bf16(h.z, h.w));
+              *reinterpret_cast<uint2*>(o + p.H) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+            }
             if (p.hseq_f32) *reinterpret_cast<float4*>(p.hseq_f32 + orow * p.H + ug + i * 4) = h;
             if (p.h_last && t == p.T - 1) *reinterpret_cast<float4*>(p.h_last + (long long)n * p.H + ug + i * 4) = h;
           }
@@ -342,11 +365,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) lstm_ws_kernel(const __grid_con
   }
 }
 
-template <int AR, int S, bool WT>
+template <int AR, int S, bool WT, bool F16 = false>
 static int launch_ws(WsParams p, const avc_lstm_ws_desc* d, cudaStream_t stream) {
   using Cfg = WsCfg<AR, S>;
-  auto kern = lstm_ws_kernel<AR, S, WT>;
-  const int smem = Cfg::smem_bytes(p.chunks, WT);
+  auto kern = lstm_ws_kernel<AR, S, WT, F16>;
+  const int smem = Cfg::smem_bytes(p.chunks, WT, F16);
   AVC_REQUIRE(smem <= 227 * 1024, "avc_lstm_seq_ws: H=%d B=%d needs %d bytes of shared memory", d->H, d->B, smem);
   static int configured = 0;
   if (configured < smem) {
@@ -401,9 +424,13 @@ extern "C" int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream_v) {
   WsParams p;
   memset(&p, 0, sizeof(p));
   if (!encode_tmap_3d(&p.tmap_w, 2, d->w_hh, H, 4 * H, 2, 2 * H * 2, H * 2, 64, kBlockM, 2)) return -3;
-  const uint64_t dh[4] = {H, (uint64_t)d->B, 2, (uint64_t)d->T};
-  const uint64_t sh[3] = {(uint64_t)d->T * 2 * H * 2, H * 2, 2 * H * 2};
-  const uint32_t bh[4] = {64, (uint32_t)ar, 2, 1};
+  AVC_REQUIRE(d->dtype == 0 || d->dtype == AVC_DTYPE_BF16X3 || d->dtype == AVC_DTYPE_F16, "avc_lstm_seq_ws: dtype %d",
+              d->dtype);
+  const bool f16 = d->dtype == AVC_DTYPE_F16;          // h: one fp16 per unit; else [hi | lo] bf16
+  const uint64_t hp = f16 ? 1 : 2;
+  const uint64_t dh[4] = {H, (uint64_t)d->B, hp, (uint64_t)d->T};
+  const uint64_t sh[3] = {(uint64_t)d->T * hp * H * 2, H * 2, hp * H * 2};
+  const uint32_t bh[4] = {64, (uint32_t)ar, (uint32_t)hp, 1};
   if (!encode_tmap_4d(&p.tmap_h, 2, d->hseq, dh, sh, bh)) return -3;
   // the W slice lives in tensor memory as the MMA's A operand (AVC_WS_W_SMEM=1: in shared memory, for A/B timing)
   static const bool wt = getenv("AVC_WS_W_SMEM") == nullptr;
@@ -423,7 +450,10 @@ extern "C" int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream_v) {
 #define AVC_WS_DISPATCH(S_)                                                                     \
   if (d->H % (64 * S_) == 0 && R * S_ <= num_sms()) {                                           \
     p.chunks = d->H / S_ / 64;                                                                  \
-    const int rc = wt ? (ar == 16   ? launch_ws<16, S_, true>(p, d, stream)                     \
+    const int rc = f16 ? (ar == 16   ? launch_ws<16, S_, true, true>(p, d, stream)              \
+                          : ar == 32 ? launch_ws<32, S_, true, true>(p, d, stream)              \
+                                     : launch_ws<64, S_, true, true>(p, d, stream))             \
+                   : wt ? (ar == 16   ? launch_ws<16, S_, true>(p, d, stream)                   \
                          : ar == 32 ? launch_ws<32, S_, true>(p, d, stream)                     \
                                     : launch_ws<64, S_, true>(p, d, stream))                    \
                       : (ar == 16   ? launch_ws<16, S_, false>(p, d, stream)                    \

@@ -99,7 +99,8 @@ class LstmLayer:
             ih, hh = self.packs(packing.WS_GROUP)
             xp = torch.empty(B * T, 4 * self.H, dtype=torch.float32, device=x.device)
             ih(x, B, T, out2=xp)
-            out = ops.lstm_seq_ws(xp, hh, B, T, self.H, hseq=hseq, hseq_f32=hseq_f32, h_last=h_last)
+            out = ops.lstm_seq_ws(xp, hh, B, T, self.H, hseq=hseq, hseq_f32=hseq_f32, h_last=h_last,
+                                  precision=self.precision)
             if out is not None:
                 return out
             self.ws = False             # the device cannot hold the grid: batched kernel from now on

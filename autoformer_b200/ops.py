@@ -306,7 +306,7 @@ def ws_supported(B, H, precision, n_sm=148):
     blocks x 4 K-slices within one wave (8 slices are used when the device can hold them); the W slice lives in
     tensor memory (<= 256 of the 512 columns, beside the accumulator), the h slice and the reduction buffer in
     shared memory."""
-    if precision != "fp32" or B < 1 or B > WS_MAX_BATCH or H % 256 or 4 * H // 128 * 4 > n_sm:
+    if precision not in packing.TWO_TERM_WEIGHTS or B < 1 or B > WS_MAX_BATCH or H % 256 or 4 * H // 128 * 4 > n_sm:
         return False
     ar = 16 if B <= 16 else (32 if B <= 32 else 64)
     chunks = H // 4 // 64
@@ -315,7 +315,7 @@ def ws_supported(B, H, precision, n_sm=148):
     return chunks * 2 * ar * 128 + red + stage + 1152 <= 227 * 1024 and 2 * ar + 64 * chunks <= 512
 
 
-def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, debug_clk=None):
+def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, debug_clk=None, precision="fp32"):
     """Small-batch recurrence with W_hh resident in shared memory (split precision).  xproj [B*T][4H] fp32 and w_hh
     [4H][2H] bf16 in the packing.WS_GROUP gate order.  Returns hseq, or None when the device cannot hold the grid
     (nothing was launched; the caller uses lstm_seq)."""
@@ -323,11 +323,14 @@ def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, deb
     _require_cuda(xproj, w_hh)
     dev = w_hh.device
     assert xproj.dtype == torch.float32 and xproj.is_contiguous() and xproj.numel() == B * T * 4 * H
-    assert w_hh.dtype == torch.bfloat16 and w_hh.shape == (4 * H, 2 * H) and w_hh.is_contiguous()
+    assert precision in packing.TWO_TERM_WEIGHTS
+    assert w_hh.dtype == TORCH_DTYPE[precision] and w_hh.shape == (4 * H, 2 * H) and w_hh.is_contiguous()
     if hseq is None:
-        hseq = alloc_act(B, T, H, "fp32", dev)
-    assert hseq.is_contiguous() and hseq.shape == (B, T, 2 * H) and hseq.dtype == torch.bfloat16
+        hseq = alloc_act(B, T, H, precision, dev)
+    assert hseq.is_contiguous() and hseq.shape == (B, T, packing.act_channels(H, precision))
+    assert hseq.dtype == TORCH_DTYPE[precision]
     d = _lib.LstmWsDesc()
+    d.dtype = _dt(precision)
     d.xproj, d.w_hh, d.hseq = xproj.data_ptr(), w_hh.data_ptr(), hseq.data_ptr()
     if hseq_f32 is not None:
         assert hseq_f32.is_contiguous() and hseq_f32.shape == (B, T, H) and hseq_f32.dtype == torch.float32

@@ -193,7 +193,7 @@ typedef struct avc_lstm_desc {
 int avc_lstm_seq(const avc_lstm_desc* d, void* stream);
 
 /*
- * Small-batch form of the same recurrence (B <= 64, split-bf16 precision only): the recurrent weights stay in
+ * Small-batch form of the same recurrence (B <= 64, split-bf16 or fp16x2 precision): the recurrent weights stay in
  * shared memory for the whole sequence (4H/128 row blocks x S K-slices, one thread-block cluster per row block
  * reducing its partial sums through distributed shared memory), so a frame moves only h_{t-1}.
  * Same semantics and references as avc_lstm_seq (factory/AutoVC.py:77,96,103,110; factory/LstmDV.py:12,20).
@@ -209,6 +209,8 @@ typedef struct avc_lstm_ws_desc {
   unsigned int* grid_barrier; /* one counter; zeroed by the library */
   int B, T, H;
   long long* debug_clk;       /* optional device buffer, 8 x int64 per (frame, CTA): clock64 stamps (profiling aid) */
+  int dtype;                  /* 0 or AVC_DTYPE_BF16X3: as above; AVC_DTYPE_F16 ("fp16x2"): w_hh = [w_hi | w_lo] fp16,
+                                 hseq [B][T][H] fp16 */
 } avc_lstm_ws_desc;
 
 int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream);

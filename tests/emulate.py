@@ -140,9 +140,9 @@ def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=No
     return hseq
 
 
-def _emu_lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None):
-    """Mirror of lstm_ws_kernel: gate rows packed p = 128 (u//32) + 4 (u%32) + gate; split-bf16 operands."""
-    assert ops.ws_supported(B, H, "fp32")
+def _emu_lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, precision="fp32"):
+    """Mirror of lstm_ws_kernel: gate rows packed p = 128 (u//32) + 4 (u%32) + gate; split-bf16 or fp16x2 operands."""
+    assert ops.ws_supported(B, H, precision)
     w = w_hh[:, :H].double() + w_hh[:, H:].double()
     xp = xproj.double().reshape(B, T, 4 * H)
     h = torch.zeros(B, H, dtype=torch.float64)
@@ -151,15 +151,15 @@ def _emu_lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None
     u = torch.arange(H)
     base = 128 * (u // 32) + 4 * (u % 32)
     for t in range(T):
-        hq = packing.act_to_float(packing.to_act(h.float(), "fp32"), "fp32").double()
+        hq = packing.act_to_float(packing.to_act(h.float(), precision), precision).double()
         z = xp[:, t] + hq @ w.t()
         zi, zf, zg, zo = (z[:, base + g] for g in range(4))
         c = torch.sigmoid(zf) * c + torch.sigmoid(zi) * torch.tanh(zg)
         h = torch.sigmoid(zo) * torch.tanh(c)
         outs[:, t] = h
     if hseq is None:
-        hseq = torch.empty(B, T, 2 * H, dtype=torch.bfloat16)
-    hseq.copy_(packing.to_act(outs.float(), "fp32"))
+        hseq = torch.empty(B, T, packing.act_channels(H, precision), dtype=packing.TORCH_DTYPE[precision])
+    hseq.copy_(packing.to_act(outs.float(), precision))
     if hseq_f32 is not None:
         hseq_f32.copy_(outs.float())
     if h_last is not None:

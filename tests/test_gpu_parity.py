@@ -113,32 +113,34 @@ def test_lstm_seq_matches_explicit_lstm(precision, B, T, I, H, persistent, fused
 @pytest.mark.parametrize("B,T,I,H", [(1, 5, 80, 512), (2, 40, 320, 512), (16, 7, 80, 768), (17, 9, 512, 1024),
                                      (32, 30, 1024, 1024), (33, 6, 768, 768), (64, 12, 80, 768), (64, 5, 320, 512),
                                      (64, 6, 512, 1024)])
-def test_lstm_ws_matches_explicit_lstm(B, T, I, H):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+def test_lstm_ws_matches_explicit_lstm(B, T, I, H, precision):
     """Small-batch recurrence with W_hh resident in shared memory (avc_lstm_seq_ws): every activation-row variant
     (16 / 32 / 64), both cluster sizes (H = 512: 8 K-slices; 768 / 1024: 4), ragged batches."""
     from autoformer_b200 import layers, ops, packing
-    assert ops.ws_supported(B, H, "fp32")
+    assert ops.ws_supported(B, H, precision)
     torch.manual_seed(H + T + B)
     k = 1.0 / H ** 0.5
     w_ih, w_hh = (torch.rand(4 * H, I) * 2 - 1) * k * 3, (torch.rand(4 * H, H) * 2 - 1) * k * 3
     b_ih, b_hh = (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
     x = torch.randn(B, T, I)
     ref = lstm_explicit(x.double(), w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
-    layer = layers.LstmLayer(w_ih.cuda(), w_hh.cuda(), b_ih.cuda(), b_hh.cuda(), "fp32")
+    layer = layers.LstmLayer(w_ih.cuda(), w_hh.cuda(), b_ih.cuda(), b_hh.cuda(), precision)
+    tol = {"fp32": 5e-5, "fp16x2": 1e-3}[precision]
     assert layer.ws
     f32 = torch.full((B, T, H), float("nan"), device="cuda")
     last = torch.full((B, H), float("nan"), device="cuda")
-    hseq = layer(packing.to_act(x, "fp32").cuda(), B, T, hseq_f32=f32, h_last=last, persistent=True)
+    hseq = layer(packing.to_act(x, precision).cuda(), B, T, hseq_f32=f32, h_last=last, persistent=True)
     torch.cuda.synchronize()
     assert layer.ws, "the weight-stationary grid was not co-resident on this device"
-    assert rel_l2(f32, ref) < 5e-5
-    assert rel_l2(last, ref[:, -1]) < 5e-5
-    assert rel_l2(packing.act_to_float(hseq, "fp32"), ref) < 1e-4
+    assert rel_l2(f32, ref) < tol
+    assert rel_l2(last, ref[:, -1]) < tol
+    assert rel_l2(packing.act_to_float(hseq, precision), ref) < 2 * tol
     # the batched kernel on the same inputs
     layer.ws = False
     f32_b = torch.empty_like(f32)
-    layer(packing.to_act(x, "fp32").cuda(), B, T, hseq_f32=f32_b, persistent=True)
-    assert rel_l2(f32_b, f32) < 2e-5
+    layer(packing.to_act(x, precision).cuda(), B, T, hseq_f32=f32_b, persistent=True)
+    assert rel_l2(f32_b, f32) < (2e-5 if precision == "fp32" else 1e-3)
 
 
 @pytest.mark.parametrize("H,freq,B,T", [(32, 32, 5, 64), (44, 22, 3, 88), (32, 32, 1, 32)])
@@ -279,8 +281,10 @@ def test_lstmdv_parity_and_golden(precision, tol):
     assert torch.allclose(e.norm(dim=-1), torch.ones(2, device="cuda"), atol=1e-4)
     m.persistent_lstm = False                                          # one launch per frame, batched kernel
     e_step = m(x.cuda())
-    # fp32 at this batch size runs the weight-stationary recurrence when persistent: same math, other summation order
-    assert rel_l2(e_step, e) < 1e-5 if precision == "fp32" else torch.equal(e_step, e)
+    # fp32 / fp16x2 at this batch size run the weight-stationary recurrence when persistent: same math, other
+    # summation order (fp16x2: values move across fp16 rounding boundaries)
+    ws_tol = {"fp32": 1e-5, "fp16x2": 1e-3}.get(precision)
+    assert rel_l2(e_step, e) < ws_tol if ws_tol else torch.equal(e_step, e)
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 5e-3), ("bf16", 5e-2), ("fp16x2", 2e-3)])
@@ -503,8 +507,8 @@ def test_autovc_edge_shapes(B, T, precision):
     assert rel_l2(mel[pick], ref[0]) < tol and rel_l2(post[pick], ref[1]) < tol and rel_l2(codes[pick], ref[2]) < tol
     m.persistent_lstm = True
     post_p = m(x.cuda(), c_org.cuda(), c_trg.cuda())[1]
-    # fp32 at B <= 64: the persistent path is the weight-stationary kernel (other summation order); else bit-identical
-    assert rel_l2(post_p, post) < 1e-5 if (B <= 64 and precision == "fp32") else torch.equal(post_p, post)
+    # B <= 64: the persistent path is the weight-stationary kernel (other summation order); else bit-identical
+    assert rel_l2(post_p, post) < (1e-5 if precision == "fp32" else 1e-3) if B <= 64 else torch.equal(post_p, post)
 
 
 def test_lstmdv_and_melgan_batch_independence():
