@@ -1,12 +1,13 @@
-// Small-batch LSTM recurrence with the recurrent weights STATIONARY in shared memory (see include/avc_b200.h:
-// avc_lstm_seq_ws).  B <= 64 utterances, split-bf16 precision.
+// Small-batch LSTM recurrence with the recurrent weights STATIONARY on chip (see include/avc_b200.h:
+// avc_lstm_seq_ws).  B <= 64 utterances, split-bf16 or fp16x2 precision.
 //
 // At a small batch the batched kernel (avc_lstm.cu) multiplies a 128-row activation tile of which only B rows are real
 // and re-streams every weight tile from L2 each frame; a frame costs ~15 K cycles whatever B is.  Here the roles of the
 // operands are swapped:
 //   z^T [4H x B] = W_hh [4H x H] . h_{t-1}^T [H x B]
 // W is the M-side operand and never moves: the grid is R = 4H / 128 row blocks x S K-slices, and CTA (r, s) keeps
-// W[128 r .. 128 r + 128, slice s] (hi and lo halves, <= 128 KB) in shared memory for the whole sequence.  Per frame a
+// W[128 r .. 128 r + 128, slice s] (hi and lo halves, <= 128 KB) on chip for the whole sequence -- in tensor memory, as
+// the A operand of tcgen05.mma (AVC_WS_W_SMEM=1: in shared memory, the first version, kept for A/B timing).  Per frame a
 // CTA loads only its K-slice of h_{t-1} (B rows: a few KB), issues
 //   W_hi x [h_hi ; h_lo]   (one MMA of width N = 2 B')      and      W_lo x h_hi   (N = B')
 // into a 128 x 2B' accumulator, and the S CTAs of a row block -- one thread-block CLUSTER -- reduce their partial sums
