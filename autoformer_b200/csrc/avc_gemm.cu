@@ -380,10 +380,9 @@ template <int BN, bool BF16, int CTAS>
 static int launch_impl(const GemmParams& p, long long m_tiles, cudaStream_t stream) {
   auto kern = conv_gemm_kernel<BN, BF16, CTAS>;
   using C = PipeCfg<BN, CTAS, 1, true, 0, 2>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
+  static PerDeviceOnce configured;   // per instantiation
+  if (configured.first_use()) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
   }
   const long long pairs_m = (m_tiles + CTAS - 1) / CTAS;          // a phantom second m-tile is masked in the epilogue
   const long long units = pairs_m * p.n_tiles;

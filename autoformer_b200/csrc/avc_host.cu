@@ -93,13 +93,11 @@ bool encode_tmap_2d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
-  }
-  return n;
+  static int n[PerDeviceOnce::kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PerDeviceOnce::kMaxDevices) return 148;
+  if (n[dev] == 0 && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 148;
+  return n[dev];
 }
 
 }  // namespace avc

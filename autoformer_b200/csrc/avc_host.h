@@ -24,7 +24,22 @@ bool encode_tmap_4d(CUtensorMap* map, int elem_bytes, const void* base, const ui
 bool encode_tmap_2d(CUtensorMap* map, int elem_bytes, const void* base, uint64_t d0, uint64_t d1,
                     uint64_t stride1_bytes, uint32_t box0, uint32_t box1);
 
-int num_sms();
+int num_sms();   // of the CURRENT device (cached per device)
+
+// Per-device "already configured" flag for a kernel's cudaFuncSetAttribute: function attributes are per device, so a
+// process that drives several GPUs must set them once on each.  One instance per kernel instantiation (a function-local
+// static at the launch site); `first_use()` returns true exactly once per (instance, current device).
+struct PerDeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  bool done[kMaxDevices] = {};
+  bool first_use() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;   // unknown: always configure
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 
 #define AVC_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \

@@ -605,10 +605,9 @@ static int run(LstmParams p, const avc_lstm_desc* d, int m_tiles, cudaStream_t s
   // a latency-bound frame wants (a TMA round trip costs ~3 K cycles whatever the tile size)
   const int fit = C::kStages * C::kStageBytes / p.stage_bytes;
   p.stages = (uint32_t)(fit < kMaxStages ? fit : kMaxStages);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first_use()) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
   }
   const int grid = (m_tiles + CTAS - 1) / CTAS * CTAS * p.n_tiles;
   cudaLaunchConfig_t cfg = {};

@@ -372,11 +372,14 @@ static int launch_ws(WsParams p, const avc_lstm_ws_desc* d, cudaStream_t stream)
   auto kern = lstm_ws_kernel<AR, S, WT, F16>;
   const int smem = Cfg::smem_bytes(p.chunks, WT, F16);
   AVC_REQUIRE(smem <= 227 * 1024, "avc_lstm_seq_ws: H=%d B=%d needs %d bytes of shared memory", d->H, d->B, smem);
-  static int configured = 0;
-  if (configured < smem) {
+  static int configured[PerDeviceOnce::kMaxDevices] = {};   // largest size set so far, per device
+  int dev = 0;
+  AVC_CHECK_CUDA(cudaGetDevice(&dev));
+  const bool known = dev >= 0 && dev < PerDeviceOnce::kMaxDevices;
+  if (!known || configured[dev] < smem) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = smem;
+    if (known) configured[dev] = smem;
   }
   const int grid = 4 * d->H / kBlockM * S;
   cudaLaunchConfig_t cfg = {};

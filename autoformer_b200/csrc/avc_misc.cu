@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_l2norm_kernel(const float* __restrict__ h, const float* __restrict__ w,
                                                             const float* __restrict__ bias, float* __restrict__ out,
-                                                            int K, int N) {
+                                                            float* __restrict__ out_raw, int K, int N) {
   extern __shared__ float sh[];   // [K] input row, then 8 partial sums
   float* red = sh + K;
   const int b = blockIdx.x;
@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(256) linear_l2norm_kernel(const float* __restr
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
   const float inv = rsqrtf(tot);
   cnt = 0;
-  for (int n = threadIdx.x; n < N; n += blockDim.x, ++cnt) out[(long long)b * N + n] = e_val[cnt] * inv;
+  for (int n = threadIdx.x; n < N; n += blockDim.x, ++cnt) {
+    if (out) out[(long long)b * N + n] = e_val[cnt] * inv;
+    if (out_raw) out_raw[(long long)b * N + n] = e_val[cnt];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,7 +371,19 @@ extern "C" int avc_linear_l2norm(const float* h, const float* w, const float* bi
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(h && w && bias && out, "avc_linear_l2norm: null buffer");
   AVC_REQUIRE(B > 0 && K > 0 && K % 4 == 0 && N > 0 && N <= 1024, "avc_linear_l2norm: bad shape B=%d K=%d N=%d", B, K, N);
-  linear_l2norm_kernel<<<B, 256, (K + 8) * sizeof(float), stream>>>(h, w, bias, out, K, N);
+  linear_l2norm_kernel<<<B, 256, (K + 8) * sizeof(float), stream>>>(h, w, bias, out, nullptr, K, N);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int avc_linear_rows(const float* h, const float* w, const float* bias, float* out_raw, float* out_normed,
+                               int B, int K, int N, void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(h && w && bias && (out_raw || out_normed), "avc_linear_rows: null buffer");
+  AVC_REQUIRE(B > 0 && K > 0 && K % 4 == 0 && N > 0 && N <= 1024, "avc_linear_rows: bad shape B=%d K=%d N=%d", B, K, N);
+  linear_l2norm_kernel<<<B, 256, (K + 8) * sizeof(float), stream>>>(h, w, bias, out_normed, out_raw, K, N);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -336,10 +336,9 @@ template <int C>
 static int launch(const RbParams& p, cudaStream_t stream) {
   using Cfg = RbCfg<C>;
   auto kern = resblock_kernel<C>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first_use()) {
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   const int max_ctas = num_sms() * Cfg::kCtasPerSm;
   const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;

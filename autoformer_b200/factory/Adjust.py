@@ -39,7 +39,7 @@ class AdjustPlan:
         return ops.linear_l2norm(h_last, self.w, self.b)               # :40-42
 
 
-class Adjust(nn.Module):
+class Adjust(layers.PlanOwner, nn.Module):
     def __init__(self, dim_emb, dim_cell=768):
         super().__init__()
         self.convolutions = nn.ModuleList([
@@ -57,6 +57,7 @@ class Adjust(nn.Module):
             return AdjustPlan(sd, "", self.precision)
         return self._cache.get(self, (self.precision,), build)
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x, emb):
         if x.dim() == 4:

@@ -50,6 +50,27 @@ class Postnet(nn.Module):
                           nn.BatchNorm1d(co)) for ci, co, g in chans])
 
 
+def check_hyper_parameters(dim_neck, dim_emb, dim_pre, freq):
+    """The kernels cover a subset of the shapes the reference's nn.Modules accept (they accept any); reject the rest
+    at construction with the reason, not as an error code deep in the C ABI.  The reference's own configurations --
+    (32, 256, 512, 32) of the paper and (44, 256, 512, 22) of train.py:142-148 -- are inside."""
+    problems = []
+    if not 1 <= dim_neck <= 64:
+        problems.append(f"dim_neck={dim_neck}: the encoder BiLSTM kernel keeps W_hh in registers for 1..64 hidden units")
+    if dim_pre % 64 != 0 or dim_pre < 64:
+        problems.append(f"dim_pre={dim_pre}: the tensor-core LSTM kernel needs a multiple of 64 hidden units")
+    if (80 + dim_emb) % 8 != 0:
+        problems.append(f"dim_emb={dim_emb}: 80 + dim_emb input channels must be a multiple of 8 (16-byte TMA rows)")
+    if (2 * dim_neck + dim_emb) % 8 != 0:
+        problems.append(f"2*dim_neck + dim_emb = {2 * dim_neck + dim_emb}: the decoder input must be a multiple of 8 "
+                        "channels (16-byte TMA rows)")
+    if freq < 1:
+        problems.append(f"freq={freq}")
+    if problems:
+        raise ValueError("autoformer_b200.AutoVC supports dim_neck <= 64, dim_pre % 64 == 0, (80 + dim_emb) % 8 == 0, "
+                         "(2 dim_neck + dim_emb) % 8 == 0; got " + "; ".join(problems))
+
+
 class _Plan:
     def __init__(self, model, precision):
         sd = {k: v.detach() for k, v in model.state_dict().items()}
@@ -65,7 +86,7 @@ class _Plan:
         self.postnet = layers.Postnet(sd, "postnet", precision)
 
 
-class AutoVC(nn.Module):
+class AutoVC(layers.PlanOwner, nn.Module):
     """AutoVC generator (Qian et al. 2019) -- B200 kernels behind the reference API (factory/AutoVC.py:182-211).
 
     Extra, optional attributes (not in the reference): ``precision`` ("fp32" default: split-bf16
@@ -76,6 +97,7 @@ class AutoVC(nn.Module):
 
     def __init__(self, dim_neck, dim_emb, dim_pre, freq):
         super().__init__()
+        check_hyper_parameters(dim_neck, dim_emb, dim_pre, freq)
         self.encoder = Encoder(dim_neck, dim_emb, freq)
         self.decoder = Decoder(dim_neck, dim_emb, dim_pre)
         self.postnet = Postnet()
@@ -97,6 +119,7 @@ class AutoVC(nn.Module):
     def _run_postnet(self, plan, mel_op, mel, B, T, taps):
         return plan.postnet(mel_op, mel, B, T, taps)
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x, c_org, c_trg):
         if self.training and not self._warned_train:

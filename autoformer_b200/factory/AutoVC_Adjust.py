@@ -5,6 +5,7 @@ returns ``(c_org_adjusted, mel, mel_postnet, codes)`` (or the codes alone when `
 adjusted with ``x_target`` when ``isConvert`` is true, else with ``x`` itself (the training-time call)."""
 import torch
 
+from .. import ops
 from .Adjust import Adjust
 from .AutoVC import AutoVC
 
@@ -19,6 +20,7 @@ class AutoVC_Adjust(AutoVC):
         self.adjust.persistent_lstm = self.persistent_lstm
         return self.adjust(x, emb)
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x, c_org, c_trg, isConvert=False, x_target=None):
         c_org = self._adjust(x, c_org)                                          # AutoVC_Adjust.py:179

@@ -11,7 +11,7 @@ import torch.nn as nn
 from .. import layers, ops
 
 
-class LstmDV(nn.Module):
+class LstmDV(layers.PlanOwner, nn.Module):
     def __init__(self, num_layers=3, dim_input=80, dim_cell=768, dim_emb=256):
         super().__init__()
         self.lstm = nn.LSTM(input_size=dim_input, hidden_size=dim_cell, num_layers=num_layers, batch_first=True)
@@ -21,17 +21,17 @@ class LstmDV(nn.Module):
         self.persistent_lstm = True
         self._cache = layers.PlanCache()
 
-    def _plan(self):
-        def build():
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
-            return dict(lstm=layers.lstm_layers(sd, "lstm", self.num_layers, self.precision),
-                        w=sd["embedding.weight"].float().contiguous(), b=sd["embedding.bias"].float().contiguous())
-        return self._cache.get(self, (self.precision,), build)
+    def _build_plan(self):
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        return dict(lstm=layers.lstm_layers(sd, "lstm", self.num_layers, self.precision),
+                    w=sd["embedding.weight"].float().contiguous(), b=sd["embedding.bias"].float().contiguous())
 
-    @torch.no_grad()
-    def forward(self, x):
+    def _plan(self):
+        return self._cache.get(self, (self.precision,), self._build_plan)
+
+    def _last_hidden(self, plan, x):
+        """h_T of the top LSTM layer, fp32 (B, dim_cell)   (LstmDV.py:20-21: ``lstm_out[:, -1, :]``)."""
         ops._require_cuda(x)
-        plan = self._plan()
         x = x.contiguous().float()
         B, T, _ = x.shape
         h = ops.to_act(x, self.precision)
@@ -39,4 +39,10 @@ class LstmDV(nn.Module):
         for i, layer in enumerate(plan["lstm"]):
             last = i == self.num_layers - 1
             h = layer(h, B, T, h_last=h_last if last else None, persistent=self.persistent_lstm)
-        return ops.linear_l2norm(h_last, plan["w"], plan["b"])        # LstmDV.py:21-24
+        return h_last
+
+    @ops.on_device_of_input
+    @torch.no_grad()
+    def forward(self, x):
+        plan = self._plan()
+        return ops.linear_l2norm(self._last_hidden(plan, x), plan["w"], plan["b"])        # LstmDV.py:21-24

@@ -2,6 +2,7 @@
 target speaker codes both pass through ``Adjust``; returns ``(c_org_adjusted, mel, mel_postnet, codes)``."""
 import torch
 
+from .. import ops
 from .Adjust import Adjust
 from ._meta import MetaBase
 
@@ -18,6 +19,7 @@ class MetaConv_Adjust(MetaBase):
         self.adjust.precision = self.precision
         return self.adjust(x, emb)
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x, c_org, c_trg, isConvert=False, x_target=None):
         if self.ADJUST_SOURCE:

@@ -97,6 +97,7 @@ class AdaINMixin:
                 for m, s in target_feature]
         return torch.stack(rows).contiguous()
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x, c_org, c_trg, target_feature=None):
         ops._require_cuda(x)

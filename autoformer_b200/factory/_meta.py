@@ -213,7 +213,7 @@ class _Plan:
         self.postnet = layers.Postnet(sd, "postnet", precision)
 
 
-class MetaBase(nn.Module):
+class MetaBase(layers.PlanOwner, nn.Module):
     KIND = None
 
     def __init__(self, dim_neck, dim, dim_pre, freq):
@@ -238,6 +238,7 @@ class MetaBase(nn.Module):
     def _run_postnet(self, plan, mel_op, mel, B, T, taps):
         return plan.postnet(mel_op, mel, B, T, taps)
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x, c_org, c_trg):
         if self.training and not self._warned_train:

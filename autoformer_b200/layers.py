@@ -8,25 +8,74 @@ from .packing import TORCH_DTYPE
 
 
 class PlanCache:
-    """Re-pack weights only when a parameter/buffer was replaced or modified in place."""
+    """Re-pack weights only when a parameter/buffer was replaced, moved or modified.
+
+    The key holds, per tensor, (data_ptr, _version, device, shape, dtype) AND a content digest: in-place writes
+    through ``.data`` (``p.data.normal_()``, ``p.data.copy_(w)`` -- what the reference's MelGAN ``weights_init`` does,
+    melgan/modules.py:9-15) do not bump ``_version``, so the version counter alone would leave a stale plan and the
+    forward would silently run with old weights.  The digest is the 1- and 2-norm of every floating-point tensor,
+    computed on the tensors' device with two multi-tensor launches (``torch._foreach_norm``) and fetched with one small
+    copy per forward.  ``frozen = True`` (set by the models' ``freeze_weights()``) skips the digest for serving loops
+    that promise not to touch the weights; ``invalidate()`` forces a re-pack."""
 
     def __init__(self):
         self.key = None
         self.plan = None
+        self.frozen = False
 
     @staticmethod
-    def fingerprint(module, extra=()):
+    def fingerprint(module, extra=(), contents=True):
         items = []
+        by_dev = {}
         for t in list(module.parameters()) + list(module.buffers()):
-            items.append((t.data_ptr(), t._version, t.device))
-        return (tuple(items), tuple(extra))
+            items.append((t.data_ptr(), t._version, str(t.device), tuple(t.shape), str(t.dtype)))
+            if contents and t.numel() and t.is_floating_point():
+                by_dev.setdefault(t.device, []).append(t.detach())
+        digest = []
+        for ts in by_dev.values():
+            n1 = torch._foreach_norm(ts, 1)
+            n2 = torch._foreach_norm(ts, 2)
+            digest.append(tuple(torch.stack([v.double() for v in n1] + [v.double() for v in n2]).tolist()))
+        return (tuple(items), tuple(extra), tuple(digest))
+
+    def invalidate(self):
+        """Forget the packed plan: the next forward re-folds and re-packs from the module's current weights."""
+        self.key = None
+        self.plan = None
 
     def get(self, module, extra, builder):
-        key = self.fingerprint(module, extra)
+        if self.frozen and self.plan is not None and self.key is not None and self.key[1] == tuple(extra):
+            return self.plan
+        key = self.fingerprint(module, extra, True)
         if key != self.key:
             self.plan = builder()
             self.key = key
         return self.plan
+
+
+class PlanOwner:
+    """Mixin of the drop-in models: public control over the packed-weight cache (``self._cache``)."""
+
+    def invalidate(self):
+        """Drop the packed weights; call after editing parameters in a way torch cannot see (the content digest catches
+        ``.data`` writes by itself -- this is the explicit form, and the only one that works while frozen)."""
+        for m in self.modules():
+            c = getattr(m, "_cache", None)
+            if isinstance(c, PlanCache):
+                c.invalidate()
+
+    repack = invalidate
+
+    def freeze_weights(self, frozen=True):
+        """Serving mode: skip the per-forward weight digest (two small launches and one host sync).  The weights must
+        not change while frozen; ``invalidate()`` or ``freeze_weights(False)`` re-arms the check."""
+        for m in self.modules():
+            c = getattr(m, "_cache", None)
+            if isinstance(c, PlanCache):
+                c.frozen = frozen
+                if not frozen:
+                    c.invalidate()
+        return self
 
 
 def conv_bn_layer(sd, prefix, precision, act):

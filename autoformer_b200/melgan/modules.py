@@ -82,7 +82,7 @@ class _Plan:
         self.b_out = float(b(f"model.{idx + 2}")[0])
 
 
-class Audio2Mel(nn.Module):
+class Audio2Mel(layers.PlanOwner, nn.Module):
     """Drop-in ``Audio2Mel`` (melgan/modules.py:26-69): audio (B, 1, L) -> log10-mel (B, n_mel, L // hop).
 
     The STFT is an implicit-GEMM convolution on the tensor cores: the reflect-padded signal is viewed as rows of
@@ -127,6 +127,7 @@ class Audio2Mel(nn.Module):
             return dict(stft=stft, mel=mel, bins=bins, bins_pad=bins_pad)
         return self._cache.get(self, (self.precision,), build)
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, audio):
         ops._require_cuda(audio)
@@ -150,7 +151,7 @@ class Audio2Mel(nn.Module):
         return out.view(B, frames, self.n_mel_channels).transpose(1, 2).contiguous()
 
 
-class Generator(nn.Module):
+class Generator(layers.PlanOwner, nn.Module):
     def __init__(self, input_size, ngf, n_residual_layers):
         super().__init__()
         ratios = [8, 8, 2, 2]
@@ -177,6 +178,7 @@ class Generator(nn.Module):
     def _plan(self):
         return self._cache.get(self, (self.precision,), lambda: _Plan(self, self.precision))
 
+    @ops.on_device_of_input
     @torch.no_grad()
     def forward(self, x):
         """x (B, input_size, T) log-mel -> waveform (B, 1, hop_length * T)   (melgan/modules.py:129-130)."""

@@ -11,7 +11,24 @@ from .packing import KC, TORCH_DTYPE
 
 
 def _stream():
+    """The current stream of the CURRENT device.  Every op checks (``_require_cuda``) that its tensors live on that
+    device; the model classes enter ``torch.cuda.device(x.device)`` around their forward (``on_device_of_input``), so
+    a model on cuda:1 launches on cuda:1 whatever the caller's current device is."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device_of_input(forward):
+    """Decorator for a drop-in model's ``forward``: run it with the first tensor argument's device current (kernel
+    launches, tensor maps and function attributes are per device; the C ABI launches on the current device)."""
+    import functools
+
+    @functools.wraps(forward)
+    def wrapped(self, x, *args, **kwargs):
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return forward(self, x, *args, **kwargs)
+        return forward(self, x, *args, **kwargs)
+    return wrapped
 
 
 class Profiler:
@@ -63,9 +80,19 @@ _warned_not_resident = False
 
 
 def _require_cuda(*tensors):
+    """Every tensor of a launch must be a CUDA tensor on the current device (the one the launch goes to)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("autoformer_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{cur}: call the op under "
+                               "`with torch.cuda.device(t.device)` (the model classes do this themselves) and keep "
+                               "all tensors of a call on one device")
 
 
 def _dt(precision):
@@ -402,6 +429,21 @@ def linear_l2norm(h, w, bias):
     _lib.check(lib.avc_linear_l2norm(h.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, K, N, _stream()),
                "avc_linear_l2norm")
     return out
+
+
+def linear_rows(h, w, bias, want_raw=True, want_normed=False):
+    """Small fp32 Linear on [B][K] rows: returns (W h + b, (W h + b) / ||.||_2), None for the one not requested."""
+    lib = _lib.load()
+    _require_cuda(h, w, bias)
+    assert h.dtype == torch.float32 and h.is_contiguous() and w.is_contiguous() and bias.is_contiguous()
+    assert want_raw or want_normed
+    B, K = h.shape
+    N = w.shape[0]
+    raw = torch.empty(B, N, dtype=torch.float32, device=h.device) if want_raw else None
+    normed = torch.empty(B, N, dtype=torch.float32, device=h.device) if want_normed else None
+    _lib.check(lib.avc_linear_rows(h.data_ptr(), w.data_ptr(), bias.data_ptr(), raw.data_ptr() if want_raw else None,
+                                   normed.data_ptr() if want_normed else None, B, K, N, _stream()), "avc_linear_rows")
+    return raw, normed
 
 
 def to_act(x, precision, round_tf32=True):

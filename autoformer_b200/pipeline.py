@@ -5,7 +5,36 @@ the end, convert, trim the padding off again (util/evaluate.py:36-43 ``crop_mel`
 :85-92 trims ``mel_trans`` back), then vocode ``mel_trans.transpose(2, 1)`` (conversion.ipynb cell 14,
 util/evaluate.py:96-98).  Utterances of one call share the same T (callers bucket by exact length: zero padding
 changes the result)."""
+import numpy as np
 import torch
+
+
+def crop_mel(mel, len_crop, rng=None):
+    """The Evaluator's ``crop_mel`` (util/evaluate.py:36-50): numpy (T, 80) -> (tensor (1, len_crop, 80), pad_size).
+
+    T < len_crop: zero-pad at the END up to ``len_crop`` (pad_size = len_crop - T); T == len_crop: as is; T > len_crop:
+    a window of len_crop frames at a random offset in [0, T - len_crop) drawn from ``rng`` (default: numpy's global
+    generator, like the reference) and pad_size = 0."""
+    mel = np.asarray(mel)
+    T = mel.shape[0]
+    pad = 0
+    if T < len_crop:
+        pad = int(len_crop - T)
+        mel = np.pad(mel, [(0, pad)] + [(0, 0)] * (mel.ndim - 1), mode="constant", constant_values=0)
+    elif T > len_crop:
+        left = (rng or np.random).randint(0, T - len_crop)
+        mel = mel[left:left + len_crop]
+    return torch.from_numpy(np.ascontiguousarray(mel)).unsqueeze(0), pad
+
+
+@torch.no_grad()
+def convert_cropped(model, mel_np, emb_org, emb_trg, len_crop, trim=True, device="cuda"):
+    """One utterance through the Evaluator's recipe: ``crop_mel`` to ``len_crop`` -> ``model(x, c_org, c_trg)`` ->
+    trim the padded frames (util/evaluate.py:63-64, 83-92 with ``isPlay``).  Returns (1, T', 80)."""
+    x, pad = crop_mel(mel_np, len_crop)
+    _, mel_trans, _ = model(x.to(device).float(), emb_org, emb_trg)
+    mel_trans = mel_trans.squeeze(1)
+    return mel_trans[:, :len_crop - pad, :] if (trim and pad > 0) else mel_trans
 
 
 def pad_to_multiple(mel, multiple):

@@ -81,30 +81,36 @@ def gather_records(record, device=None):
     return torch.stack(out)
 
 
-def gather_outputs(local, total_count, ids, dst=0):
+def gather_outputs(local, total_count, ids, dst=0, chunk=4096):
     """Gather per-utterance outputs of equal shape to rank ``dst``: local (n_local, ...) with global ids ``ids``.
 
-    Chunked all_gather of padded blocks (ranks may hold different counts).  Returns the (total_count, ...) tensor on
+    Point-to-destination: only ``dst`` allocates the (total_count, ...) result and a receive block of at most ``chunk``
+    utterances; the other ranks send their rows in chunks and allocate nothing (an all_gather would hold
+    world x max_count x shape on EVERY rank -- 65,536 waveforms at 8 ranks do not fit).  Returns the full tensor on
     ``dst`` and None elsewhere.  Outside any timed region in bench.py."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         full = local.new_zeros((total_count,) + tuple(local.shape[1:]))
         full[torch.as_tensor(ids, device=local.device, dtype=torch.long)] = local
         return full
     world, rank = dist.get_world_size(), dist.get_rank()
-    counts = gather_records([float(len(ids))], device=local.device).long().flatten()
-    cap = int(counts.max().item())
-    pad_local = local.new_zeros((cap,) + tuple(local.shape[1:]))
-    pad_local[:len(ids)] = local
-    pad_ids = torch.full((cap,), -1, dtype=torch.long, device=local.device)
-    pad_ids[:len(ids)] = torch.as_tensor(ids, dtype=torch.long, device=local.device)
-    all_vals = [torch.zeros_like(pad_local) for _ in range(world)]
-    all_ids = [torch.zeros_like(pad_ids) for _ in range(world)]
-    dist.all_gather(all_vals, pad_local)
-    dist.all_gather(all_ids, pad_ids)
+    counts = [int(c) for c in gather_records([float(len(ids))], device=local.device).flatten().tolist()]
+    ids_t = torch.as_tensor(ids, dtype=torch.long, device=local.device)
+    tail = tuple(local.shape[1:])
     if rank != dst:
+        for s in range(0, counts[rank], chunk):
+            dist.send(ids_t[s:s + chunk].contiguous(), dst)
+            dist.send(local[s:s + chunk].contiguous(), dst)
         return None
-    full = local.new_zeros((total_count,) + tuple(local.shape[1:]))
-    for v, i in zip(all_vals, all_ids):
-        keep = i >= 0
-        full[i[keep]] = v[keep]
+    full = local.new_zeros((total_count,) + tail)
+    full[ids_t] = local
+    for src in range(world):
+        if src == dst:
+            continue
+        for s in range(0, counts[src], chunk):
+            n = min(chunk, counts[src] - s)
+            rid = torch.empty(n, dtype=torch.long, device=local.device)
+            rv = local.new_empty((n,) + tail)
+            dist.recv(rid, src)
+            dist.recv(rv, src)
+            full[rid] = rv
     return full

@@ -244,6 +244,16 @@ int avc_linear_l2norm(const float* h, const float* w, const float* bias, float* 
                       void* stream);
 
 /*
+ * Small fp32 Linear on a handful of rows with both forms of the result: e = W h + b to out_raw and / or e / ||e||_2 to
+ * out_normed (either may be NULL).  The classifier twin of the speaker embedder (make_data/factory/LstmDV.py:19-25)
+ * needs the un-normalised embedding for its `output` head (`predictions = output(embeds)`, :24) next to the d-vector
+ * (`embeds / ||embeds||`, :22-23); the head itself is a second call with out_normed = NULL.
+ *   h [B][K], W [N][K], b [N], outputs [B][N]; K multiple of 4, N <= 1024.
+ */
+int avc_linear_rows(const float* h, const float* w, const float* bias, float* out_raw, float* out_normed, int B, int K,
+                    int N, void* stream);
+
+/*
  * in [B][C][L] fp32 (channels-first, the reference's (B, 80, T) mel layout) -> out [B][L + 2*pad][C'] channels-last in
  * out_dtype (C' = C, or 2C for split bf16), with `pad` reflected rows each side (nn.ReflectionPad1d(3) in front of the
  * MelGAN stem, melgan/modules.py:96; `mel.transpose` at conversion.ipynb cell 14).  C multiple of 4, L > pad.

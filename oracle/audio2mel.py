@@ -1,11 +1,13 @@
 """CPU oracle for ``Audio2Mel`` (melgan/modules.py:26-69).  Test infrastructure.
 
-PARITY PARTLY UNPINNED: the reference's ``Audio2Mel`` cannot run in this container -- it builds ``mel_basis`` with
-librosa (absent, no network) and calls ``torch.stft`` without ``return_complex``, which torch >= 2.0 rejects -- so no
-golden vector of the reference itself exists for this row.  What IS pinned: the filter bank (librosa 0.8's published
-``filters.mel`` algorithm, restated below as plain loops) agrees to 1e-9 with the librosa-compatible
-``transformers.audio_utils.mel_filter_bank`` (tests/test_audio2mel.py), and the STFT is torch's own ``torch.stft``, the
-function the reference calls, with the reference's arguments.
+Pinned (round 2) against the reference's own ``Audio2Mel`` class run through two shims
+(``oracle/make_golden.py::golden_audio2mel`` -> tests/golden/audio2mel_*.npz): as written the class cannot run on this
+container's stack -- it builds ``mel_basis`` with librosa (absent, no network) and calls ``torch.stft`` without
+``return_complex``, which torch >= 2.0 rejects -- so (1) ``librosa.filters.mel`` is supplied by the restated filter
+bank below and (2) ``torch.stft`` is wrapped to return the pre-2.0 real view.  Padding, framing, window, magnitude, mel
+projection and log10 clamp are the reference's code.  NOT pinned by the reference: the filter bank itself (librosa
+0.8's published ``filters.mel`` algorithm, restated as plain loops); it agrees to 1e-9 with the librosa-compatible
+``transformers.audio_utils.mel_filter_bank`` (tests/test_audio2mel.py).
 """
 import math
 

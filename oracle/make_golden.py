@@ -148,6 +148,90 @@ def golden_adain(ref, name, cls_name, args, B, T, wseed, xseed):
     print(name, "|post own|", float(own[1].norm()), "|post styled|", float(styled[1].norm()), rec["features"].tolist())
 
 
+def golden_lstmdv_twin(name, B, T, wseed, xseed):
+    """make_data/factory/LstmDV.py (the classifier twin the Evaluator calls): (predictions, d_vec)."""
+    import importlib.util
+    path = os.path.join(ref_import.REFERENCE_ROOT, "make_data", "factory", "LstmDV.py")
+    spec = importlib.util.spec_from_file_location("_ref_make_data_lstmdv", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    model = mod.LstmDV().eval()
+    sd = seeded_state_dict(model.state_dict(), wseed, lstm_gain=1.5)
+    model.load_state_dict(sd)
+    x = synthetic_mel(B, T, xseed)
+    with torch.no_grad():
+        pred, dv = model(x)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cls="make_data.LstmDV", B=B, T=T, wseed=wseed, xseed=xseed,
+                        lstm_gain=1.5, predictions=pred.numpy(), d_vec=dv.numpy())
+    print(name, tuple(pred.shape), tuple(dv.shape))
+
+
+def golden_audio2mel(ref, name, B, L, seed):
+    """The reference's own Audio2Mel (melgan/modules.py:26-69) run through two shims, because as written it cannot
+    run on this container's stack: (1) ``librosa.filters.mel`` (librosa absent) is supplied by the restated filter bank
+    ``oracle.audio2mel.librosa_mel`` -- itself cross-checked against transformers' librosa-compatible implementation;
+    (2) ``torch.stft`` is wrapped to pass ``return_complex=True`` and hand back ``view_as_real`` (the pre-2.0 return
+    convention the reference unbinds, :65).  Everything else -- padding, framing, window, magnitude, mel projection,
+    log10 clamp -- is the reference's code."""
+    import importlib
+    from .audio2mel import librosa_mel
+    mods = importlib.import_module("melgan.modules")
+    mods.librosa_mel_fn = lambda sr, n_fft, n_mels, fmin, fmax: librosa_mel(sr, n_fft, n_mels, fmin, fmax).numpy()
+    real_stft = torch.stft
+
+    def stft_pre2(*a, **k):
+        k["return_complex"] = True
+        return torch.view_as_real(real_stft(*a, **k))
+    model = mods.Audio2Mel().eval()
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(L) / 22050.0
+    tones = sum(a * torch.sin(2 * torch.pi * f * t + ph) for a, f, ph in ((0.4, 220.0, 0.1), (0.2, 1760.0, 1.0),
+                                                                            (0.1, 5200.0, 2.0)))
+    audio = (tones.unsqueeze(0) + 0.05 * torch.randn(B, L, generator=g)).unsqueeze(1)
+    torch.stft = stft_pre2
+    try:
+        with torch.no_grad():
+            mel = model(audio)
+    finally:
+        torch.stft = real_stft
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cls="Audio2Mel", B=B, L=L, seed=seed,
+                        audio=audio.numpy().astype(np.float32), mel=mel.numpy())
+    print(name, tuple(mel.shape), "range", float(mel.min()), float(mel.max()))
+
+
+def golden_evaluator(ref, name, T_src, T_trg, wseed, xseed):
+    """The reference's Evaluator (util/evaluate.py:36-98) on synthetic .npy utterances shorter than ``len_crop``:
+    ``get_trans_mel(..., isPlay=True)`` = crop_mel (zero-pad to 176) -> AutoVC(44,256,512,22) -> trim."""
+    import importlib
+    import tempfile
+    import types
+    ev = importlib.import_module("util.evaluate")
+    model = ref.AutoVC(44, 256, 512, 22).eval()
+    sd = seeded_state_dict(model.state_dict(), wseed)
+    model.load_state_dict(sd)
+    src = synthetic_mel(1, T_src, xseed)[0].numpy()
+    trg = synthetic_mel(1, T_trg, xseed + 1)[0].numpy()
+    e_src = synthetic_speaker(1, xseed, "org")[0].numpy()
+    e_trg = synthetic_speaker(1, xseed, "trg")[0].numpy()
+    with tempfile.TemporaryDirectory() as root:
+        np.save(os.path.join(root, "a.npy"), src)
+        np.save(os.path.join(root, "b.npy"), trg)
+        cfg = types.SimpleNamespace(root=root, num_speaker=2, batch_size=1, max_uttr_idx=4, erroment_num=1, len_crop=176,
+                                    device="cpu", all_speaker=["p1", "p2"], embedder=None,
+                                    metadata=[["p1", e_src, "a.npy"], ["p2", e_trg, "b.npy"]])
+        E = ev.Evaluator.__new__(ev.Evaluator)                    # __init__ loads a vocoder checkpoint from disk (:23)
+        for k, v in vars(cfg).items():
+            setattr(E, k, v)
+        E.metadata = E.build_metadata(cfg.metadata)
+        with torch.no_grad():
+            ms, mt, trans_play = E.get_trans_mel(model, 0, 1, 2, False, False, isPlay=True)
+            _, _, trans_full = E.get_trans_mel(model, 0, 1, 2, False, False, isPlay=False)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), cls="Evaluator", T_src=T_src, T_trg=T_trg, wseed=wseed,
+                        xseed=xseed, src=src, trg=trg, e_src=e_src, e_trg=e_trg, mel_source=ms.numpy(),
+                        mel_target=mt.numpy(), mel_trans_play=trans_play.numpy(), mel_trans_full=trans_full.numpy())
+    print(name, tuple(ms.shape), tuple(mt.shape), tuple(trans_play.shape), tuple(trans_full.shape))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load()
@@ -166,7 +250,19 @@ def main():
     golden_adain(ref, "autovc2_b2_t64", "AutoVC2", (32, 256, 512, 32), 2, 64, 16, 17)
     golden_adain(ref, "metapool2_b1_t176", "MetaPool2", (44, 256, 512, 22), 1, 176, 18, 19)
     golden_adain(ref, "metaconv2_b1_t176", "MetaConv2", (44, 256, 512, 22), 1, 176, 20, 21)
+    round2(ref)
+
+
+def round2(ref):
+    golden_lstmdv_twin("lstmdv_twin_b2_t100", 2, 100, 22, 23)
+    golden_audio2mel(ref, "audio2mel_b2_l5120", 2, 5120, 24)
+    golden_audio2mel(ref, "audio2mel_b1_l2381", 1, 2381, 25)
+    golden_evaluator(ref, "evaluator_autovcR_t100_t150", 100, 150, 26, 27)
 
 
 if __name__ == "__main__":
+    if "--round2" in sys.argv:          # only the fixtures added in round 2 (the earlier ones are unchanged)
+        os.makedirs(OUT, exist_ok=True)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        sys.exit(round2(ref_import.load()))
     sys.exit(main())

@@ -69,6 +69,14 @@ def lstmdv_template():
     return sd
 
 
+def lstmdv_twin_template(num_classes=256):
+    """make_data/factory/LstmDV.py:8-16: the embedder plus the ``output`` classifier head."""
+    sd = lstmdv_template()
+    sd["output.weight"] = _z(num_classes, 256)
+    sd["output.bias"] = _z(num_classes)
+    return sd
+
+
 def _wn(sd, prefix, w_shape, bias_len):
     sd[f"{prefix}.bias"] = _z(bias_len)
     sd[f"{prefix}.weight_g"] = _z(w_shape[0], 1, 1)
