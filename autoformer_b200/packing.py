@@ -66,6 +66,22 @@ def act_to_float(buf: torch.Tensor, precision: str) -> torch.Tensor:
     return buf.float()
 
 
+FP16_MAX = 65504.0
+
+
+def fp16_overflow_margin(taps) -> float:
+    """fp16 range / largest |activation| over a model's stage taps (``model.collect_taps = True``).  The kernels'
+    fp16 stores SATURATE at +-65504 (csrc/avc_ptx.cuh: sat_f16) so an out-of-range activation costs accuracy instead
+    of poisoning the utterance with inf / NaN -- which also makes it silent.  A margin <= 1 means some activation
+    reached the limit: the "fp16x2" precision is not valid for that checkpoint, use "fp32" (split bf16, fp32 range).
+    Trained checkpoints should be probed once with this before serving in fp16x2."""
+    peak = 0.0
+    for v in taps.values():
+        if torch.is_tensor(v) and v.numel():
+            peak = max(peak, float(v.detach().abs().max()))
+    return float("inf") if peak == 0.0 else FP16_MAX / peak
+
+
 def round_tf32(t: torch.Tensor) -> torch.Tensor:
     """cvt.rna.tf32.f32 on the host: keep 10 mantissa bits, round to nearest, ties away from zero."""
     assert t.dtype == torch.float32
