@@ -17,7 +17,7 @@ EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm",
            "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_linear_rows", "avc_transpose_pad",
            "avc_conv_to_mono_tanh", "avc_gn_stats", "avc_gn_pool_residual", "avc_gn_apply", "avc_patchify",
            "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes", "avc_global_stats", "avc_adain", "avc_audio_frames",
-           "avc_complex_mag", "avc_resblock"]
+           "avc_complex_mag", "avc_resblock", "avc_resblock2"]
 
 
 MAX_SOURCES = 4
@@ -60,6 +60,7 @@ class GemmDesc(ctypes.Structure):
         ("block_n", ctypes.c_int),
         ("cta_group", ctypes.c_int),
         ("debug_clk", ctypes.c_void_p),
+        ("out_raw_dtype", ctypes.c_int),
     ]
 
 
@@ -131,6 +132,29 @@ class ResblockDesc(ctypes.Structure):
     ]
 
 
+class Resblock2Desc(ctypes.Structure):
+    """struct avc_resblock2_desc"""
+    _fields_ = [
+        ("x", ctypes.c_void_p),
+        ("x_ld", ctypes.c_longlong),
+        ("w", ctypes.c_void_p),
+        ("bias3", ctypes.c_void_p),
+        ("bias1", ctypes.c_void_p),
+        ("B", ctypes.c_int),
+        ("L", ctypes.c_int),
+        ("C", ctypes.c_int),
+        ("dilation", ctypes.c_int),
+        ("y", ctypes.c_void_p),
+        ("y_ld", ctypes.c_longlong),
+        ("y_rows_per_utt", ctypes.c_int),
+        ("y_row0", ctypes.c_int),
+        ("y_reflect", ctypes.c_int),
+        ("y_act", ctypes.c_int),
+        ("out2", ctypes.c_void_p),
+        ("out2_ld", ctypes.c_longlong),
+    ]
+
+
 _lib = None
 
 
@@ -155,6 +179,8 @@ def load():
     lib.avc_lstm_seq_ws.restype = ctypes.c_int
     lib.avc_resblock.argtypes = [ctypes.POINTER(ResblockDesc), ctypes.c_void_p]
     lib.avc_resblock.restype = ctypes.c_int
+    lib.avc_resblock2.argtypes = [ctypes.POINTER(Resblock2Desc), ctypes.c_void_p]
+    lib.avc_resblock2.restype = ctypes.c_int
     lib.avc_bilstm_small.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_void_p]

@@ -37,7 +37,8 @@ struct alignas(64) GemmParams {
   int phases, cs;        // N = phases * cs; output time = phases * t + n / cs
   void* out;
   long long out_ld;
-  int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16, 3 fp16
+  int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16, 3 fp16, 4 split fp16
+  int raw_mode;           // format of out_raw (same codes)
   uint32_t fmt_xor;       // kIdescF16Xor when the 16-bit operands are fp16
   void* out_raw;
   long long out_raw_ld;
@@ -81,6 +82,10 @@ __device__ __forceinline__ void store4(void* base, int mode, int round, long lon
     __nv_bfloat16* ptr = static_cast<__nv_bfloat16*>(base) + row * ld + c;
     *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
     *reinterpret_cast<uint2*>(ptr + cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+  } else if (mode == 4) {
+    __half* ptr = static_cast<__half*>(base) + row * ld + c;
+    *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]));
+    *reinterpret_cast<uint2*>(ptr + cs) = make_uint2(pack_f16(f16_lo(v[0]), f16_lo(v[1])), pack_f16(f16_lo(v[2]), f16_lo(v[3])));
   } else if (mode == 1) {
     uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + row * ld + c) = pk;
@@ -173,7 +178,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
             for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
             const long long off = ((long long)b * p.out_rows_per_utt + p.out_row0 + t) * p.out_ld + n;
             __nv_bfloat16* ptr = static_cast<__nv_bfloat16*>(p.out) + off;      // 2-byte elements in all three formats
-            const bool f16 = p.out_mode == 3;
+            const bool f16 = p.out_mode >= 3;
             const uint2 hi = f16 ? make_uint2(pack_f16(o[0], o[1]), pack_f16(o[2], o[3]))
                                  : make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
             if (ok) *reinterpret_cast<uint2*>(ptr) = hi;
@@ -182,6 +187,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
 #pragma unroll
               for (int e = 0; e < 4; ++e) lo[e] = o[e] - __bfloat162float(__float2bfloat16_rn(o[e]));
               if (ok) *reinterpret_cast<uint2*>(ptr + p.cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+            } else if (p.out_mode == 4) {
+              if (ok) *reinterpret_cast<uint2*>(ptr + p.cs) =
+                  make_uint2(pack_f16(f16_lo(o[0]), f16_lo(o[1])), pack_f16(f16_lo(o[2]), f16_lo(o[3])));
             }
           } else {
             const long long lr = (long long)b * p.T + t;
@@ -214,7 +222,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
             rv = __ldg(reinterpret_cast<const float4*>(p.residual + lr * p.res_ld + c));
             if (!res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
           }
-          if (p.out_raw) store4(p.out_raw, p.out_mode, p.out_round, lr, p.out_raw_ld, c, p.cs, o);
+          if (p.out_raw) store4(p.out_raw, p.raw_mode, p.out_round, lr, p.out_raw_ld, c, p.cs, o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
           if (has_res && res_after) { o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w; }
@@ -512,9 +520,13 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   p.out_rows_per_utt = d->out_rows_per_utt;
   p.out_row0 = d->out_row0;
   p.out_mode = d->out_dtype;
-  AVC_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 3, "avc_conv_gemm: out_dtype %d", d->out_dtype);
+  AVC_REQUIRE(d->out_dtype >= 0 && d->out_dtype <= 4, "avc_conv_gemm: out_dtype %d", d->out_dtype);
+  // out_raw_dtype = 0 keeps the historical meaning "same format as out" (fp32 raw copies go through out2)
+  p.raw_mode = d->out_raw_dtype > 0 ? d->out_raw_dtype : d->out_dtype;
+  AVC_REQUIRE(p.raw_mode >= 0 && p.raw_mode <= 4, "avc_conv_gemm: out_raw_dtype %d", d->out_raw_dtype);
   p.fmt_xor = d->dtype == AVC_DTYPE_F16 ? kIdescF16Xor : 0u;
-  const long long min_ld = d->out_dtype == 2 ? 2LL * p.cs : p.cs;
+  const long long min_ld = (d->out_dtype == 2 || d->out_dtype == 4) ? 2LL * p.cs : p.cs;
+  const long long min_raw_ld = (p.raw_mode == 2 || p.raw_mode == 4) ? 2LL * p.cs : p.cs;
   p.out_round = d->out_round_tf32;
   p.out_reflect = d->out_reflect;
   p.out_raw = d->out_raw;
@@ -532,7 +544,7 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
     AVC_REQUIRE(d->out_reflect < t_out, "avc_conv_gemm: reflect %d needs more than that many output frames",
                 d->out_reflect);
   }
-  if (d->out_raw) AVC_REQUIRE(d->out_raw_ld % 4 == 0 && d->out_raw_ld >= min_ld, "avc_conv_gemm: out_raw_ld");
+  if (d->out_raw) AVC_REQUIRE(d->out_raw_ld % 4 == 0 && d->out_raw_ld >= min_raw_ld, "avc_conv_gemm: out_raw_ld");
   if (d->out2) AVC_REQUIRE(d->out2_ld % 4 == 0 && d->out2_ld >= p.cs, "avc_conv_gemm: out2_ld");
   if (d->residual) AVC_REQUIRE(d->res_ld % 4 == 0 && d->res_ld >= p.cs, "avc_conv_gemm: res_ld");
 

@@ -235,6 +235,11 @@ __device__ __forceinline__ void store1(void* out, int mode, int round, long long
     __nv_bfloat16* p = static_cast<__nv_bfloat16*>(out) + row * ld + c;
     p[0] = hi;
     p[C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  } else if (mode == 4) {
+    const __half hi = __float2half_rn(sat_f16(v));
+    __half* p = static_cast<__half*>(out) + row * ld + c;
+    p[0] = hi;
+    p[C] = __float2half_rn(f16_lo(v));
   } else if (mode == 1) {
     static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
   } else if (mode == 3) {
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restr
     tile[i][threadIdx.x] = (c < C && l < L) ? __ldg(in + ((long long)b * C + c) * L + l) : 0.0f;
   }
   __syncthreads();
-  const int ld = mode == 2 ? 2 * C : C;
+  const int ld = (mode == 2 || mode == 4) ? 2 * C : C;
   const long long base = (long long)b * (L + 2 * pad) + pad;
   for (int i = threadIdx.y; i < 32; i += 8) {          // coalesced along C
     const int l = l0 + i, c = c0 + threadIdx.x;
@@ -396,7 +401,7 @@ extern "C" int avc_transpose_pad(const float* in, void* out, int B, int C, int L
   AVC_REQUIRE(in && out, "avc_transpose_pad: null buffer");
   AVC_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && L > pad && pad >= 0 && B < 65536, "avc_transpose_pad: bad shape B=%d C=%d L=%d pad=%d",
               B, C, L, pad);
-  AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 3, "avc_transpose_pad: out_dtype %d", out_dtype);
+  AVC_REQUIRE(out_dtype >= 0 && out_dtype <= 4, "avc_transpose_pad: out_dtype %d", out_dtype);
   dim3 grid((L + 31) / 32, (C + 31) / 32, B);
   transpose_pad_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, C, L, pad, out_dtype, out_round_tf32);
   AVC_CHECK_CUDA(cudaGetLastError());

@@ -244,5 +244,11 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   __half2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// second term of the two-term fp16 form v ~ hi + lo, hi = fp16(v): what fp16(v) lost (exact in fp32, ~2^-22 relative after
+// its own rounding; values below fp16's subnormal step flush towards zero, which costs < 6e-8 absolute)
+__device__ __forceinline__ float f16_lo(float v) {
+  const float s = sat_f16(v);
+  return s - __half2float(__float2half_rn(s));
+}
 
 }  // namespace avc

@@ -1,4 +1,5 @@
-// Element / 4-element stores into the operand formats: 0 fp32 [TF32-rounded], 1 bf16, 2 split bf16 [hi | lo], 3 fp16.
+// Element / 4-element stores into the operand formats: 0 fp32 [TF32-rounded], 1 bf16, 2 split bf16 [hi | lo], 3 fp16,
+// 4 split fp16 [hi | lo] (two fp16 terms, ~2^-22: the MelGAN residual stream of the "fp16s" precision).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -14,6 +15,11 @@ __device__ __forceinline__ void store_op1(void* out, int mode, int round, long l
     __nv_bfloat16* p = static_cast<__nv_bfloat16*>(out) + row * ld + c;
     p[0] = hi;
     p[C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  } else if (mode == 4) {
+    const __half hi = __float2half_rn(sat_f16(v));
+    __half* p = static_cast<__half*>(out) + row * ld + c;
+    p[0] = hi;
+    p[C] = __float2half_rn(sat_f16(v) - __half2float(hi));
   } else if (mode == 1) {
     static_cast<__nv_bfloat16*>(out)[row * ld + c] = __float2bfloat16_rn(v);
   } else if (mode == 3) {
@@ -34,6 +40,10 @@ __device__ __forceinline__ void store_op4(void* out, int mode, int round, long l
     const float lw = v.w - __bfloat162float(__float2bfloat16_rn(v.w));
     *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
     *reinterpret_cast<uint2*>(p + C) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
+  } else if (mode == 4) {
+    __half* p = static_cast<__half*>(out) + row * ld + c;
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16(v.x, v.y), pack_f16(v.z, v.w));
+    *reinterpret_cast<uint2*>(p + C) = make_uint2(pack_f16(f16_lo(v.x), f16_lo(v.y)), pack_f16(f16_lo(v.z), f16_lo(v.w)));
   } else if (mode == 1) {
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + row * ld + c) =
         make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
@@ -46,6 +56,6 @@ __device__ __forceinline__ void store_op4(void* out, int mode, int round, long l
   }
 }
 
-__host__ __device__ inline long long op_ld(int C, int mode) { return mode == 2 ? 2LL * C : C; }
+__host__ __device__ inline long long op_ld(int C, int mode) { return (mode == 2 || mode == 4) ? 2LL * C : C; }
 
 }  // namespace avc

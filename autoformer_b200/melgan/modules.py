@@ -82,6 +82,59 @@ class _Plan:
         self.b_out = float(b(f"model.{idx + 2}")[0])
 
 
+class _PlanF16s:
+    """Packed layers of the "fp16s" precision (round 2).  Tensor formats, chosen per role from
+    scripts/melgan_precision_study.py (waveform rel-L2 <= 5.3e-4 over six weight seeds, against 1.2e-3 when every
+    activation is ONE fp16 value):
+      two fp16 terms (hi | lo)  the residual stream x, the ConvTranspose operands, the ResnetBlock intermediate
+      one fp16 value            LeakyReLU(x), the operand of the dilated k3 convolutions (60 % of a block's MMAs)
+    Weights are two fp16 terms everywhere.  Stages of 32 / 64 channels run each ResnetBlock as ONE kernel
+    (avc_resblock2) that reads the raw stream and writes its output, nothing else."""
+
+    def __init__(self, gen):
+        sd = {k: v.detach() for k, v in gen.state_dict().items()}
+        W = lambda p: packing.fold_weight_norm(sd[p + ".weight_g"], sd[p + ".weight_v"])
+        b = lambda p: sd[p + ".bias"].float()
+        self.precision = "fp16s"
+        self.stem = ops.ConvGemm(*packing.pack_conv(W("model.1"), b("model.1"), "fp16s"), tap_t0=[0], act="lrelu",
+                                 tag="melgan_conv")
+        self.stages = []
+        idx = 2
+        for r in gen.ratios:
+            wt = W(f"model.{idx + 1}")                                   # (C_in, C_out, 2r)
+            c_out = wt.shape[1]
+            w3 = packing.conv_transpose_as_conv(wt, r, r // 2 + r % 2)
+            packed_up = packing.pack_conv(w3, b(f"model.{idx + 1}").repeat(r), "fp16s")
+            # a fused stage wants the raw stream only; a layer-wise stage wants LeakyReLU(x) (one fp16) plus the raw x
+            up_raw = ops.ConvGemm(*packed_up, tap_t0=[-1], act="none", tag="melgan_up")
+            up_act = ops.ConvGemm(*packed_up, tap_t0=[-1], act="lrelu", tag="melgan_up")
+            blocks = []
+            for j in range(gen.n_residual_layers):
+                p = f"model.{idx + 2 + j}"
+                d = 3 ** j
+                c3 = ops.ConvGemm(*packing.pack_conv(W(p + ".block.2"), b(p + ".block.2"), "fp16x2"), tap_t0=[0],
+                                  tap_dt=[d], act="lrelu", tag="melgan_conv")
+                k1 = ops.ConvGemm(*packing.pack_conv_sources([W(p + ".block.4"), W(p + ".shortcut")],
+                                                             b(p + ".block.4") + b(p + ".shortcut"), "fp16s"),
+                                  tap_t0=[0, 0], act="lrelu", tag="melgan_conv")
+                fused = None
+                if c_out in packing.RESBLOCK_CHANNELS:
+                    fused = ops.Resblock2(*packing.pack_resblock2(W(p + ".block.2"), b(p + ".block.2"), W(p + ".block.4"),
+                                                                  b(p + ".block.4"), W(p + ".shortcut"),
+                                                                  b(p + ".shortcut")), dilation=d)
+                blocks.append((d, c3, k1, fused))
+            self.stages.append((r, c_out, up_raw, up_act, blocks))
+            idx += 2 + gen.n_residual_layers
+        wf = W(f"model.{idx + 2}")                                        # (1, ngf, 7)
+        self.w_out = wf[0].t().contiguous().float()                      # [K][C]
+        self.b_out = float(b(f"model.{idx + 2}")[0])
+
+
+def _inv_lrelu(a):
+    """y from LeakyReLU(y) (slope 0.2): exact up to one fp32 rounding.  Used only for the parity taps."""
+    return torch.where(a >= 0, a, a / 0.2)
+
+
 class Audio2Mel(layers.PlanOwner, nn.Module):
     """Drop-in ``Audio2Mel`` (melgan/modules.py:26-69): audio (B, 1, L) -> log10-mel (B, n_mel, L // hop).
 
@@ -176,7 +229,74 @@ class Generator(layers.PlanOwner, nn.Module):
         self._cache = layers.PlanCache()
 
     def _plan(self):
-        return self._cache.get(self, (self.precision,), lambda: _Plan(self, self.precision))
+        build = (lambda: _PlanF16s(self)) if self.precision == "fp16s" else (lambda: _Plan(self, self.precision))
+        return self._cache.get(self, (self.precision,), build)
+
+    def _forward_f16s(self, plan, x):
+        """The "fp16s" data flow (see _PlanF16s): raw residual stream as two fp16 terms, one tensor between kernels."""
+        B, _, T = x.shape
+        dev = x.device
+        P = "fp16s"
+        taps = self.taps if self.collect_taps else None
+        m0 = ops.transpose_pad(x, 3, P)                                   # model.0 + layout change
+        cur = ops.alloc_act(B, T, plan.stem.meta["N"], P, dev)
+        plan.stem(m0, B, T, out=cur)                                      # model.1 (+ model.2's LeakyReLU)
+        L = T
+        final = None
+        n_stage = len(plan.stages)
+        for si, (r, C, up_raw, up_act, blocks) in enumerate(plan.stages):
+            Lr = r * L
+            last_stage = si + 1 == n_stage
+            d0 = blocks[0][0]
+            if self.fuse_resblocks and ops.Resblock2.eligible(C, Lr):
+                xs = ops.alloc_act(B, Lr + 2 * d0, C, P, dev)
+                up_raw(cur, B, L, out=xs, out_row0=d0, reflect=d0, phases=r)            # ConvTranspose1d: raw stream + halo
+                if taps is not None:
+                    taps[f"up{si}"] = packing.act_to_float(xs[:, d0:d0 + Lr], P)
+                for j, (d, _, _, fused) in enumerate(blocks):
+                    if j + 1 < len(blocks):
+                        dn = blocks[j + 1][0]
+                        ys = ops.alloc_act(B, Lr + 2 * dn, C, P, dev)
+                        fused(xs, B, Lr, y=ys, y_row0=dn, y_reflect=dn)
+                        xs = ys
+                    elif not last_stage:
+                        cur = ops.alloc_act(B, Lr, C, P, dev)
+                        fused(xs, B, Lr, y=cur, y_act=True)                              # + the next model.{i} LeakyReLU
+                        if taps is not None:
+                            taps[f"stage{si}"] = _inv_lrelu(packing.act_to_float(cur, P))
+                    else:
+                        final = torch.empty(B * Lr, C, dtype=torch.float32, device=dev)
+                        fused(xs, B, Lr, out2=final)
+                        if taps is not None:
+                            taps[f"stage{si}"] = _inv_lrelu(final.view(B, Lr, C))
+            else:
+                x_raw = ops.alloc_act(B, Lr, C, P, dev)
+                xa = ops.alloc_act(B, Lr + 2 * d0, C, "f16", dev)
+                up_act(cur, B, L, out=xa, out_row0=d0, reflect=d0, out_raw=x_raw, phases=r, out_fmt="f16", raw_fmt=P)
+                if taps is not None:
+                    taps[f"up{si}"] = packing.act_to_float(x_raw, P)
+                for j, (d, c3, k1, _) in enumerate(blocks):
+                    h1 = ops.alloc_act(B, Lr, C, P, dev)
+                    c3(xa, B, Lr, out=h1, out_fmt=P)                                     # block.0-3 (one fp16 operand in)
+                    if j + 1 < len(blocks):
+                        dn = blocks[j + 1][0]
+                        y_raw = ops.alloc_act(B, Lr, C, P, dev)
+                        ya = ops.alloc_act(B, Lr + 2 * dn, C, "f16", dev)
+                        k1([h1, x_raw], B, Lr, out=ya, out_row0=dn, reflect=dn, out_raw=y_raw, out_fmt="f16", raw_fmt=P)
+                        x_raw, xa = y_raw, ya
+                    elif not last_stage:
+                        cur = ops.alloc_act(B, Lr, C, P, dev)
+                        k1([h1, x_raw], B, Lr, out=cur)                                  # block.4 + shortcut + next LeakyReLU
+                        if taps is not None:
+                            taps[f"stage{si}"] = _inv_lrelu(packing.act_to_float(cur, P))
+                    else:
+                        final = torch.empty(B * Lr, C, dtype=torch.float32, device=dev)
+                        k1([h1, x_raw], B, Lr, out2=final)
+                        if taps is not None:
+                            taps[f"stage{si}"] = _inv_lrelu(final.view(B, Lr, C))
+            L = Lr
+        wav = ops.conv_to_mono_tanh(final.view(B, L, -1), plan.w_out, plan.b_out)      # model.22-25
+        return wav.unsqueeze(1)
 
     @ops.on_device_of_input
     @torch.no_grad()
@@ -185,6 +305,10 @@ class Generator(layers.PlanOwner, nn.Module):
         ops._require_cuda(x)
         plan = self._plan()
         prec = plan.precision
+        if prec == "fp16s":
+            if self.collect_taps:
+                self.taps.clear()
+            return self._forward_f16s(plan, x.contiguous().float())
         x = x.contiguous().float()
         B, _, T = x.shape
         dev = x.device

@@ -96,7 +96,9 @@ def _require_cuda(*tensors):
 
 
 def _dt(precision):
-    return {"tf32": _lib.DTYPE_TF32, "bf16": _lib.DTYPE_BF16, "fp32": 2, "fp16x2": 3}[precision]
+    """Operand-format code of an activation buffer (include/avc_b200.h out_dtype): 0 fp32/TF32, 1 bf16, 2 split bf16,
+    3 fp16, 4 split fp16."""
+    return {"tf32": _lib.DTYPE_TF32, "bf16": _lib.DTYPE_BF16, "fp32": 2, "fp16x2": 3, "f16": 3, "fp16s": 4}[precision]
 
 
 def alloc_act(B, rows, C, precision, device):
@@ -105,10 +107,10 @@ def alloc_act(B, rows, C, precision, device):
 
 
 def _out_dtype(t, split):
-    """C-ABI out_dtype code of an operand-format output buffer: 0 fp32, 1 bf16, 2 split bf16, 3 fp16."""
+    """C-ABI out_dtype code of an operand-format output buffer: 0 fp32, 1 bf16, 2 split bf16, 3 fp16, 4 split fp16."""
     assert t.dtype in (torch.float32, torch.bfloat16, torch.float16)
     if t.dtype == torch.float16:
-        return 3
+        return 4 if split else 3
     return (2 if split else 1) if t.dtype == torch.bfloat16 else 0
 
 
@@ -144,11 +146,13 @@ class ConvGemm:
         return self
 
     def __call__(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                 out_raw=None, phases=1, res_after=False):
+                 out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None):
         """srcs: channels-last activation tensors [B][rows][C_s], one per logical source.
         out: act(v) [B][rows_out][Cs'] (operand format) at rows out_row0 + time (+ `reflect` mirrored halo rows);
         out_raw: v before the activation [B][phases*T][Cs'] (operand format); out2: act(v) as exact fp32
-        [B*phases*T][Cs]; residual fp32 [B*phases*T][Cs] is added before the activation.  Cs = N / phases."""
+        [B*phases*T][Cs]; residual fp32 [B*phases*T][Cs] is added before the activation.  Cs = N / phases.
+        out_fmt / raw_fmt: operand format (a precision name) of out / out_raw when it differs from this layer's own
+        input precision -- e.g. a "fp16s" layer writing LeakyReLU(y) as "f16" and y as "fp16s"."""
         lib = _lib.load()
         meta = self.meta
         if not isinstance(srcs, (list, tuple)):
@@ -181,30 +185,34 @@ class ConvGemm:
             d.a_tap_dt[s] = self.tap_dt[s]
         d.w_ptr = self.w.data_ptr()
         d.n_pad, d.k_pad = meta["n_pad"], meta["k_pad"]
-        d.dtype = {"tf32": _lib.DTYPE_TF32, "fp16x2": _lib.DTYPE_F16}.get(self.precision, _lib.DTYPE_BF16)
+        d.dtype = {"tf32": _lib.DTYPE_TF32, "fp16x2": _lib.DTYPE_F16, "fp16s": _lib.DTYPE_F16,
+                   "f16": _lib.DTYPE_F16}.get(self.precision, _lib.DTYPE_BF16)
         d.B, d.T, d.N = B, T, meta["N"]
         d.bias = self.bias.data_ptr()
         d.act = self.act
         d.out_phases = phases
         cs = meta["N"] // phases
+        out_fmt = out_fmt or self.precision
+        raw_fmt = raw_fmt or out_fmt
         if out is not None:
             assert out.is_cuda and out.dim() == 3 and out.shape[0] == B and out.stride(2) == 1
-            assert out.shape[2] >= packing.act_channels(cs, self.precision)
+            assert out.dtype == TORCH_DTYPE[out_fmt] and out.shape[2] >= packing.act_channels(cs, out_fmt)
             assert out.stride(0) == out.shape[1] * out.stride(1)
             d.out = out.data_ptr()
             d.out_ld = out.stride(1)
             d.out_rows_per_utt = out.shape[1]
             d.out_row0 = out_row0
-            d.out_dtype = _out_dtype(out, split)
+            d.out_dtype = _dt(out_fmt)
             d.out_round_tf32 = 1 if (round_tf32 and out.dtype == torch.float32) else 0
             d.out_reflect = reflect
         if out_raw is not None:
-            assert out_raw.is_cuda and out_raw.dtype == TORCH_DTYPE[self.precision] and out_raw.stride(-1) == 1
-            assert out_raw.shape[-1] >= packing.act_channels(cs, self.precision)
-            assert out is None or out.dtype == out_raw.dtype
+            assert out_raw.is_cuda and out_raw.dtype == TORCH_DTYPE[raw_fmt] and out_raw.stride(-1) == 1
+            assert out_raw.shape[-1] >= packing.act_channels(cs, raw_fmt)
             d.out_raw = out_raw.data_ptr()
             d.out_raw_ld = out_raw.stride(-2)
-            d.out_dtype = _out_dtype(out_raw, split)
+            d.out_raw_dtype = _dt(raw_fmt)
+            if out is None:
+                d.out_dtype = _dt(raw_fmt)
             d.out_round_tf32 = 1 if (round_tf32 and out_raw.dtype == torch.float32) else 0
         if out2 is not None:
             assert out2.is_cuda and out2.dtype == torch.float32 and out2.stride(-1) == 1
@@ -527,6 +535,53 @@ class Resblock:
         with PROFILER.span(self.tag, flops=2.0 * 5 * C * C * B * L):
             _lib.check(lib.avc_resblock(ctypes.byref(desc), _stream()), "avc_resblock")
         return out if out is not None else (out2 if out2 is not None else out_raw)
+
+
+class Resblock2:
+    """One MelGAN ResnetBlock bound to avc_resblock2 ("fp16s" precision, C = 32 / 64): reads only the raw residual
+    stream (two fp16 terms, halo rows included) and writes one tensor.  ``w``/``bias3``/``bias1`` from
+    ``packing.pack_resblock2``."""
+
+    def __init__(self, w, bias3, bias1, dilation, tag="melgan_res"):
+        self.w, self.bias3, self.bias1 = w, bias3, bias1
+        self.C = bias3.numel()
+        self.dilation = dilation
+        self.tag = tag
+
+    @staticmethod
+    def eligible(C, L):
+        return C in packing.RESBLOCK_CHANNELS and L % 128 == 0
+
+    def to(self, device):
+        self.w, self.bias3, self.bias1 = self.w.to(device), self.bias3.to(device), self.bias1.to(device)
+        return self
+
+    def __call__(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=False, out2=None):
+        """x [B][L + 2d][2C] fp16 two-term residual stream with reflected halo rows (time t at row t + d).
+        y: raw output (y_act False) or LeakyReLU(output) (True) as two fp16 terms [B][rows][2C] at rows y_row0 + t
+        (+ `y_reflect` mirrored halo rows); out2: LeakyReLU(output) as exact fp32 [B*L][C].  Exactly one of y / out2."""
+        lib = _lib.load()
+        C, d = self.C, self.dilation
+        _require_cuda(self.w, x)
+        assert x.dtype == torch.float16 and x.dim() == 3 and x.shape == (B, L + 2 * d, 2 * C), (x.shape, (B, L + 2 * d, 2 * C))
+        assert x.stride(2) == 1 and x.stride(0) == x.shape[1] * x.stride(1)
+        assert (y is None) != (out2 is None)
+        desc = _lib.Resblock2Desc()
+        desc.x, desc.x_ld = x.data_ptr(), x.stride(1)
+        desc.w, desc.bias3, desc.bias1 = self.w.data_ptr(), self.bias3.data_ptr(), self.bias1.data_ptr()
+        desc.B, desc.L, desc.C, desc.dilation = B, L, C, d
+        if y is not None:
+            assert y.is_cuda and y.dtype == torch.float16 and y.dim() == 3 and y.shape[0] == B and y.shape[2] == 2 * C
+            assert y.stride(2) == 1 and y.stride(0) == y.shape[1] * y.stride(1)
+            desc.y, desc.y_ld = y.data_ptr(), y.stride(1)
+            desc.y_rows_per_utt, desc.y_row0, desc.y_reflect, desc.y_act = y.shape[1], y_row0, y_reflect, 1 if y_act else 0
+        else:
+            assert out2.is_cuda and out2.dtype == torch.float32 and out2.shape == (B * L, C) and out2.is_contiguous()
+            desc.out2, desc.out2_ld = out2.data_ptr(), out2.stride(0)
+        with PROFILER.span(self.tag, flops=2.0 * 5 * C * C * B * L,
+                           bytes=float(x.numel() * 2 + (B * L * C * 4))):
+            _lib.check(lib.avc_resblock2(ctypes.byref(desc), _stream()), "avc_resblock2")
+        return y if y is not None else out2
 
 
 # ------------------------------------------------------------------------------------------------ Meta glue

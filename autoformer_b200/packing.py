@@ -15,16 +15,22 @@ import torch
 # "fp32" (split bf16: hi + lo channels, three bf16 products per fp32 product -- fp32-grade accuracy),
 # "fp16x2" (fp16 activations, every weight as two fp16 terms w_hi + w_lo: two fp16 products per fp32 product; the
 # only rounding is the 2^-12 of the activations -- ~3e-4 end to end on AutoVC, scripts/precision_study.py)
-KC = {"tf32": 32, "bf16": 64, "fp32": 64, "fp16x2": 64, "f16": 64}      # "f16": single fp16 operand (internal)
+# "fp16s" (MelGAN, round 2): the split format with fp16 terms -- activations AND weights as two fp16 values hi + lo
+# (~2^-22), three products per fp32 product like "fp32" -- used for the tensors whose rounding the vocoder's output is
+# sensitive to (the residual stream, the ConvTranspose operands, the ResnetBlock intermediate), while the dilated k3
+# convolutions read ONE fp16 value per activation ("fp16x2" products).  scripts/melgan_precision_study.py.
+KC = {"tf32": 32, "bf16": 64, "fp32": 64, "fp16x2": 64, "f16": 64, "fp16s": 64}      # "f16": single fp16 operand (internal)
 TORCH_DTYPE = {"tf32": torch.float32, "bf16": torch.bfloat16, "fp32": torch.bfloat16, "fp16x2": torch.float16,
-               "f16": torch.float16}
+               "f16": torch.float16, "fp16s": torch.float16}
 TWO_TERM_WEIGHTS = ("fp32", "fp16x2")     # precisions whose packed LSTM weights are [w_hi | w_lo]
 PRECISIONS = ("tf32", "bf16", "fp32", "fp16x2")
+SPLIT_ACTS = ("fp32", "fp16s")            # activation buffers hold [hi | lo] halves (2C channels)
+FP16_MAX = 65504.0
 
 
 def act_channels(c: int, precision: str) -> int:
     """Channels of the activation buffer that carries c logical channels."""
-    return 2 * c if precision == "fp32" else c
+    return 2 * c if precision in SPLIT_ACTS else c
 
 
 def split_bf16(t: torch.Tensor):
@@ -47,6 +53,10 @@ def split_terms(t: torch.Tensor, precision: str):
     return split_bf16(t) if precision == "fp32" else split_f16(t)
 
 
+def sat_f16(t: torch.Tensor) -> torch.Tensor:
+    return t.float().clamp(-FP16_MAX, FP16_MAX)
+
+
 def to_act(t: torch.Tensor, precision: str) -> torch.Tensor:
     """fp32 channels-last activation -> the buffer format of `precision` (tests / host-side staging)."""
     if precision == "tf32":
@@ -55,18 +65,15 @@ def to_act(t: torch.Tensor, precision: str) -> torch.Tensor:
         return t.to(torch.bfloat16)
     if precision in ("fp16x2", "f16"):
         return t.to(torch.float16)
-    hi, lo = split_bf16(t)
+    hi, lo = split_f16(sat_f16(t)) if precision == "fp16s" else split_bf16(t)
     return torch.cat([hi, lo], dim=-1).contiguous()
 
 
 def act_to_float(buf: torch.Tensor, precision: str) -> torch.Tensor:
-    if precision == "fp32":
+    if precision in SPLIT_ACTS:
         c = buf.shape[-1] // 2
         return buf[..., :c].float() + buf[..., c:].float()
     return buf.float()
-
-
-FP16_MAX = 65504.0
 
 
 def fp16_overflow_margin(taps) -> float:
@@ -128,16 +135,16 @@ def pack_conv_sources(weights, bias, precision, block_n=None):
     Returns (W [n_pad][k_pad] operand dtype, bias [n_pad] fp32, meta dict)."""
     kc = KC[precision]
     n = weights[0].shape[0]
-    if precision == "fp32":
+    if precision in SPLIT_ACTS:
         # a*w ~ a_hi*w_hi + a_lo*w_hi + a_hi*w_lo: each logical source becomes two physical ones over the same
         # buffer: [a_hi|a_lo] x [w_hi|w_hi] (2C channels) and a_hi x w_lo (the first C channels)
         assert len(weights) <= 2, "at most two logical sources in split precision (four physical sources)"
         phys = []
         for w in weights:
-            hi, lo = split_bf16(w)
+            hi, lo = split_terms(w, precision)
             phys += [torch.cat([hi, hi], dim=1).float(), lo.float()]
-        w_p, b_p, meta = pack_conv_sources(phys, bias, "bf16", block_n)
-        meta.update(precision="fp32", split=True, logical_channels=[w.shape[1] for w in weights],
+        w_p, b_p, meta = pack_conv_sources(phys, bias, "bf16" if precision == "fp32" else "f16", block_n)
+        meta.update(precision=precision, split=True, logical_channels=[w.shape[1] for w in weights],
                     logical_taps=[w.shape[2] for w in weights])
         return w_p, b_p, meta
     if precision == "fp16x2":
@@ -204,6 +211,30 @@ def pack_resblock(w3, b3, w1, b1, wsc, bsc):
             tiles.append(torch.cat([torch.cat([hi, hi], dim=1), torch.cat([lo, torch.zeros_like(lo)], dim=1)], dim=0))
     w = torch.stack(tiles).contiguous()
     assert w.shape == (5, 2 * c, 64) and w.dtype == torch.bfloat16
+    return w, b3.float().contiguous(), (b1.float() + bsc.float()).contiguous()
+
+
+def pack_resblock2(w3, b3, w1, b1, wsc, bsc):
+    """Weights of one MelGAN ResnetBlock for avc_resblock2 ("fp16s" precision: every weight as two fp16 terms).
+
+    Returns (W [rows][64] fp16, bias3 [C], bias1 [C]); tiles in order W3 tap 0..2, W1 (block.4), Wsc (shortcut):
+      C = 64: every tile rows [w_hi (64) ; w_lo (64)]
+      C = 32: W3 tiles rows [w_hi | w_lo] (32 rows: the k3 operand rows are [xa | xa]);
+              W1 / Wsc tiles rows [[w_hi | w_hi] (32) ; [w_lo | 0] (32)] (operand rows [a_hi | a_lo])."""
+    c = w3.shape[0]
+    assert c in RESBLOCK_CHANNELS and w3.shape == (c, c, 3) and w1.shape == (c, c, 1) and wsc.shape == (c, c, 1)
+    tiles = []
+    for k in range(3):
+        hi, lo = split_f16(w3[:, :, k])
+        tiles.append(torch.cat([hi, lo], dim=0) if c == 64 else torch.cat([hi, lo], dim=1))
+    for m in (w1[:, :, 0], wsc[:, :, 0]):
+        hi, lo = split_f16(m)
+        if c == 64:
+            tiles.append(torch.cat([hi, lo], dim=0))
+        else:
+            tiles.append(torch.cat([torch.cat([hi, hi], dim=1), torch.cat([lo, torch.zeros_like(lo)], dim=1)], dim=0))
+    w = torch.cat(tiles, dim=0).contiguous()
+    assert w.shape == ((640 if c == 64 else 224), 64) and w.dtype == torch.float16
     return w, b3.float().contiguous(), (b1.float() + bsc.float()).contiguous()
 
 

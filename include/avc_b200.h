@@ -93,7 +93,8 @@ typedef struct avc_gemm_desc {
   void* out;                 /* act(v): [B][out_rows_per_utt][out_ld], written at row out_row0 + time */
   long long out_ld;
   int out_rows_per_utt, out_row0;
-  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column c, lo at column Cs + c (out_ld >= 2Cs), 3 = fp16 */
+  int out_dtype;             /* 0 = fp32, 1 = bf16, 2 = split bf16: hi at column c, lo at column Cs + c (out_ld >= 2Cs), 3 = fp16,
+                                4 = split fp16 (two fp16 terms hi | lo, same layout as 2) */
   int out_round_tf32;        /* round fp32 outputs to TF32 (rna) so the next GEMM reads them exactly */
   int out_reflect;           /* also write `out_reflect` reflected halo rows each side (ReflectionPad1d,
                                 melgan/modules.py:77,96,121); needs out_row0 >= out_reflect */
@@ -111,6 +112,9 @@ typedef struct avc_gemm_desc {
                                 producer start / loads issued / MMA thread at unit / accumulator buffer free / first
                                 k-block landed / MMAs issued / accumulator ready / epilogue done
                                 (profiling aid; NULL in production) */
+  int out_raw_dtype;         /* format of out_raw (codes of out_dtype); 0 = same as out_dtype.  The MelGAN "fp16s" layers
+                                write LeakyReLU(y) as ONE fp16 value (out, the next k3 convolution's operand) and y itself
+                                as two fp16 terms (out_raw, the residual stream, melgan/modules.py:84-85) */
 } avc_gemm_desc;
 
 int avc_conv_gemm(const avc_gemm_desc* d, void* stream);
@@ -155,6 +159,41 @@ typedef struct avc_resblock_desc {
 } avc_resblock_desc;
 
 int avc_resblock(const avc_resblock_desc* d, void* stream);
+
+/*
+ * The same ResnetBlock (melgan/modules.py:72-85) in the "fp16s" precision, reading ONLY the raw residual stream:
+ *
+ *   y = W_sc x + W_1 LeakyReLU( W_3 *_d LeakyReLU(ReflectionPad_d(x)) + b_3 ) + (b_1 + b_sc)
+ *
+ * x is stored as two fp16 terms [hi(C) | lo(C)] (AVC out_dtype 4) with its reflected halo rows; the kernel forms the k3
+ * operand LeakyReLU(x) itself, in shared memory, as ONE fp16 value per element (two products per weight), keeps the
+ * intermediate as two fp16 terms on chip (three products), and reads the shortcut operand from the centre rows of the
+ * same window (three products).  HBM traffic per block: one read of x, one write of the output -- half of avc_resblock.
+ *   x     [B][L + 2*dilation][x_ld]   time t at row t + dilation; halo rows hold the reflected samples
+ *   w     packing.pack_resblock2: tiles W3 tap 0, 1, 2, W1 (block.4), Wsc (shortcut), rows of 64 fp16.
+ *         C = 64: every tile [w_hi (64 rows) ; w_lo (64 rows)];  C = 32: W3 tiles rows [w_hi | w_lo] (32 rows),
+ *         W1 / Wsc tiles rows [ [w_hi | w_hi] (32) ; [w_lo | 0] (32) ]
+ *   bias3 [C] fp32 (block.2);  bias1 [C] fp32 (block.4 bias + shortcut bias)
+ *   y     y (y_act = 0) or LeakyReLU(y) (y_act = 1) as two fp16 terms [B][y_rows_per_utt][y_ld] at row y_row0 + t, plus
+ *         y_reflect mirrored halo rows each side (the next block's ReflectionPad1d)
+ *   out2  LeakyReLU(y), exact fp32 [B*L][out2_ld]           -- exactly one of y / out2
+ * C is 32 or 64, L a multiple of 128, 1 <= dilation <= 16.
+ */
+typedef struct avc_resblock2_desc {
+  const void* x;
+  long long x_ld;
+  const void* w;
+  const float* bias3;
+  const float* bias1;
+  int B, L, C, dilation;
+  void* y;
+  long long y_ld;
+  int y_rows_per_utt, y_row0, y_reflect, y_act;
+  float* out2;
+  long long out2_ld;
+} avc_resblock2_desc;
+
+int avc_resblock2(const avc_resblock2_desc* d, void* stream);
 
 /*
  * Recurrence of one uni-directional LSTM layer with hidden size H (multiple of gate_group, >= 64):

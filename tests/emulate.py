@@ -60,9 +60,11 @@ _ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(
 
 
 def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                       out_raw=None, phases=1, res_after=False):
+                       out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None):
     meta = self.meta
     prec = self.precision
+    out_fmt = out_fmt or prec
+    raw_fmt = raw_fmt or out_fmt
     if not isinstance(srcs, (list, tuple)):
         srcs = [srcs]
     if meta.get("split"):
@@ -83,18 +85,19 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
     res = residual.reshape(B, tl, -1)[..., :cs].double() if residual is not None else 0.0
     if not res_after:
         v = v + res
-    ac = packing.act_channels(cs, prec)
     if out_raw is not None:
-        out_raw.view(B, tl, -1)[..., :ac] = packing.to_act(v.float(), prec)
+        assert out_raw.dtype == packing.TORCH_DTYPE[raw_fmt]
+        out_raw.view(B, tl, -1)[..., :packing.act_channels(cs, raw_fmt)] = packing.to_act(v.float(), raw_fmt)
     a = _ACT[self.act](v)
     if res_after:
         a = a + res
     if out is not None:
-        assert out.shape[1] >= out_row0 + tl + reflect and out_row0 >= reflect
+        assert out.shape[1] >= out_row0 + tl + reflect and out_row0 >= reflect and out.dtype == packing.TORCH_DTYPE[out_fmt]
         full = a
         if reflect:
             full = F.pad(a.transpose(1, 2), (reflect, reflect), mode="reflect").transpose(1, 2)
-        out[:, out_row0 - reflect:out_row0 + tl + reflect, :ac] = packing.to_act(full.float(), prec)
+        out[:, out_row0 - reflect:out_row0 + tl + reflect, :packing.act_channels(cs, out_fmt)] = \
+            packing.to_act(full.float(), out_fmt)
     if out2 is not None:
         out2.view(B, tl, -1)[..., :cs] = a.float()
     return out if out is not None else (out2 if out2 is not None else out_raw)
@@ -335,8 +338,42 @@ def _emu_resblock_call(self, xa, x, B, L, out=None, out_row0=0, reflect=0, out_r
     return out if out is not None else (out2 if out2 is not None else out_raw)
 
 
+def _emu_resblock2_call(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=False, out2=None):
+    """Mirror of avc_resblock2: reads the PACKED tiles (packing.pack_resblock2 is what gets validated), forms the k3
+    operand as ONE fp16 value from the two-term window, keeps the intermediate as two fp16 terms, reads the shortcut
+    operand from the centre rows of the same window."""
+    C, d = self.C, self.dilation
+    assert x.shape == (B, L + 2 * d, 2 * C) and x.dtype == torch.float16 and L % 128 == 0
+    w = self.w.double()
+    if C == 64:
+        tiles = [w[128 * i:128 * (i + 1)] for i in range(5)]
+        mats = [t[:64] + t[64:] for t in tiles]
+    else:
+        k3 = [w[32 * i:32 * (i + 1)] for i in range(3)]
+        k1 = [w[96 + 64 * i:96 + 64 * (i + 1)] for i in range(2)]
+        for t in k1:
+            assert torch.equal(t[:32, :32], t[:32, 32:]) and not t[32:, 32:].any()
+        mats = [t[:, :32] + t[:, 32:] for t in k3] + [t[:32, :32] + t[32:, :32] for t in k1]
+    xs = packing.act_to_float(x, "fp16s").double()                                   # the stored stream (hi + lo)
+    xa = F.leaky_relu(xs, 0.2).float().half().double()                                # one fp16 value
+    mid = self.bias3.double().view(1, 1, C).expand(B, L, C).clone()
+    for tap in range(3):
+        mid = mid + xa[:, tap * d:tap * d + L] @ mats[tap].t()
+    mid = packing.act_to_float(packing.to_act(F.leaky_relu(mid, 0.2).float(), "fp16s"), "fp16s").double()
+    v = mid @ mats[3].t() + xs[:, d:d + L] @ mats[4].t() + self.bias1.double()
+    if y is not None:
+        a = F.leaky_relu(v, 0.2) if y_act else v
+        assert y.shape[1] >= y_row0 + L + y_reflect and y_row0 >= y_reflect
+        full = F.pad(a.transpose(1, 2), (y_reflect, y_reflect), mode="reflect").transpose(1, 2) if y_reflect else a
+        y[:, y_row0 - y_reflect:y_row0 + L + y_reflect] = packing.to_act(full.float(), "fp16s")
+        return y
+    out2[:] = F.leaky_relu(v, 0.2).float().reshape(B * L, C)
+    return out2
+
+
 def install_cpu_kernels(monkeypatch):
     monkeypatch.setattr(ops.Resblock, "__call__", _emu_resblock_call)
+    monkeypatch.setattr(ops.Resblock2, "__call__", _emu_resblock2_call)
     monkeypatch.setattr(ops, "audio_frames", _emu_audio_frames)
     monkeypatch.setattr(ops, "complex_mag", _emu_complex_mag)
     monkeypatch.setattr(ops, "global_stats", _emu_global_stats)

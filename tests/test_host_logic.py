@@ -65,7 +65,7 @@ def test_lstmdv_host_logic(cpu_kernels, precision, tol):
     assert e.shape == (2, 256) and rel_l2(e, ref) < tol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 3e-2), ("fp16x2", 2e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("tf32", 3e-3), ("bf16", 3e-2), ("fp16x2", 2e-3), ("fp16s", 1e-3)])
 @pytest.mark.parametrize("B,T", [(1, 12), (2, 17)])
 def test_melgan_host_logic(cpu_kernels, precision, tol, B, T):
     from autoformer_b200.melgan.modules import Generator
