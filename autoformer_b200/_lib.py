@@ -17,7 +17,7 @@ EXPORTS = ["avc_version", "avc_last_error", "avc_launch_count", "avc_conv_gemm",
            "avc_bilstm_small", "avc_concat_bcast", "avc_linear_l2norm", "avc_linear_rows", "avc_transpose_pad",
            "avc_conv_to_mono_tanh", "avc_gn_stats", "avc_gn_pool_residual", "avc_gn_apply", "avc_patchify",
            "avc_ln_transpose", "avc_meta_decoder_input", "avc_gather_codes", "avc_global_stats", "avc_adain", "avc_audio_frames",
-           "avc_complex_mag", "avc_resblock", "avc_resblock2"]
+           "avc_complex_mag", "avc_resblock", "avc_resblock2", "avc_reflect_halo"]
 
 
 MAX_SOURCES = 4
@@ -179,6 +179,9 @@ def load():
     lib.avc_lstm_seq_ws.restype = ctypes.c_int
     lib.avc_resblock.argtypes = [ctypes.POINTER(ResblockDesc), ctypes.c_void_p]
     lib.avc_resblock.restype = ctypes.c_int
+    lib.avc_reflect_halo.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.avc_reflect_halo.restype = ctypes.c_int
     lib.avc_resblock2.argtypes = [ctypes.POINTER(Resblock2Desc), ctypes.c_void_p]
     lib.avc_resblock2.restype = ctypes.c_int
     lib.avc_bilstm_small.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,

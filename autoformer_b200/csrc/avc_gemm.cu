@@ -54,7 +54,7 @@ template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
   if (ACT == AVC_ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == AVC_ACT_TANH) return tanh_fast(v);
-  if (ACT == AVC_ACT_LRELU) return v > 0.0f ? v : 0.2f * v;
+  if (ACT == AVC_ACT_LRELU) return fmaxf(v, 0.2f * v);      // slope < 1
   if (ACT == AVC_ACT_GELU) {
     // exact-erf GELU, 0.5 v (1 + erf(v / sqrt 2)), with erfc(|x|) = t (a1 + t (a2 + ... a5 t)) exp(-x^2), t = 1 / (1 + p |x|)
     // (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 -- fp32 rounding level; two MUFU ops and no branch, where erff()
@@ -84,8 +84,11 @@ __device__ __forceinline__ void store4(void* base, int mode, int round, long lon
     *reinterpret_cast<uint2*>(ptr + cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
   } else if (mode == 4) {
     __half* ptr = static_cast<__half*>(base) + row * ld + c;
-    *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]));
-    *reinterpret_cast<uint2*>(ptr + cs) = make_uint2(pack_f16(f16_lo(v[0]), f16_lo(v[1])), pack_f16(f16_lo(v[2]), f16_lo(v[3])));
+    uint2 hi, lo;
+    split_f16_pair(v[0], v[1], hi.x, lo.x);
+    split_f16_pair(v[2], v[3], hi.y, lo.y);
+    *reinterpret_cast<uint2*>(ptr) = hi;
+    *reinterpret_cast<uint2*>(ptr + cs) = lo;
   } else if (mode == 1) {
     uint2 pk = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(base) + row * ld + c) = pk;
@@ -96,6 +99,29 @@ __device__ __forceinline__ void store4(void* base, int mode, int round, long lon
     float4 o = round ? make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]))
                      : make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(static_cast<float*>(base) + row * ld + c) = o;
+  }
+}
+
+// Predicated store of four consecutive channels in a 16-bit operand format (1 bf16, 2 split bf16, 3 fp16, 4 split fp16).
+__device__ __forceinline__ void store16(__nv_bfloat16* ptr, int mode, int cs, const float (&o)[4], bool ok) {
+  if (mode >= 3) {
+    uint2 hi, lo;
+    if (mode == 4) {
+      split_f16_pair(o[0], o[1], hi.x, lo.x);
+      split_f16_pair(o[2], o[3], hi.y, lo.y);
+      if (ok) *reinterpret_cast<uint2*>(ptr + cs) = lo;
+    } else {
+      hi = make_uint2(pack_f16(o[0], o[1]), pack_f16(o[2], o[3]));
+    }
+    if (ok) *reinterpret_cast<uint2*>(ptr) = hi;
+  } else {
+    if (ok) *reinterpret_cast<uint2*>(ptr) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    if (mode == 2) {
+      float lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) lo[e] = o[e] - __bfloat162float(__float2bfloat16_rn(o[e]));
+      if (ok) *reinterpret_cast<uint2*>(ptr + cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
+    }
   }
 }
 
@@ -132,10 +158,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
   };
   float4 bv_next = c_first < chunks ? load_bias(c_first) : make_float4(0.f, 0.f, 0.f, 0.f);
   // output shapes served by the branch-free row loops (see below); tiles with one real chunk keep the general loop
+  // (poly-phase outputs qualify when a 32-column chunk lies inside one phase; reflected halo rows never do -- callers
+  // that want the fast path write them with avc_reflect_halo afterwards)
   int simple = 0;
-  if (!split_rows && p.phases == 1 && p.out_reflect == 0 && !p.out_raw) {
-    if (p.out && !p.out2 && !has_res && p.out_mode != 0) simple = 1;
-    if (!p.out && p.out2 && !(has_res && res_after)) simple = 2;
+  if (!split_rows && p.out_reflect == 0 && (p.phases == 1 || (p.cs & 31) == 0)) {
+    if (p.out && !p.out2 && !has_res && p.out_mode != 0 && (!p.out_raw || p.raw_mode != 0)) simple = 1;
+    if (!p.out && p.out2 && !(has_res && res_after) && p.phases == 1 && !p.out_raw) simple = 2;
   }
   // The row loop is deliberately NOT fully unrolled: with 8 copies of the (mode x output x halo) store code the
   // epilogue was ~4000 instructions, and layers with few k-blocks per tile (MelGAN stages 2-3, 1x1 convolutions) spent
@@ -162,8 +190,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
       // The two common output shapes without any per-row branching (the general loop below crosses ~10 branches per
       // 4-element store; with two epilogue warps per scheduler nothing hides their latency, and layers with few
       // k-blocks per tile were bound by it: 13.5 K cycles per 128 x 256 tile against 9 K cycles of MMAs).
-      //   simple 1: act(v) to `out` in a 16-bit operand format or the split format, nothing else
+      //   simple 1: act(v) to `out` (and optionally v itself to `out_raw`) in 16-bit operand formats, one or two terms
       //   simple 2: act(v [+ residual]) to `out2` (fp32), nothing else
+      const int phase = p.phases == 1 ? 0 : n / p.cs;      // constant over the chunk (cs % 32 == 0)
+      const int c = n - phase * p.cs;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {          // (simple excludes split_rows: all eight row groups are this warp's)
         {
@@ -174,23 +204,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
           const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
           float o[4] = {a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w};
           if (simple == 1) {
+            const int time = t * p.phases + phase;
+            if (p.out_raw) {
+              __nv_bfloat16* rp = static_cast<__nv_bfloat16*>(p.out_raw) + ((long long)b * t_out + time) * p.out_raw_ld + c;
+              store16(rp, p.raw_mode, p.cs, o, ok);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
-            const long long off = ((long long)b * p.out_rows_per_utt + p.out_row0 + t) * p.out_ld + n;
-            __nv_bfloat16* ptr = static_cast<__nv_bfloat16*>(p.out) + off;      // 2-byte elements in all three formats
-            const bool f16 = p.out_mode >= 3;
-            const uint2 hi = f16 ? make_uint2(pack_f16(o[0], o[1]), pack_f16(o[2], o[3]))
-                                 : make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
-            if (ok) *reinterpret_cast<uint2*>(ptr) = hi;
-            if (p.out_mode == 2) {
-              float lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) lo[e] = o[e] - __bfloat162float(__float2bfloat16_rn(o[e]));
-              if (ok) *reinterpret_cast<uint2*>(ptr + p.cs) = make_uint2(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]));
-            } else if (p.out_mode == 4) {
-              if (ok) *reinterpret_cast<uint2*>(ptr + p.cs) =
-                  make_uint2(pack_f16(f16_lo(o[0]), f16_lo(o[1])), pack_f16(f16_lo(o[2]), f16_lo(o[3])));
-            }
+            const long long off = ((long long)b * p.out_rows_per_utt + p.out_row0 + time) * p.out_ld + c;
+            store16(static_cast<__nv_bfloat16*>(p.out) + off, p.out_mode, p.cs, o, ok);   // 2-byte elements in all four formats
           } else {
             const long long lr = (long long)b * p.T + t;
             if (has_res) {

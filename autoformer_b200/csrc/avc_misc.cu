@@ -410,6 +410,51 @@ extern "C" int avc_transpose_pad(const float* in, void* out, int B, int C, int L
 }
 
 // ---------------------------------------------------------------------------------------------
+// Reflected halo rows of a channels-last buffer (nn.ReflectionPad1d of the consumer, melgan/modules.py:77,96,121)
+// ---------------------------------------------------------------------------------------------
+namespace avc {
+__global__ void __launch_bounds__(256) reflect_halo_kernel(uint4* __restrict__ buf, long long rows_per_utt, int vec_per_row,
+                                                           long long row0, long long L, int reflect, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = static_cast<int>(i % vec_per_row);
+    long long r = i / vec_per_row;
+    const int k = static_cast<int>(r % (2 * reflect));       // 0..reflect-1: left halo row -(k+1); rest: right halo
+    const long long b = r / (2 * reflect);
+    long long dst, src;
+    if (k < reflect) {
+      dst = row0 - (k + 1);
+      src = row0 + (k + 1);
+    } else {
+      const int j = k - reflect + 1;
+      dst = row0 + L - 1 + j;
+      src = row0 + L - 1 - j;
+    }
+    uint4* base = buf + b * rows_per_utt * vec_per_row;
+    base[dst * vec_per_row + v] = base[src * vec_per_row + v];
+  }
+}
+}  // namespace avc
+
+extern "C" int avc_reflect_halo(void* buf, int B, int rows_per_utt, long long row_bytes, int row0, int L, int reflect,
+                                void* stream_v) {
+  using namespace avc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  AVC_REQUIRE(buf != nullptr, "avc_reflect_halo: null buffer");
+  AVC_REQUIRE(B > 0 && reflect >= 1 && L > reflect && row0 >= reflect && rows_per_utt >= row0 + L + reflect &&
+                  row_bytes > 0 && row_bytes % 16 == 0,
+              "avc_reflect_halo: bad geometry B=%d rows=%d row_bytes=%lld row0=%d L=%d reflect=%d", B, rows_per_utt,
+              row_bytes, row0, L, reflect);
+  const int vec = static_cast<int>(row_bytes / 16);
+  const long long total = (long long)B * 2 * reflect * vec;
+  const long long blocks = (total + 255) / 256;
+  reflect_halo_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, stream>>>(
+      static_cast<uint4*>(buf), rows_per_utt, vec, row0, L, reflect, total);
+  AVC_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Audio2Mel front end glue (melgan/modules.py:55-66): reflect padding + framing rows, complex magnitude
 // ---------------------------------------------------------------------------------------------
 namespace avc {

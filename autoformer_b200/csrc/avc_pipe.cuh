@@ -240,15 +240,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // fp16 stores saturate at +-65504 instead of producing inf (an out-of-range activation then costs accuracy, not a
 // NaN-poisoned utterance; values on this path are O(1..100))
 __device__ __forceinline__ float sat_f16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+// two floats -> packed fp16 pair with saturation, ONE instruction (F2FP.SATFINITE.F16.F32.PACK_AB); `lo` lands in the low half
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 // second term of the two-term fp16 form v ~ hi + lo, hi = fp16(v): what fp16(v) lost (exact in fp32, ~2^-22 relative after
 // its own rounding; values below fp16's subnormal step flush towards zero, which costs < 6e-8 absolute)
 __device__ __forceinline__ float f16_lo(float v) {
   const float s = sat_f16(v);
   return s - __half2float(__float2half_rn(s));
+}
+// (v0, v1) -> packed hi pair and packed lo pair of the two-term form (8 instructions for two values)
+__device__ __forceinline__ void split_f16_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16(v0, v1);
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16(sat_f16(v0) - h.x, sat_f16(v1) - h.y);
 }
 
 }  // namespace avc

@@ -125,7 +125,8 @@ __device__ __forceinline__ void issue_src(uint32_t a0, uint32_t a1, uint32_t w, 
   }
 }
 
-__device__ __forceinline__ float lrelu(float v) { return v > 0.0f ? v : 0.2f * v; }
+// slope < 1: LeakyReLU(v) = max(v, slope * v)
+__device__ __forceinline__ float lrelu(float v) { return fmaxf(v, 0.2f * v); }
 
 // Writes NCH channels starting at channel c0 of row `row` as split bf16 into operand tile(s) at `tiles`
 // (C = 64: hi tile, lo tile; C = 32: one tile with [hi | lo] rows), 128-byte swizzle.
@@ -365,9 +366,10 @@ static int launch(const RbParams& p, cudaStream_t stream) {
 //   mid   = LeakyReLU(D1 + b3) as two fp16 terms in shared memory
 //   GEMM2: D2 = [mid_hi, mid_lo] . W1 + [x_hi, x_lo](centre rows) . Wsc   (three products each)
 //
-// Schedule per CTA: the epilogue warps run  ep1(i) -> form xa(i+1) -> ep2(i), the MMA thread  GEMM1(i) -> GEMM2(i), so
-// GEMM2(i) overlaps the xa pass of the next tile and GEMM1(i+1) overlaps ep2(i); the window of tile i+2 is loaded as soon
-// as GEMM2(i) has read the centre rows of its buffer.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two per TMEM lane quarter), 10..13 = xa warps.
+// Schedule per CTA: the xa warps form xa(i+1) as soon as GEMM1(i) has read the xa tile, the epilogue warps run
+// ep1(i) -> ep2(i), the MMA thread GEMM1(i) -> GEMM2(i): GEMM2(i) and ep1/ep2(i) overlap the xa pass of the next tile,
+// GEMM1(i+1) overlaps ep2(i); the window of tile i+2 is loaded as soon as GEMM2(i) has read the centre rows of its buffer.
 template <int C>
 struct Rb2Cfg {
   static_assert(C == 32 || C == 64, "fused ResnetBlock: 32 or 64 channels");
@@ -415,10 +417,10 @@ __device__ __forceinline__ void write_split_f16(uint8_t* tiles, int row, int c0,
                                                 uint4 (&lo)[NCH / 8]) {
 #pragma unroll
   for (int j = 0; j < NCH / 8; ++j) {
-    hi[j] = make_uint4(pack_f16(v[j * 8], v[j * 8 + 1]), pack_f16(v[j * 8 + 2], v[j * 8 + 3]),
-                       pack_f16(v[j * 8 + 4], v[j * 8 + 5]), pack_f16(v[j * 8 + 6], v[j * 8 + 7]));
-    lo[j] = make_uint4(pack_f16(f16_lo(v[j * 8]), f16_lo(v[j * 8 + 1])), pack_f16(f16_lo(v[j * 8 + 2]), f16_lo(v[j * 8 + 3])),
-                       pack_f16(f16_lo(v[j * 8 + 4]), f16_lo(v[j * 8 + 5])), pack_f16(f16_lo(v[j * 8 + 6]), f16_lo(v[j * 8 + 7])));
+    split_f16_pair(v[j * 8], v[j * 8 + 1], hi[j].x, lo[j].x);
+    split_f16_pair(v[j * 8 + 2], v[j * 8 + 3], hi[j].y, lo[j].y);
+    split_f16_pair(v[j * 8 + 4], v[j * 8 + 5], hi[j].z, lo[j].z);
+    split_f16_pair(v[j * 8 + 6], v[j * 8 + 7], hi[j].w, lo[j].w);
     const int chunk = c0 / 8 + j;
     uint8_t* r = tiles + row * kRowBytes;
     if (C == 64) {
@@ -433,10 +435,13 @@ __device__ __forceinline__ void write_split_f16(uint8_t* tiles, int row, int c0,
 
 // xa = fp16(LeakyReLU(hi + lo)) for every row of the window, written with the window's own swizzle so that the three taps
 // read it through row-shifted descriptors.  C = 32: rows [xa | xa] against weight rows [w_hi | w_lo].
+constexpr int kXaWarps = 4;
+constexpr int kRb2Threads = kRbThreads + 32 * kXaWarps;
+
 template <int C>
 __device__ __forceinline__ void form_xa(const uint8_t* win, uint8_t* xa, int win_rows, int tid) {
   constexpr int CH = C / 8;                 // 16-byte chunks of one term per row
-  for (int it = tid; it < win_rows * CH; it += 32 * kEpiWarps) {
+  for (int it = tid; it < win_rows * CH; it += 32 * kXaWarps) {
     const int r = it / CH, c = it - r * CH;
     const int sw = r & 7;
     const uint8_t* row = win + r * kRowBytes;
@@ -491,7 +496,7 @@ __device__ __forceinline__ void issue_src_f16(uint32_t a0, uint32_t a1, uint32_t
 }
 
 template <int C>
-__global__ void __launch_bounds__(kRbThreads, Rb2Cfg<C>::kCtasPerSm) resblock2_kernel(const __grid_constant__ Rb2Params p) {
+__global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_kernel(const __grid_constant__ Rb2Params p) {
   using Cfg = Rb2Cfg<C>;
   constexpr int P = Cfg::kParts;
   constexpr int NCH = C / 2;                 // channels per epilogue thread
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(kRbThreads, Rb2Cfg<C>::kCtasPerSm) resblock2_k
       mbar_init(&win_full[i], 1);
       mbar_init(&win_free[i], 1);
     }
-    mbar_init(xa_ready, kEpiWarps);
+    mbar_init(xa_ready, kXaWarps);
     mbar_init(d1_full, 1);
     mbar_init(mid_ready, kEpiWarps);
     mbar_init(d2_full, 1);
@@ -529,11 +534,11 @@ __global__ void __launch_bounds__(kRbThreads, Rb2Cfg<C>::kCtasPerSm) resblock2_k
   }
   // weight tiles -> shared memory, 128-byte swizzle (row n, 16-byte chunk c at n * 128 + ((c ^ n % 8) << 4)); every tile
   // starts on a multiple of 8 rows, so the global row index gives the right swizzle phase
-  for (int i = threadIdx.x; i < Cfg::kWBytes / 16; i += kRbThreads) {
+  for (int i = threadIdx.x; i < Cfg::kWBytes / 16; i += kRb2Threads) {
     const int n = i >> 3, c = i & 7;
     *reinterpret_cast<uint4*>(s_w + n * kRowBytes + ((c ^ (n & 7)) << 4)) = p.w[i];
   }
-  for (int i = threadIdx.x; i < 2 * C; i += kRbThreads) s_bias[i] = i < C ? p.bias3[i] : p.bias1[i - C];
+  for (int i = threadIdx.x; i < 2 * C; i += kRb2Threads) s_bias[i] = i < C ? p.bias3[i] : p.bias1[i - C];
   fence_proxy_async();          // the tensor core reads the weight tiles through the async proxy
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -580,22 +585,27 @@ __global__ void __launch_bounds__(kRbThreads, Rb2Cfg<C>::kCtasPerSm) resblock2_k
       }
     }
     __syncwarp();
+  } else if (warp >= 2 + kEpiWarps) {
+    // ---------------- xa warps: the k3 operand of tile i from its raw window, as soon as GEMM1(i-1) has read the xa tile
+    const int tid = threadIdx.x - kRbThreads;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&win_full[buf], (it >> 1) & 1);
+      if (it > 0) mbar_wait(d1_full, (it - 1) & 1);
+      form_xa<C>(s_win + buf * P * Cfg::kWinTile, s_xa, win_rows, tid);
+      fence_proxy_async();   // generic-proxy writes -> tensor-core (async proxy) reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xa_ready);
+    }
   } else {
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int h = (warp - 2) >> 2;             // which half of the channels
     const int row = q * 32 + lane;
     const int c0 = h * NCH;
-    const int tid = threadIdx.x - 64;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const bool storer = threadIdx.x == 64;
     int it = 0;
-    if (blockIdx.x < p.n_tiles) {              // xa of the first tile
-      mbar_wait(&win_full[0], 0);
-      form_xa<C>(s_win, s_xa, win_rows, tid);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(xa_ready);
-    }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
       float v[NCH];
@@ -623,15 +633,6 @@ __global__ void __launch_bounds__(kRbThreads, Rb2Cfg<C>::kCtasPerSm) resblock2_k
       tc_fence_before();     // ... and this warp's reads of accumulator 1 before the next GEMM1
       __syncwarp();
       if (lane == 0) mbar_arrive(mid_ready);
-      // ---- xa of the next tile, while GEMM2 of this one runs (GEMM1 of this tile has finished: the xa tile is free)
-      if (tile + (int)gridDim.x < p.n_tiles) {
-        const int nb = (it + 1) & 1;
-        mbar_wait(&win_full[nb], ((it + 1) >> 1) & 1);
-        form_xa<C>(s_win + nb * P * Cfg::kWinTile, s_xa, win_rows, tid);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(xa_ready);
-      }
       // ---- epilogue 2: y = k1(mid) + shortcut(x) + bias; store
       mbar_wait(d2_full, it & 1);
       tc_fence_after();
@@ -702,7 +703,7 @@ static int launch2(const Rb2Params& p, cudaStream_t stream) {
   }
   const int max_ctas = num_sms() * Cfg::kCtasPerSm;
   const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-  kern<<<grid, kRbThreads, Cfg::kSmemBytes, stream>>>(p);
+  kern<<<grid, kRb2Threads, Cfg::kSmemBytes, stream>>>(p);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

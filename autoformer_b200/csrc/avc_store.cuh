@@ -42,8 +42,11 @@ __device__ __forceinline__ void store_op4(void* out, int mode, int round, long l
     *reinterpret_cast<uint2*>(p + C) = make_uint2(pack_bf16(lx, ly), pack_bf16(lz, lw));
   } else if (mode == 4) {
     __half* p = static_cast<__half*>(out) + row * ld + c;
-    *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16(v.x, v.y), pack_f16(v.z, v.w));
-    *reinterpret_cast<uint2*>(p + C) = make_uint2(pack_f16(f16_lo(v.x), f16_lo(v.y)), pack_f16(f16_lo(v.z), f16_lo(v.w)));
+    uint2 hi, lo;
+    split_f16_pair(v.x, v.y, hi.x, lo.x);
+    split_f16_pair(v.z, v.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(p) = hi;
+    *reinterpret_cast<uint2*>(p + C) = lo;
   } else if (mode == 1) {
     *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + row * ld + c) =
         make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));

@@ -250,7 +250,7 @@ class Generator(layers.PlanOwner, nn.Module):
             d0 = blocks[0][0]
             if self.fuse_resblocks and ops.Resblock2.eligible(C, Lr):
                 xs = ops.alloc_act(B, Lr + 2 * d0, C, P, dev)
-                up_raw(cur, B, L, out=xs, out_row0=d0, reflect=d0, phases=r)            # ConvTranspose1d: raw stream + halo
+                up_raw(cur, B, L, out=xs, out_row0=d0, reflect=d0, phases=r, halo_after=True)   # ConvTranspose1d: raw stream + halo
                 if taps is not None:
                     taps[f"up{si}"] = packing.act_to_float(xs[:, d0:d0 + Lr], P)
                 for j, (d, _, _, fused) in enumerate(blocks):
@@ -272,7 +272,8 @@ class Generator(layers.PlanOwner, nn.Module):
             else:
                 x_raw = ops.alloc_act(B, Lr, C, P, dev)
                 xa = ops.alloc_act(B, Lr + 2 * d0, C, "f16", dev)
-                up_act(cur, B, L, out=xa, out_row0=d0, reflect=d0, out_raw=x_raw, phases=r, out_fmt="f16", raw_fmt=P)
+                up_act(cur, B, L, out=xa, out_row0=d0, reflect=d0, out_raw=x_raw, phases=r, out_fmt="f16", raw_fmt=P,
+                       halo_after=True)
                 if taps is not None:
                     taps[f"up{si}"] = packing.act_to_float(x_raw, P)
                 for j, (d, c3, k1, _) in enumerate(blocks):
@@ -282,7 +283,8 @@ class Generator(layers.PlanOwner, nn.Module):
                         dn = blocks[j + 1][0]
                         y_raw = ops.alloc_act(B, Lr, C, P, dev)
                         ya = ops.alloc_act(B, Lr + 2 * dn, C, "f16", dev)
-                        k1([h1, x_raw], B, Lr, out=ya, out_row0=dn, reflect=dn, out_raw=y_raw, out_fmt="f16", raw_fmt=P)
+                        k1([h1, x_raw], B, Lr, out=ya, out_row0=dn, reflect=dn, out_raw=y_raw, out_fmt="f16", raw_fmt=P,
+                           halo_after=True)
                         x_raw, xa = y_raw, ya
                     elif not last_stage:
                         cur = ops.alloc_act(B, Lr, C, P, dev)

@@ -146,13 +146,15 @@ class ConvGemm:
         return self
 
     def __call__(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                 out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None):
+                 out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None, halo_after=False):
         """srcs: channels-last activation tensors [B][rows][C_s], one per logical source.
         out: act(v) [B][rows_out][Cs'] (operand format) at rows out_row0 + time (+ `reflect` mirrored halo rows);
         out_raw: v before the activation [B][phases*T][Cs'] (operand format); out2: act(v) as exact fp32
         [B*phases*T][Cs]; residual fp32 [B*phases*T][Cs] is added before the activation.  Cs = N / phases.
         out_fmt / raw_fmt: operand format (a precision name) of out / out_raw when it differs from this layer's own
-        input precision -- e.g. a "fp16s" layer writing LeakyReLU(y) as "f16" and y as "fp16s"."""
+        input precision -- e.g. a "fp16s" layer writing LeakyReLU(y) as "f16" and y as "fp16s".
+        halo_after: write the `reflect` halo rows with a separate avc_reflect_halo launch instead of in the GEMM's
+        epilogue, which keeps the GEMM on its branch-free store path."""
         lib = _lib.load()
         meta = self.meta
         if not isinstance(srcs, (list, tuple)):
@@ -204,7 +206,8 @@ class ConvGemm:
             d.out_row0 = out_row0
             d.out_dtype = _dt(out_fmt)
             d.out_round_tf32 = 1 if (round_tf32 and out.dtype == torch.float32) else 0
-            d.out_reflect = reflect
+            d.out_reflect = 0 if halo_after else reflect
+            assert not halo_after or out.is_contiguous()
         if out_raw is not None:
             assert out_raw.is_cuda and out_raw.dtype == TORCH_DTYPE[raw_fmt] and out_raw.stride(-1) == 1
             assert out_raw.shape[-1] >= packing.act_channels(cs, raw_fmt)
@@ -230,7 +233,21 @@ class ConvGemm:
             d.debug_clk = dbg.data_ptr()
         with PROFILER.span(self.tag, flops=2.0 * self.macs_per_row * B * T):
             _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
+        if halo_after and reflect and out is not None:
+            reflect_halo(out, out_row0, T * phases, reflect)
         return out if out is not None else (out2 if out2 is not None else out_raw)
+
+
+def reflect_halo(buf, row0, L, reflect):
+    """Fill the `reflect` mirrored rows each side of rows [row0, row0 + L) of a channels-last buffer [B][rows][C']."""
+    lib = _lib.load()
+    _require_cuda(buf)
+    assert buf.dim() == 3 and buf.is_contiguous()
+    B, rows, _ = buf.shape
+    with PROFILER.span("halo", bytes=float(2 * B * 2 * reflect * buf.shape[2] * buf.element_size())):
+        _lib.check(lib.avc_reflect_halo(buf.data_ptr(), B, rows, buf.shape[2] * buf.element_size(), row0, L, reflect,
+                                        _stream()), "avc_reflect_halo")
+    return buf
 
 
 def persistent_batch_cap(H, n_sm=148):

@@ -293,6 +293,15 @@ int avc_linear_rows(const float* h, const float* w, const float* bias, float* ou
                     int N, void* stream);
 
 /*
+ * Fill the `reflect` halo rows each side of a channels-last buffer [B][rows_per_utt][row_bytes]: row (row0 - k) = row
+ * (row0 + k), row (row0 + L - 1 + k) = row (row0 + L - 1 - k), k = 1..reflect -- nn.ReflectionPad1d of the consumer
+ * (melgan/modules.py:77,96,121).  avc_conv_gemm can write these rows itself (out_reflect), but only on its general
+ * epilogue path; the MelGAN "fp16s" layers keep the GEMM on its branch-free path and add the 2 x reflect rows per
+ * utterance with this launch (a few KB).  row_bytes multiple of 16.
+ */
+int avc_reflect_halo(void* buf, int B, int rows_per_utt, long long row_bytes, int row0, int L, int reflect, void* stream);
+
+/*
  * in [B][C][L] fp32 (channels-first, the reference's (B, 80, T) mel layout) -> out [B][L + 2*pad][C'] channels-last in
  * out_dtype (C' = C, or 2C for split bf16), with `pad` reflected rows each side (nn.ReflectionPad1d(3) in front of the
  * MelGAN stem, melgan/modules.py:96; `mel.transpose` at conversion.ipynb cell 14).  C multiple of 4, L > pad.

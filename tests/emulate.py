@@ -60,7 +60,7 @@ _ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(
 
 
 def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                       out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None):
+                       out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None, halo_after=False):
     meta = self.meta
     prec = self.precision
     out_fmt = out_fmt or prec
