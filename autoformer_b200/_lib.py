@@ -152,6 +152,7 @@ class Resblock2Desc(ctypes.Structure):
         ("y_act", ctypes.c_int),
         ("out2", ctypes.c_void_p),
         ("out2_ld", ctypes.c_longlong),
+        ("debug_clk", ctypes.c_void_p),
     ]
 
 

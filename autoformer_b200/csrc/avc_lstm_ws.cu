@@ -86,24 +86,7 @@ __device__ __forceinline__ void st_async_f4(uint32_t addr, uint32_t mbar, float4
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("avc: cluster mbarrier timeout block %d thread %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
+// (mbar_wait_cluster: the cluster-scope acquire wait lives in avc_ptx.cuh)
 
 // F16 ("fp16x2" precision, W in tensor memory only): h is one fp16 value per unit, the weights two fp16 terms; both
 // products W_hi x h and W_lo x h are N = AR MMAs onto the SAME accumulator columns.

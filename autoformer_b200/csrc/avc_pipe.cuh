@@ -252,6 +252,16 @@ __device__ __forceinline__ float f16_lo(float v) {
   const float s = sat_f16(v);
   return s - __half2float(__float2half_rn(s));
 }
+// Cheaper two-term split for the fused ResnetBlock epilogues (6 instructions for two values): hi = v with the 13 low
+// mantissa bits cleared -- exactly representable in fp16 over its normal range, so the pack below is exact -- and
+// lo = v - hi, exact in fp32, < 2^-10 |v|, rounded to fp16 by its own pack: hi + lo = v to ~2^-21.  (hi is truncated, not
+// rounded, so it is NOT fp16(v); every consumer reads hi + lo.)  Out-of-range values saturate in the packs.
+__device__ __forceinline__ void split_f16_pair_trunc(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+  hi = pack_f16(h0, h1);
+  lo = pack_f16(v0 - h0, v1 - h1);
+}
 // (v0, v1) -> packed hi pair and packed lo pair of the two-term form (8 instructions for two values)
 __device__ __forceinline__ void split_f16_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   hi = pack_f16(v0, v1);

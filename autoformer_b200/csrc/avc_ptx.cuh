@@ -262,6 +262,57 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
+// Same with release semantics at CLUSTER scope: the arriving CTA's earlier writes (its shared-memory operand tiles) are
+// ordered before whatever the leader does after a cluster-scope acquire of the barrier.
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Latency-critical cluster-scope wait: mbarrier.test_wait never suspends the thread (try_wait may park it for a
+// system-chosen time), so the waiter reacts within a few cycles of the last arrival.  For the ONE thread whose reaction
+// time is on a serial chain (the MMA issuer between the phases of a fused kernel); bounded like the others.
+__device__ __forceinline__ void mbar_spin_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("avc: cluster mbarrier spin timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, (void*)bar, parity);
+      __trap();
+    }
+  }
+}
+// Bounded cluster-scope acquire wait (see mbar_wait).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("avc: cluster mbarrier timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             (void*)bar, parity);
+      __trap();
+    }
+  }
+}
 
 // K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 128 bytes, 8-row
 // groups 1024 bytes apart).  Field layout: bits [0,14) start address >> 4, [16,30) leading byte

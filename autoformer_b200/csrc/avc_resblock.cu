@@ -417,10 +417,10 @@ __device__ __forceinline__ void write_split_f16(uint8_t* tiles, int row, int c0,
                                                 uint4 (&lo)[NCH / 8]) {
 #pragma unroll
   for (int j = 0; j < NCH / 8; ++j) {
-    split_f16_pair(v[j * 8], v[j * 8 + 1], hi[j].x, lo[j].x);
-    split_f16_pair(v[j * 8 + 2], v[j * 8 + 3], hi[j].y, lo[j].y);
-    split_f16_pair(v[j * 8 + 4], v[j * 8 + 5], hi[j].z, lo[j].z);
-    split_f16_pair(v[j * 8 + 6], v[j * 8 + 7], hi[j].w, lo[j].w);
+    split_f16_pair_trunc(v[j * 8], v[j * 8 + 1], hi[j].x, lo[j].x);
+    split_f16_pair_trunc(v[j * 8 + 2], v[j * 8 + 3], hi[j].y, lo[j].y);
+    split_f16_pair_trunc(v[j * 8 + 4], v[j * 8 + 5], hi[j].z, lo[j].z);
+    split_f16_pair_trunc(v[j * 8 + 6], v[j * 8 + 7], hi[j].w, lo[j].w);
     const int chunk = c0 / 8 + j;
     uint8_t* r = tiles + row * kRowBytes;
     if (C == 64) {
@@ -709,13 +709,15 @@ static int launch2(const Rb2Params& p, cudaStream_t stream) {
   return 0;
 }
 
+int launch_resblock2_big(const avc_resblock2_desc* d, cudaStream_t stream);   // avc_resblock_big.cu (C = 128)
+
 }  // namespace avc
 
 extern "C" int avc_resblock2(const avc_resblock2_desc* d, void* stream_v) {
   using namespace avc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   AVC_REQUIRE(d != nullptr, "avc_resblock2: null descriptor");
-  AVC_REQUIRE(d->C == 32 || d->C == 64, "avc_resblock2: C=%d (32 or 64)", d->C);
+  AVC_REQUIRE(d->C == 32 || d->C == 64 || d->C == 128, "avc_resblock2: C=%d (32, 64 or 128)", d->C);
   AVC_REQUIRE(d->B > 0 && d->L > 0 && d->L % kBlockM == 0, "avc_resblock2: B=%d L=%d (L must be a multiple of 128)",
               d->B, d->L);
   AVC_REQUIRE(d->dilation >= 1 && d->dilation <= 16, "avc_resblock2: dilation %d (1..16)", d->dilation);
@@ -723,6 +725,7 @@ extern "C" int avc_resblock2(const avc_resblock2_desc* d, void* stream_v) {
   AVC_REQUIRE(d->x_ld >= 2 * d->C, "avc_resblock2: input row stride too small");
   AVC_REQUIRE((d->y != nullptr) != (d->out2 != nullptr), "avc_resblock2: exactly one of y / out2");
   AVC_REQUIRE((long long)d->B * d->L < (1LL << 31), "avc_resblock2: B*L too large");
+  if (d->C == 128) return launch_resblock2_big(d, stream);
   const int C = d->C, P = C == 64 ? 2 : 1;
   const uint64_t B = (uint64_t)d->B, L = (uint64_t)d->L;
   Rb2Params p;

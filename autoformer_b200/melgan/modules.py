@@ -118,7 +118,7 @@ class _PlanF16s:
                                                              b(p + ".block.4") + b(p + ".shortcut"), "fp16s"),
                                   tap_t0=[0, 0], act="lrelu", tag="melgan_conv")
                 fused = None
-                if c_out in packing.RESBLOCK_CHANNELS:
+                if c_out in packing.RESBLOCK2_CHANNELS:
                     fused = ops.Resblock2(*packing.pack_resblock2(W(p + ".block.2"), b(p + ".block.2"), W(p + ".block.4"),
                                                                   b(p + ".block.4"), W(p + ".shortcut"),
                                                                   b(p + ".shortcut")), dilation=d)

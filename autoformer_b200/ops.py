@@ -567,7 +567,7 @@ class Resblock2:
 
     @staticmethod
     def eligible(C, L):
-        return C in packing.RESBLOCK_CHANNELS and L % 128 == 0
+        return C in packing.RESBLOCK2_CHANNELS and L % 128 == 0
 
     def to(self, device):
         self.w, self.bias3, self.bias1 = self.w.to(device), self.bias3.to(device), self.bias1.to(device)
@@ -595,6 +595,9 @@ class Resblock2:
         else:
             assert out2.is_cuda and out2.dtype == torch.float32 and out2.shape == (B * L, C) and out2.is_contiguous()
             desc.out2, desc.out2_ld = out2.data_ptr(), out2.stride(0)
+        dbg = getattr(self, "debug_clk", None)
+        if dbg is not None:
+            desc.debug_clk = dbg.data_ptr()
         with PROFILER.span(self.tag, flops=2.0 * 5 * C * C * B * L,
                            bytes=float(x.numel() * 2 + (B * L * C * 4))):
             _lib.check(lib.avc_resblock2(ctypes.byref(desc), _stream()), "avc_resblock2")

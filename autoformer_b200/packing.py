@@ -191,6 +191,7 @@ def pack_linear(weight, bias, precision, block_n=None):
 
 
 RESBLOCK_CHANNELS = (32, 64)      # widths the fused ResnetBlock kernel (avc_resblock) is built for
+RESBLOCK2_CHANNELS = (32, 64, 128)   # ... and its "fp16s" successor avc_resblock2 (128: CTA pairs, streamed weights)
 
 
 def pack_resblock(w3, b3, w1, b1, wsc, bsc):
@@ -222,7 +223,19 @@ def pack_resblock2(w3, b3, w1, b1, wsc, bsc):
       C = 32: W3 tiles rows [w_hi | w_lo] (32 rows: the k3 operand rows are [xa | xa]);
               W1 / Wsc tiles rows [[w_hi | w_hi] (32) ; [w_lo | 0] (32)] (operand rows [a_hi | a_lo])."""
     c = w3.shape[0]
-    assert c in RESBLOCK_CHANNELS and w3.shape == (c, c, 3) and w1.shape == (c, c, 1) and wsc.shape == (c, c, 1)
+    assert c in RESBLOCK2_CHANNELS and w3.shape == (c, c, 3) and w1.shape == (c, c, 1) and wsc.shape == (c, c, 1)
+    if c == 128:
+        # CTA pairs, weights streamed: [matrix (W3 tap 0..2, W1, Wsc)][64-channel k-chunk][256 rows][64]; the 256 rows of a
+        # tile are CTA 0's half then CTA 1's half, each [w_hi[64 r .. 64 r + 64) ; w_lo[64 r .. 64 r + 64)]
+        tiles = []
+        for m in (w3[:, :, 0], w3[:, :, 1], w3[:, :, 2], w1[:, :, 0], wsc[:, :, 0]):
+            hi, lo = split_f16(m)
+            for kc in range(c // 64):
+                ks = slice(kc * 64, kc * 64 + 64)
+                tiles.append(torch.cat([hi[0:64, ks], lo[0:64, ks], hi[64:128, ks], lo[64:128, ks]], dim=0))
+        w = torch.cat(tiles, dim=0).contiguous()
+        assert w.shape == (10 * 256, 64) and w.dtype == torch.float16
+        return w, b3.float().contiguous(), (b1.float() + bsc.float()).contiguous()
     tiles = []
     for k in range(3):
         hi, lo = split_f16(w3[:, :, k])

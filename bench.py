@@ -472,7 +472,7 @@ def profile_families(fn, steps, pk, passes):
     return family_summary(steps, pk, passes)
 
 
-PASSES = {"fp32": 3, "fp16x2": 2, "tf32": 2, "bf16": 1}      # bf16-MMA-equivalent passes per algorithmic FLOP
+PASSES = {"fp32": 3, "fp16x2": 2, "tf32": 2, "bf16": 1, "fp16s": 3}      # bf16-MMA-equivalent passes per algorithmic FLOP
 
 
 def dram_traffic(kernel, key):
@@ -580,7 +580,7 @@ def sub_cfg4(ctx, ref, pk, B, T=1000):
     ms_vc = events_ms(lambda: pipeline.convert(vc, sd_, eo, et), steps=2, warmup=1)
     melT = mel.transpose(2, 1).contiguous()
     ms_gen = events_ms(lambda: gen(melT), steps=2, warmup=1)
-    fam_gen = profile_families(lambda: gen(melT), 1, pk, PASSES[MELGAN_PRECISION])
+    fam_gen = profile_families(lambda: gen(melT), 1, pk, None)      # (mixed two- and three-product layers)
     fam_dv = profile_families(lambda: dv(both), 1, pk, PASSES["fp16x2"])
     # parity of one utterance end to end against the reference pipeline on the CPU (same recipe: embed both, zero-pad
     # to a multiple of freq, convert, trim, vocode), and of the vocoder alone on the reference's own converted mel
@@ -611,7 +611,9 @@ def sub_cfg4(ctx, ref, pk, B, T=1000):
                 rel_l2=par, families=dict(melgan=fam_gen, lstmdv=fam_dv))
 
 
-MELGAN_PRECISION = os.environ.get("AVC_BENCH_MELGAN_PRECISION", "fp32")
+# "fp16s" (round 2): residual stream / ConvTranspose operands / ResnetBlock intermediate as two fp16 terms, the k3 operand
+# as one; waveform rel-L2 <= 5.3e-4 over six weight seeds (scripts/melgan_precision_study.py); "fp32" = split bf16
+MELGAN_PRECISION = os.environ.get("AVC_BENCH_MELGAN_PRECISION", "fp16s")
 
 
 def sub_cfg5(ctx, ref, pk, args, precision):

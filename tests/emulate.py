@@ -345,7 +345,16 @@ def _emu_resblock2_call(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=Fals
     C, d = self.C, self.dilation
     assert x.shape == (B, L + 2 * d, 2 * C) and x.dtype == torch.float16 and L % 128 == 0
     w = self.w.double()
-    if C == 64:
+    if C == 128:      # [matrix][k-chunk][CTA 0: w_hi[0:64]; w_lo[0:64] | CTA 1: w_hi[64:128]; w_lo[64:128]][64]
+        mats = []
+        for m in range(5):
+            mat = torch.zeros(128, 128, dtype=torch.float64)
+            for kc in range(2):
+                t = w[(m * 2 + kc) * 256:(m * 2 + kc + 1) * 256]
+                mat[0:64, kc * 64:kc * 64 + 64] = t[0:64] + t[64:128]
+                mat[64:128, kc * 64:kc * 64 + 64] = t[128:192] + t[192:256]
+            mats.append(mat)
+    elif C == 64:
         tiles = [w[128 * i:128 * (i + 1)] for i in range(5)]
         mats = [t[:64] + t[64:] for t in tiles]
     else:
