@@ -43,8 +43,9 @@ struct PipeCfg {
   // full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], extra barrier, epilogue-done barrier, TMEM address word
   static constexpr int kSmemBytes = kBarOffset + (2 * kMaxStages + 6) * 8 + 16 + 1024 /* alignment slack */;
   static constexpr int kAccCols = ACCW;
-  static constexpr uint32_t kTmemCols = ACCW * ACC < 32 ? 32 : ACCW * ACC;
-  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns: power of two, at most 512");
+  static constexpr uint32_t pow2_at_least(uint32_t v) { uint32_t r = 32; while (r < v) r <<= 1; return r; }
+  static constexpr uint32_t kTmemCols = pow2_at_least(ACCW * ACC);      // allocations are powers of two >= 32
+  static_assert(kTmemCols <= 512, "TMEM columns: at most 512");
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };

@@ -90,6 +90,15 @@ def lstm_ws_default():
     return os.environ.get("AVC_LSTM_WS", "1") != "0"
 
 
+def gate28_default():
+    """AVC_LSTM_G28=1 selects 28-unit gate tiles where they fill more SMs (H = 1024, B = 512: 37 x 4 = 148 CTAs instead
+    of 128).  Built, parity-tested (bit-identical outputs) and MEASURED SLOWER on the bench configuration -- LSTM layers
+    4.30 ms against 4.14 ms per step (gpurun r02i): the frame is bound by its serial shadow (barrier among more CTAs, cell
+    update in groups of 4 units, 15 % more h-tile loads out of L2), not by the MMAs the extra SMs would shorten -- so
+    the default stays 32."""
+    return os.environ.get("AVC_LSTM_G28", "0") == "1"
+
+
 def lstm_fused_default():
     """AVC_LSTM_FUSED=0 selects the two-kernel form (dense input projection, then the recurrence) for A/B timing."""
     return os.environ.get("AVC_LSTM_FUSED", "1") != "0"
@@ -153,8 +162,9 @@ class LstmLayer:
             if out is not None:
                 return out
             self.ws = False             # the device cannot hold the grid: batched kernel from now on
-        group = ops.choose_gate_group(B, self.H, persistent)
-        if self.use_fused(B):
+        fused = self.use_fused(B)
+        group = ops.choose_gate_group(B, self.H, persistent, fused=fused and gate28_default(), precision=self.precision)
+        if fused:
             wih, bias, hh = self.fused_packs(group)
             return ops.lstm_seq(None, hh, B, T, self.H, self.precision, group, hseq=hseq, hseq_f32=hseq_f32,
                                 h_last=h_last, persistent=persistent, xin=x, w_ih=wih, bias=bias, c_in=self.C_in)

@@ -256,23 +256,36 @@ WS_GROUP = "ws"     # gate packing of the weight-stationary small-batch recurren
 
 def gate_permutation(hidden: int, group, device=None) -> torch.Tensor:
     """index[p] = PyTorch gate row (g*H + u) stored at packed position p = (u//G)*4G + g*G + u%G; for
-    group == WS_GROUP the four gates of a unit are adjacent: p = 128 (u//32) + 4 (u%32) + g."""
-    p = torch.arange(4 * hidden, device=device)
+    group == WS_GROUP the four gates of a unit are adjacent: p = 128 (u//32) + 4 (u%32) + g.
+
+    When G does not divide H (G = 28: 37 tiles of H = 1024 fill the 148 SMs) the last tile is ragged: there are
+    ceil(H/G) * 4G packed positions and those of the missing units hold -1 (``take_rows`` turns them into zero rows)."""
     if group == WS_GROUP:
+        p = torch.arange(4 * hidden, device=device)
         assert hidden % 32 == 0
         return (p % 4) * hidden + (p // 128) * 32 + (p % 128) // 4
-    assert hidden % group == 0
+    tiles = (hidden + group - 1) // group
+    p = torch.arange(tiles * 4 * group, device=device)
     blk = p // (4 * group)
     g = (p % (4 * group)) // group
     u = blk * group + p % group
-    return g * hidden + u
+    return torch.where(u < hidden, g * hidden + u, torch.full_like(u, -1))
+
+
+def take_rows(t: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """t[perm] with zero rows where perm is -1 (the padding units of a ragged last gate tile)."""
+    out = t[perm.clamp(min=0)]
+    if bool((perm < 0).any()):
+        out = out.clone()
+        out[perm < 0] = 0
+    return out
 
 
 def pack_lstm_ih(w_ih, b_ih, b_hh, precision, group):
     """Input projection of one uni-directional layer with gate-interleaved output columns."""
     h = w_ih.shape[0] // 4
     perm = gate_permutation(h, group, w_ih.device)
-    return pack_linear(w_ih[perm], (b_ih + b_hh)[perm], precision)
+    return pack_linear(take_rows(w_ih, perm), take_rows(b_ih + b_hh, perm), precision)
 
 
 def pack_lstm_ih_fused(w_ih, b_ih, b_hh, precision, group):
@@ -281,9 +294,9 @@ def pack_lstm_ih_fused(w_ih, b_ih, b_hh, precision, group):
     h, c_in = w_ih.shape[0] // 4, w_ih.shape[1]
     perm = gate_permutation(h, group, w_ih.device)
     kpad = _ceil_to(c_in, KC[precision])
-    w = torch.zeros(4 * h, kpad, dtype=torch.float32, device=w_ih.device)
-    w[:, :c_in] = w_ih[perm].float()
-    bias = (b_ih.float() + b_hh.float())[perm].contiguous()
+    w = torch.zeros(perm.numel(), kpad, dtype=torch.float32, device=w_ih.device)
+    w[:, :c_in] = take_rows(w_ih.float(), perm)
+    bias = take_rows(b_ih.float() + b_hh.float(), perm).contiguous()
     if precision in TWO_TERM_WEIGHTS:
         hi, lo = split_terms(w, precision)
         return torch.cat([hi, lo], dim=1).contiguous(), bias
@@ -293,7 +306,7 @@ def pack_lstm_ih_fused(w_ih, b_ih, b_hh, precision, group):
 def pack_lstm_hh(w_hh, precision, group):
     h = w_hh.shape[1]
     perm = gate_permutation(h, group, w_hh.device)
-    w = w_hh[perm].float()
+    w = take_rows(w_hh.float(), perm)
     if precision in TWO_TERM_WEIGHTS:
         hi, lo = split_terms(w, precision)
         # [w_hi | w_lo]; "fp32": the kernel forms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, "fp16x2": a*w_hi + a*w_lo

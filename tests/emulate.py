@@ -114,13 +114,14 @@ def _emu_lstm_seq(xproj, w_hh, B, T, H, precision, group, hseq=None, hseq_f32=No
         assert xproj is None
         kc = KC[precision]
         kp = (c_in + kc - 1) // kc * kc
-        assert w_ih.shape == (4 * H, 2 * kp if two else kp) and bias.shape == (4 * H,)
+        rows = (H + group - 1) // group * 4 * group          # ragged last gate tile when G does not divide H
+        assert w_ih.shape == (rows, 2 * kp if two else kp) and bias.shape == (rows,) and w_hh.shape[0] == rows
         wi = (w_ih[:, :kp].double() + w_ih[:, kp:].double()) if two else w_ih.double()
         assert float(wi[:, c_in:].abs().max()) == 0.0 if kp > c_in else True
         assert xin.shape[:2] == (B, T) and xin.dtype == packing.TORCH_DTYPE[precision]
         xa = packing.act_to_float(xin[..., :packing.act_channels(c_in, precision)], precision).double()
         xproj = xa @ wi[:, :c_in].t() + bias.double()
-    xp = xproj.double().reshape(B, T, 4 * H)
+    xp = xproj.double().reshape(B, T, -1)
     h = torch.zeros(B, H, dtype=torch.float64)
     c = torch.zeros(B, H, dtype=torch.float64)
     outs = torch.zeros(B, T, H, dtype=torch.float64)
