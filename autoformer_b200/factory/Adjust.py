@@ -53,7 +53,7 @@ class Adjust(layers.PlanOwner, nn.Module):
 
     def _plan(self):
         def build():
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            sd = layers.state_for_packing(self)
             return AdjustPlan(sd, "", self.precision)
         return self._cache.get(self, (self.precision,), build)
 

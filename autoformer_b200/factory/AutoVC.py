@@ -73,7 +73,7 @@ def check_hyper_parameters(dim_neck, dim_emb, dim_pre, freq):
 
 class _Plan:
     def __init__(self, model, precision):
-        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        sd = layers.state_for_packing(model)
         self.precision = precision
         self.enc_convs = [layers.conv_bn_layer(sd, f"encoder.convolutions.{i}", precision, "relu") for i in range(3)]
         self.enc_lstm = layers.BiLstmSmall(sd, "encoder.lstm", 2, precision)

@@ -22,7 +22,7 @@ class LstmDV(layers.PlanOwner, nn.Module):
         self._cache = layers.PlanCache()
 
     def _build_plan(self):
-        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        sd = layers.state_for_packing(self)
         return dict(lstm=layers.lstm_layers(sd, "lstm", self.num_layers, self.precision),
                     w=sd["embedding.weight"].float().contiguous(), b=sd["embedding.bias"].float().contiguous())
 

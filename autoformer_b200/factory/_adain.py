@@ -50,7 +50,7 @@ class AdaINMixin:
 
     def _adain_plan(self):
         def build():
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            sd = layers.state_for_packing(self)
             return AdaINPlan(sd, self.precision)
         return self._adain_cache.get(self, (self.precision,), build)
 

@@ -194,7 +194,7 @@ class BlockPlan:
 
 class _Plan:
     def __init__(self, model, kind, precision):
-        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        sd = layers.state_for_packing(model)
         self.precision = precision
         emb = lambda p: ops.ConvGemm(*packing.pack_conv(sd[p + ".weight"].float(), sd[p + ".bias"].float(), precision),
                                      tag="conv")

@@ -7,6 +7,40 @@ from . import ops, packing
 from .packing import TORCH_DTYPE
 
 
+# Where the one-off weight folding / re-packing of a model runs.  False (default): on the model's own device -- a few
+# hundred tiny torch kernels per model, microseconds each.  True: on the host, the packed tensors then move to the device
+# with plain copies -- no torch kernel is launched at all, which keeps a profiler's launch list of a short run (smoke())
+# to this library's own kernels.  Same arithmetic either way (torch CPU vs CUDA elementwise ops, fp64 folding).
+PACK_ON_CPU = False
+
+
+def state_for_packing(module):
+    """The module's state_dict as detached tensors, on the host when PACK_ON_CPU."""
+    sd = {k: v.detach() for k, v in module.state_dict().items()}
+    if PACK_ON_CPU:
+        sd = {k: v.cpu() for k, v in sd.items()}
+    return sd
+
+
+def plan_to(obj, device, _seen=None):
+    """Move every tensor reachable from a packed plan (objects of this package, lists, tuples, dicts) to `device`."""
+    if _seen is None:
+        _seen = set()
+    if torch.is_tensor(obj):
+        return obj.to(device)
+    if isinstance(obj, (list, tuple)):
+        moved = [plan_to(o, device, _seen) for o in obj]
+        return type(obj)(moved) if isinstance(obj, tuple) else moved
+    if isinstance(obj, dict):
+        return {k: plan_to(v, device, _seen) for k, v in obj.items()}
+    if hasattr(obj, "__dict__") and type(obj).__module__.startswith("autoformer_b200") and id(obj) not in _seen:
+        _seen.add(id(obj))
+        for k, v in list(vars(obj).items()):
+            if torch.is_tensor(v) or isinstance(v, (list, tuple, dict)) or hasattr(v, "__dict__"):
+                setattr(obj, k, plan_to(v, device, _seen))
+    return obj
+
+
 class PlanCache:
     """Re-pack weights only when a parameter/buffer was replaced, moved or modified.
 
@@ -14,8 +48,8 @@ class PlanCache:
     through ``.data`` (``p.data.normal_()``, ``p.data.copy_(w)`` -- what the reference's MelGAN ``weights_init`` does,
     melgan/modules.py:9-15) do not bump ``_version``, so the version counter alone would leave a stale plan and the
     forward would silently run with old weights.  The digest is the 1- and 2-norm of every floating-point tensor,
-    computed on the tensors' device with two multi-tensor launches (``torch._foreach_norm``) and fetched with one small
-    copy per forward.  ``frozen = True`` (set by the models' ``freeze_weights()``) skips the digest for serving loops
+    computed on the tensors' device with multi-tensor launches (``torch._foreach_norm``: a handful of kernels for all
+    tensors of one dtype) and fetched with one small copy per forward.  ``frozen = True`` (set by the models' ``freeze_weights()``) skips the digest for serving loops
     that promise not to touch the weights; ``invalidate()`` forces a re-pack."""
 
     def __init__(self):
@@ -35,7 +69,7 @@ class PlanCache:
         for ts in by_dev.values():
             n1 = torch._foreach_norm(ts, 1)
             n2 = torch._foreach_norm(ts, 2)
-            digest.append(tuple(torch.stack([v.double() for v in n1] + [v.double() for v in n2]).tolist()))
+            digest.append(tuple(torch.stack(list(n1) + list(n2)).tolist()))      # one stack, one copy
         return (tuple(items), tuple(extra), tuple(digest))
 
     def invalidate(self):
@@ -48,7 +82,12 @@ class PlanCache:
             return self.plan
         key = self.fingerprint(module, extra, True)
         if key != self.key:
-            self.plan = builder()
+            plan = builder()
+            if PACK_ON_CPU:
+                first = next(iter(module.parameters()), None)
+                if first is not None and first.is_cuda:
+                    plan = plan_to(plan, first.device)
+            self.plan = plan
             self.key = key
         return self.plan
 

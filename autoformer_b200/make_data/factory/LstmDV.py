@@ -12,7 +12,7 @@ L2-normalised form (:21-23), then ``predictions = output(embeds)`` on the UN-nor
 import torch
 import torch.nn as nn
 
-from ... import ops
+from ... import layers, ops
 from ...factory.LstmDV import LstmDV as _Embedder
 
 
@@ -25,7 +25,7 @@ class LstmDV(_Embedder):
     def _plan(self):
         def build():
             plan = self._build_plan()
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            sd = layers.state_for_packing(self)
             plan["w_out"] = sd["output.weight"].float().contiguous()
             plan["b_out"] = sd["output.bias"].float().contiguous()
             return plan

@@ -46,7 +46,7 @@ class ResnetBlock(nn.Module):
 
 class _Plan:
     def __init__(self, gen, precision):
-        sd = {k: v.detach() for k, v in gen.state_dict().items()}
+        sd = layers.state_for_packing(gen)
         W = lambda p: packing.fold_weight_norm(sd[p + ".weight_g"], sd[p + ".weight_v"])
         b = lambda p: sd[p + ".bias"].float()
         self.precision = precision
@@ -92,7 +92,7 @@ class _PlanF16s:
     (avc_resblock2) that reads the raw stream and writes its output, nothing else."""
 
     def __init__(self, gen):
-        sd = {k: v.detach() for k, v in gen.state_dict().items()}
+        sd = layers.state_for_packing(gen)
         W = lambda p: packing.fold_weight_norm(sd[p + ".weight_g"], sd[p + ".weight_v"])
         b = lambda p: sd[p + ".bias"].float()
         self.precision = "fp16s"

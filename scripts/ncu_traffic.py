@@ -1,7 +1,7 @@
 """Summarise .ncu-rep captures into (a) a per-launch text table for profiles/ and (b) profiles/r02_dram_traffic.json,
 the table bench.py reads `roofline.traffic` from (DRAM bytes per launch = dram__bytes_read.sum + dram__bytes_write.sum).
 
-    python scripts/ncu_traffic.py <config key> <file.ncu-rep> [<out.txt>]
+    python scripts/ncu_traffic.py <config key> <file.ncu-rep | raw-page .csv | .csv.gz> [<out.txt>]
 
 Runs in the build container (ncu -i needs no GPU)."""
 import csv
@@ -37,7 +37,13 @@ def short(name):
 
 
 def main(key, path, out_txt=None):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".gz"):
+        import gzip
+        raw = gzip.open(path, "rt").read()
+    elif path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
