@@ -392,6 +392,11 @@ struct Rb2Cfg {
   static constexpr uint32_t kD2Cols = 2 * C;
   static constexpr uint32_t kTmemCols = C == 64 ? 256 : 128;
   static constexpr int kCtasPerSm = C == 32 ? 2 : 1;
+  // epilogue warps: a multiple of 4 (one set per TMEM lane quarter).  16 warps for C = 64 (16 channels per thread) were
+  // measured SLOWER than 8 (0.62 ms against 0.58 ms per block at B = 32, L = 128,000: the passes are bound by issue
+  // slots, not by latency), so both widths run 8
+  static constexpr int kEpi = 8;
+  static constexpr int kThreads = 64 + 32 * kEpi + 32 * 4 /* xa warps */;
   static_assert(kWBytes % 1024 == 0 && kWinTile % 1024 == 0, "tiles must stay 1024-byte aligned");
   static_assert(kSmemBytes * kCtasPerSm + 1024 * kCtasPerSm <= 228 * 1024, "shared memory budget exceeded");
 };
@@ -436,7 +441,8 @@ __device__ __forceinline__ void write_split_f16(uint8_t* tiles, int row, int c0,
 // xa = fp16(LeakyReLU(hi + lo)) for every row of the window, written with the window's own swizzle so that the three taps
 // read it through row-shifted descriptors.  C = 32: rows [xa | xa] against weight rows [w_hi | w_lo].
 constexpr int kXaWarps = 4;
-constexpr int kRb2Threads = kRbThreads + 32 * kXaWarps;
+template <int N>
+__device__ __forceinline__ void epilogue_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 template <int C>
 __device__ __forceinline__ void form_xa(const uint8_t* win, uint8_t* xa, int win_rows, int tid) {
@@ -496,10 +502,12 @@ __device__ __forceinline__ void issue_src_f16(uint32_t a0, uint32_t a1, uint32_t
 }
 
 template <int C>
-__global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_kernel(const __grid_constant__ Rb2Params p) {
+__global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) resblock2_kernel(const __grid_constant__ Rb2Params p) {
   using Cfg = Rb2Cfg<C>;
   constexpr int P = Cfg::kParts;
-  constexpr int NCH = C / 2;                 // channels per epilogue thread
+  constexpr int kEpi = Cfg::kEpi;
+  constexpr int kThreads = Cfg::kThreads;
+  constexpr int NCH = C / (kEpi / 4);        // channels per epilogue thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_w = base;
@@ -526,7 +534,7 @@ __global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_
     }
     mbar_init(xa_ready, kXaWarps);
     mbar_init(d1_full, 1);
-    mbar_init(mid_ready, kEpiWarps);
+    mbar_init(mid_ready, kEpi);
     mbar_init(d2_full, 1);
     fence_mbar_init();
 #pragma unroll
@@ -534,11 +542,11 @@ __global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_
   }
   // weight tiles -> shared memory, 128-byte swizzle (row n, 16-byte chunk c at n * 128 + ((c ^ n % 8) << 4)); every tile
   // starts on a multiple of 8 rows, so the global row index gives the right swizzle phase
-  for (int i = threadIdx.x; i < Cfg::kWBytes / 16; i += kRb2Threads) {
+  for (int i = threadIdx.x; i < Cfg::kWBytes / 16; i += kThreads) {
     const int n = i >> 3, c = i & 7;
     *reinterpret_cast<uint4*>(s_w + n * kRowBytes + ((c ^ (n & 7)) << 4)) = p.w[i];
   }
-  for (int i = threadIdx.x; i < 2 * C; i += kRb2Threads) s_bias[i] = i < C ? p.bias3[i] : p.bias1[i - C];
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) s_bias[i] = i < C ? p.bias3[i] : p.bias1[i - C];
   fence_proxy_async();          // the tensor core reads the weight tiles through the async proxy
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -585,9 +593,9 @@ __global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_
       }
     }
     __syncwarp();
-  } else if (warp >= 2 + kEpiWarps) {
+  } else if (warp >= 2 + kEpi) {
     // ---------------- xa warps: the k3 operand of tile i from its raw window, as soon as GEMM1(i-1) has read the xa tile
-    const int tid = threadIdx.x - kRbThreads;
+    const int tid = threadIdx.x - (64 + 32 * kEpi);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_
       for (int e = 0; e < NCH; ++e) v[e] = lrelu(v[e] + s_bias[c0 + e]);
       if (it > 0) {          // the previous tile's TMA stores must have read the staging tiles (= the intermediate tiles)
         if (storer) bulk_wait_read();
-        epilogue_bar();
+        epilogue_bar_n<32 * kEpi>();
       }
       write_split_f16<C, NCH>(s_mid, row, c0, v, hi, lo);
       fence_proxy_async();   // generic-proxy writes -> tensor-core (async proxy) reads
@@ -672,7 +680,7 @@ __global__ void __launch_bounds__(kRb2Threads, Rb2Cfg<C>::kCtasPerSm) resblock2_
       }
       fence_proxy_async();   // staging tiles -> TMA store (async proxy)
       tc_fence_before();
-      epilogue_bar();
+      epilogue_bar_n<32 * kEpi>();
       if (storer) {
 #pragma unroll
         for (int part = 0; part < P; ++part) {
@@ -703,7 +711,7 @@ static int launch2(const Rb2Params& p, cudaStream_t stream) {
   }
   const int max_ctas = num_sms() * Cfg::kCtasPerSm;
   const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-  kern<<<grid, kRb2Threads, Cfg::kSmemBytes, stream>>>(p);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(p);
   AVC_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -108,7 +108,11 @@ __device__ __forceinline__ void write_split32(uint8_t* tiles, int row, int c0, c
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) resblock2_big_kernel(const __grid_constant__ Params p) {
+}  // namespace big
+
+using namespace big;      // (the kernel itself lives in avc:: so that profilers list it beside the library's other kernels)
+
+__global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const __grid_constant__ big::Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_win = base + kOffWin;         // [term][chunk] window tiles
@@ -389,10 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) resblock2_big_kernel(const __grid
   }
 }
 
-}  // namespace big
-
 int launch_resblock2_big(const avc_resblock2_desc* d, cudaStream_t stream) {
-  using namespace big;
   AVC_REQUIRE(d->C == C, "avc_resblock2: wide kernel is built for C = %d", C);
   AVC_REQUIRE(d->dilation <= kMaxDilation, "avc_resblock2: C = 128 supports dilation <= %d", kMaxDilation);
   AVC_REQUIRE(d->y != nullptr && d->out2 == nullptr, "avc_resblock2: C = 128 writes y only (two fp16 terms)");

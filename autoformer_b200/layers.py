@@ -158,18 +158,25 @@ class LstmLayer:
         self._packs = {}
         self._fused_packs = {}
 
+    def _raw(self):
+        """The layer's raw weights where the (lazy, per gate group) packing runs: the host when PACK_ON_CPU."""
+        ws = (self.w_ih, self.w_hh, self.b_ih, self.b_hh)
+        return tuple(w.cpu() for w in ws) if PACK_ON_CPU else ws
+
     def fused_packs(self, group):
         if group not in self._fused_packs:
-            wih, bias = packing.pack_lstm_ih_fused(self.w_ih, self.b_ih, self.b_hh, self.precision, group)
-            self._fused_packs[group] = (wih, bias, packing.pack_lstm_hh(self.w_hh, self.precision, group))
+            w_ih, w_hh, b_ih, b_hh = self._raw()
+            wih, bias = packing.pack_lstm_ih_fused(w_ih, b_ih, b_hh, self.precision, group)
+            packs = (wih, bias, packing.pack_lstm_hh(w_hh, self.precision, group))
+            self._fused_packs[group] = tuple(t.to(self.w_hh.device) for t in packs)
         return self._fused_packs[group]
 
     def packs(self, group):
         if group not in self._packs:
-            ih = ops.ConvGemm(*packing.pack_lstm_ih(self.w_ih, self.b_ih, self.b_hh, self.precision, group),
-                              tag="inproj")
-            hh = packing.pack_lstm_hh(self.w_hh, self.precision, group)
-            self._packs[group] = (ih, hh)
+            w_ih, w_hh, b_ih, b_hh = self._raw()
+            ih = ops.ConvGemm(*packing.pack_lstm_ih(w_ih, b_ih, b_hh, self.precision, group), tag="inproj")
+            hh = packing.pack_lstm_hh(w_hh, self.precision, group)
+            self._packs[group] = (ih.to(self.w_hh.device), hh.to(self.w_hh.device))
         return self._packs[group]
 
     def use_fused(self, B):
