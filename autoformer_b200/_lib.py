@@ -61,6 +61,8 @@ class GemmDesc(ctypes.Structure):
         ("cta_group", ctypes.c_int),
         ("debug_clk", ctypes.c_void_p),
         ("out_raw_dtype", ctypes.c_int),
+        ("out_phase0", ctypes.c_int),
+        ("out_phase_count", ctypes.c_int),
     ]
 
 

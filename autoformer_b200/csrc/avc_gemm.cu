@@ -34,7 +34,8 @@ struct alignas(64) GemmParams {
   // epilogue
   const float* bias;
   int act;
-  int phases, cs;        // N = phases * cs; output time = phases * t + n / cs
+  int phases, cs;        // output time = phases * t + phase0 + n / cs; this launch produces N / cs of the `phases` phases
+  int phase0;
   void* out;
   long long out_ld;
   int out_rows_per_utt, out_row0, out_mode, out_round, out_reflect;   // out_mode: 0 fp32, 1 bf16, 2 split bf16, 3 fp16, 4 split fp16
@@ -161,7 +162,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
   // (poly-phase outputs qualify when a 32-column chunk lies inside one phase; reflected halo rows never do -- callers
   // that want the fast path write them with avc_reflect_halo afterwards)
   int simple = 0;
-  if (!split_rows && p.out_reflect == 0 && (p.phases == 1 || (p.cs & 31) == 0)) {
+  if (!split_rows && p.out_reflect == 0 && ((p.phases == 1 && p.phase0 == 0) || (p.cs & 31) == 0)) {
     if (p.out && !p.out2 && !has_res && p.out_mode != 0 && (!p.out_raw || p.raw_mode != 0)) simple = 1;
     if (!p.out && p.out2 && !(has_res && res_after) && p.phases == 1 && !p.out_raw) simple = 2;
   }
@@ -192,8 +193,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
       // k-blocks per tile were bound by it: 13.5 K cycles per 128 x 256 tile against 9 K cycles of MMAs).
       //   simple 1: act(v) to `out` (and optionally v itself to `out_raw`) in 16-bit operand formats, one or two terms
       //   simple 2: act(v [+ residual]) to `out2` (fp32), nothing else
-      const int phase = p.phases == 1 ? 0 : n / p.cs;      // constant over the chunk (cs % 32 == 0)
-      const int c = n - phase * p.cs;
+      const int pidx = p.phases == 1 ? 0 : n / p.cs;       // constant over the chunk (cs % 32 == 0)
+      const int c = n - pidx * p.cs;
+      const int phase = p.phase0 + pidx;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {          // (simple excludes split_rows: all eight row groups are this warp's)
         {
@@ -227,8 +229,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
         }
       }
     } else if (n < p.N) {
-      const int phase = p.phases == 1 ? 0 : n / p.cs;
-      const int c = n - phase * p.cs;
+      const int pidx = p.phases == 1 ? 0 : n / p.cs;
+      const int c = n - pidx * p.cs;
+      const int phase = p.phase0 + pidx;
 #pragma unroll 2
       for (int i = g_first; i < g_last; ++i) {
         const int m = q * 32 + 4 * i + rsub;
@@ -533,9 +536,15 @@ extern "C" int avc_conv_gemm(const avc_gemm_desc* d, void* stream_v) {
   p.bias = d->bias;
   p.act = d->act;
   p.phases = d->out_phases > 0 ? d->out_phases : 1;
-  AVC_REQUIRE(d->N % p.phases == 0 && (d->N / p.phases) % 4 == 0, "avc_conv_gemm: N=%d not divisible into %d phases",
-              d->N, p.phases);
-  p.cs = d->N / p.phases;
+  // a launch may produce only `out_phase_count` consecutive phases starting at `out_phase0` (the two halves of a
+  // ConvTranspose1d use different pairs of input taps and run as two GEMMs without the all-zero third tap)
+  const int phase_count = d->out_phase_count > 0 ? d->out_phase_count : p.phases;
+  p.phase0 = d->out_phase0;
+  AVC_REQUIRE(p.phase0 >= 0 && p.phase0 + phase_count <= p.phases, "avc_conv_gemm: phases [%d, %d) of %d", p.phase0,
+              p.phase0 + phase_count, p.phases);
+  AVC_REQUIRE(d->N % phase_count == 0 && (d->N / phase_count) % 4 == 0, "avc_conv_gemm: N=%d not divisible into %d phases",
+              d->N, phase_count);
+  p.cs = d->N / phase_count;
   const long long t_out = (long long)d->T * p.phases;
   p.out = d->out;
   p.out_ld = d->out_ld;

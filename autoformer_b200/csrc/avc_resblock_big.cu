@@ -44,7 +44,7 @@ constexpr int kRegionB = 2 * KC * kATileBytes;                   // 64 KB
 constexpr int kOffRing = kOffB + kRegionB;
 constexpr int kOffBias = kOffRing + kStages * kBStage;
 constexpr int kOffBar = kOffBias + 2 * C * 4;
-constexpr int kNumBars = 2 * kStages + 8;
+constexpr int kNumBars = 2 * kStages + 8;      // (7 used)
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024 /* alignment slack */;
 constexpr int kXaWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * kXaWarps;    // 576
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
   uint64_t* mid_ready = bars + 2 * kStages + 3;   // leader: intermediate written by the epilogue warps of BOTH CTAs
   uint64_t* d2_full = bars + 2 * kStages + 4;     // GEMM2 done (both CTAs): window and intermediate are free
   uint64_t* stage_free = bars + 2 * kStages + 5;  // this CTA's TMA stores have read the staging tiles: region B is free
+  uint64_t* d2_free = bars + 2 * kStages + 6;     // leader: the epilogue warps of BOTH CTAs have read accumulator 2
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
     mbar_init(mid_ready, 2 * kEpiWarps);
     mbar_init(d2_full, 1);
     mbar_init(stage_free, 1);
+    mbar_init(d2_free, 2 * kEpiWarps);
     fence_mbar_init();
     prefetch_tmap(&p.tmap_x);
     prefetch_tmap(&p.tmap_w);
@@ -202,10 +204,12 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
             for (int i = 0; i < 2 * KC; ++i) tma_prefetch_3d(&p.tmap_x, i * 64, nt0, nb);
           }
         }
-        for (int s = 0; s < kStagesPerTile; ++s) {             // weight tiles in consumption order: W3 (tap, chunk), W1, Wsc
+        for (int s = 0; s < kStagesPerTile; ++s) {             // weight tiles in CONSUMPTION order: W3 (tap, chunk), Wsc, W1
+          // (packed order is W3, W1, Wsc: the shortcut is issued before k1, see the MMA thread)
+          const int tile = s < 3 * KC ? s : (s < 4 * KC ? s + KC : s - KC);
           mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
           if (leader) mbar_arrive_expect_tx(&full[rs.stage], 2 * kBStage);
-          tma_load_2d_2sm(s_ring + rs.stage * kBStage, &p.tmap_w, &full[rs.stage], 0, s * 256 + rank * 128);
+          tma_load_2d_2sm(s_ring + rs.stage * kBStage, &p.tmap_w, &full[rs.stage], 0, tile * 256 + rank * 128);
           rs.advance<kStages>();
         }
         stamp(it, 1);                                          // all weight tiles of the tile requested
@@ -237,17 +241,24 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
         }
         umma_commit_2sm(d1_full, 0x3);
         stamp(it, 3);                                          // GEMM1 issued
-        // ---- GEMM2: D2 = [mid_hi, mid_lo] . W1 + [x_hi, x_lo](centre rows) . Wsc, three products per matrix:
-        // a_hi . [w_hi | w_lo] (N = 256) and a_lo . w_hi (N = 128, landing on a column block of the same channels)
-        mbar_spin_cluster(mid_ready, it & 1);
-        stamp(it, 4);                                          // intermediate of both CTAs ready
+        // ---- GEMM2: D2 = [x_hi, x_lo](centre rows) . Wsc + [mid_hi, mid_lo] . W1, three products per matrix:
+        // a_hi . [w_hi | w_lo] (N = 256) and a_lo . w_hi (N = 128, landing on a column block of the same channels).
+        // The shortcut half needs only the window, so it is issued right behind GEMM1 and runs while the epilogue warps
+        // turn accumulator 1 into the intermediate; it must not overwrite accumulator 2 before the previous tile's
+        // epilogue has read it.
+        if (it > 0) mbar_spin_cluster(d2_free, (it - 1) & 1);
         tc_fence_after();
         for (int m = 0; m < 2; ++m) {
+          if (m == 1) {
+            mbar_spin_cluster(mid_ready, it & 1);
+            stamp(it, 4);                                      // intermediate of both CTAs ready
+            tc_fence_after();
+          }
           for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(&full[rs.stage], rs.phase);
             tc_fence_after();
-            const uint32_t a_hi = m == 0 ? rb + kc * kATileBytes : win + kc * kWinTile + shift;
-            const uint32_t a_lo = m == 0 ? a_hi + KC * kATileBytes : a_hi + KC * kWinTile;
+            const uint32_t a_hi = m == 1 ? rb + kc * kATileBytes : win + kc * kWinTile + shift;
+            const uint32_t a_lo = m == 1 ? a_hi + KC * kATileBytes : a_hi + KC * kWinTile;
             const uint32_t w = ring + rs.stage * kBStage;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -298,10 +309,12 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
           }
         }
       }
-      fence_proxy_async();   // generic-proxy writes -> tensor-core (async proxy) reads
+      // generic-proxy writes -> tensor-core (async proxy) reads of THIS SM; the fence completes before the arrive below,
+      // so a plain remote arrive is enough (a cluster-scope release would also drain every earlier global store)
+      fence_proxy_async();
       __syncwarp();
       if (tid == 0) stamp(it, 8);                               // xa written (warp 0 of the xa warps)
-      if (lane == 0) mbar_arrive_leader_release(xa_ready);
+      if (lane == 0) mbar_arrive_leader(xa_ready);
     }
   } else {
     // ---------------- epilogue warps: thread owns sample `row`; the two warps of a TMEM lane quarter take 64 channels each
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
       tc_fence_before();
       __syncwarp();
       if (storer) stamp(it, 10);                                // intermediate written
-      if (lane == 0) mbar_arrive_leader_release(mid_ready);
+      if (lane == 0) mbar_arrive_leader(mid_ready);
       // ---- epilogue 2: y = k1(mid) + shortcut(x) + bias -> staging tiles (over the intermediate) -> TMA stores
       mbar_wait(d2_full, it & 1);
       if (storer) stamp(it, 11);                                // accumulator 2 ready
@@ -367,8 +380,10 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
           }
         }
       }
+      tc_fence_before();     // this warp's reads of accumulator 2 are complete: the next tile's shortcut may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(d2_free);
       fence_proxy_async();   // staging tiles -> TMA store (async proxy)
-      tc_fence_before();
       epilogue_bar();
       if (storer) stamp(it, 12);                                // staging tiles written by all epilogue warps
       if (storer) {

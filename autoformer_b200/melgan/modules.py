@@ -104,10 +104,21 @@ class _PlanF16s:
             wt = W(f"model.{idx + 1}")                                   # (C_in, C_out, 2r)
             c_out = wt.shape[1]
             w3 = packing.conv_transpose_as_conv(wt, r, r // 2 + r % 2)
-            packed_up = packing.pack_conv(w3, b(f"model.{idx + 1}").repeat(r), "fp16s")
-            # a fused stage wants the raw stream only; a layer-wise stage wants LeakyReLU(x) (one fp16) plus the raw x
-            up_raw = ops.ConvGemm(*packed_up, tap_t0=[-1], act="none", tag="melgan_up")
-            up_act = ops.ConvGemm(*packed_up, tap_t0=[-1], act="lrelu", tag="melgan_up")
+            bias_up = b(f"model.{idx + 1}")
+            # a fused stage wants the raw stream only; a layer-wise stage wants LeakyReLU(x) (one fp16) plus the raw x.
+            # Each output phase of the transposed convolution uses two of the three input taps -- (t-1, t) for phases
+            # < r/2, (t, t+1) for the rest -- so a wide up-sampler (r = 8) runs as two GEMMs of two taps each: a third
+            # less MMA work and operand traffic than one GEMM whose weights are one third zeros.  (r = 2 stays one GEMM:
+            # its halves would be N = C_out <= 64 wide, below the tile width at which the tensor pipe is fed.)
+            if r >= 4:
+                half = r // 2 * c_out
+                assert not w3[:half, :, 2].any() and not w3[half:, :, 0].any()
+                parts = [(packing.pack_conv(w3[:half, :, 0:2].contiguous(), bias_up.repeat(r // 2), "fp16s"), -1, 0),
+                         (packing.pack_conv(w3[half:, :, 1:3].contiguous(), bias_up.repeat(r // 2), "fp16s"), 0, r // 2)]
+            else:
+                parts = [(packing.pack_conv(w3, bias_up.repeat(r), "fp16s"), -1, 0)]
+            up_raw = [(ops.ConvGemm(*pk, tap_t0=[t0], act="none", tag="melgan_up"), p0) for pk, t0, p0 in parts]
+            up_act = [(ops.ConvGemm(*pk, tap_t0=[t0], act="lrelu", tag="melgan_up"), p0) for pk, t0, p0 in parts]
             blocks = []
             for j in range(gen.n_residual_layers):
                 p = f"model.{idx + 2 + j}"
@@ -250,7 +261,9 @@ class Generator(layers.PlanOwner, nn.Module):
             d0 = blocks[0][0]
             if self.fuse_resblocks and ops.Resblock2.eligible(C, Lr):
                 xs = ops.alloc_act(B, Lr + 2 * d0, C, P, dev)
-                up_raw(cur, B, L, out=xs, out_row0=d0, reflect=d0, phases=r, halo_after=True)   # ConvTranspose1d: raw stream + halo
+                for up, p0 in up_raw:                                                   # ConvTranspose1d: raw stream
+                    up(cur, B, L, out=xs, out_row0=d0, phases=r, phase0=p0, phase_count=r // len(up_raw))
+                ops.reflect_halo(xs, d0, Lr, d0)                                        # + the first block's halo rows
                 if taps is not None:
                     taps[f"up{si}"] = packing.act_to_float(xs[:, d0:d0 + Lr], P)
                 for j, (d, _, _, fused) in enumerate(blocks):
@@ -272,8 +285,10 @@ class Generator(layers.PlanOwner, nn.Module):
             else:
                 x_raw = ops.alloc_act(B, Lr, C, P, dev)
                 xa = ops.alloc_act(B, Lr + 2 * d0, C, "f16", dev)
-                up_act(cur, B, L, out=xa, out_row0=d0, reflect=d0, out_raw=x_raw, phases=r, out_fmt="f16", raw_fmt=P,
-                       halo_after=True)
+                for up, p0 in up_act:
+                    up(cur, B, L, out=xa, out_row0=d0, out_raw=x_raw, phases=r, out_fmt="f16", raw_fmt=P, phase0=p0,
+                       phase_count=r // len(up_act))
+                ops.reflect_halo(xa, d0, Lr, d0)
                 if taps is not None:
                     taps[f"up{si}"] = packing.act_to_float(x_raw, P)
                 for j, (d, c3, k1, _) in enumerate(blocks):

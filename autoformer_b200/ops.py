@@ -146,7 +146,8 @@ class ConvGemm:
         return self
 
     def __call__(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                 out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None, halo_after=False):
+                 out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None, halo_after=False, phase0=0,
+                 phase_count=None):
         """srcs: channels-last activation tensors [B][rows][C_s], one per logical source.
         out: act(v) [B][rows_out][Cs'] (operand format) at rows out_row0 + time (+ `reflect` mirrored halo rows);
         out_raw: v before the activation [B][phases*T][Cs'] (operand format); out2: act(v) as exact fp32
@@ -154,7 +155,9 @@ class ConvGemm:
         out_fmt / raw_fmt: operand format (a precision name) of out / out_raw when it differs from this layer's own
         input precision -- e.g. a "fp16s" layer writing LeakyReLU(y) as "f16" and y as "fp16s".
         halo_after: write the `reflect` halo rows with a separate avc_reflect_halo launch instead of in the GEMM's
-        epilogue, which keeps the GEMM on its branch-free store path."""
+        epilogue, which keeps the GEMM on its branch-free store path.
+        phase0 / phase_count: this layer produces only phases [phase0, phase0 + phase_count) of the `phases` (its N is
+        phase_count * Cs); the halo launch, if any, is then the caller's business."""
         lib = _lib.load()
         meta = self.meta
         if not isinstance(srcs, (list, tuple)):
@@ -193,7 +196,10 @@ class ConvGemm:
         d.bias = self.bias.data_ptr()
         d.act = self.act
         d.out_phases = phases
-        cs = meta["N"] // phases
+        if phase_count is None:
+            phase_count = phases
+        d.out_phase0, d.out_phase_count = phase0, phase_count
+        cs = meta["N"] // phase_count
         out_fmt = out_fmt or self.precision
         raw_fmt = raw_fmt or out_fmt
         if out is not None:
@@ -233,7 +239,7 @@ class ConvGemm:
             d.debug_clk = dbg.data_ptr()
         with PROFILER.span(self.tag, flops=2.0 * self.macs_per_row * B * T):
             _lib.check(lib.avc_conv_gemm(ctypes.byref(d), _stream()), "avc_conv_gemm")
-        if halo_after and reflect and out is not None:
+        if halo_after and reflect and out is not None and phase_count == phases:
             reflect_halo(out, out_row0, T * phases, reflect)
         return out if out is not None else (out2 if out2 is not None else out_raw)
 

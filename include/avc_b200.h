@@ -115,6 +115,11 @@ typedef struct avc_gemm_desc {
   int out_raw_dtype;         /* format of out_raw (codes of out_dtype); 0 = same as out_dtype.  The MelGAN "fp16s" layers
                                 write LeakyReLU(y) as ONE fp16 value (out, the next k3 convolution's operand) and y itself
                                 as two fp16 terms (out_raw, the residual stream, melgan/modules.py:84-85) */
+  int out_phase0;            /* this launch produces phases [out_phase0, out_phase0 + out_phase_count) of the out_phases */
+  int out_phase_count;       /* poly-phase outputs, N = out_phase_count * Cs (0 = all of them).  A ConvTranspose1d(K = 2r,
+                                stride r) needs only two of the three input taps per output phase -- (t-1, t) for phases
+                                < r/2, (t, t+1) for the rest -- so it runs as two GEMMs of two taps each instead of one
+                                of three with a third of the weights zero (melgan/modules.py:101-112) */
 } avc_gemm_desc;
 
 int avc_conv_gemm(const avc_gemm_desc* d, void* stream);

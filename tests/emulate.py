@@ -60,7 +60,8 @@ _ACT = {0: lambda v: v, 1: torch.relu, 2: torch.tanh, 3: lambda v: F.leaky_relu(
 
 
 def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, reflect=0, out2=None, residual=None,
-                       out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None, halo_after=False):
+                       out_raw=None, phases=1, res_after=False, out_fmt=None, raw_fmt=None, halo_after=False, phase0=0,
+                       phase_count=None):
     meta = self.meta
     prec = self.precision
     out_fmt = out_fmt or prec
@@ -79,6 +80,19 @@ def _emu_convgemm_call(self, srcs, B, T, out=None, out_row0=0, round_tf32=True, 
         assert a.shape[2] == c and a.dtype == packing.TORCH_DTYPE[prec]
     v = emulate_conv_gemm(self.w, self.bias, meta, srcs, B, T, self.tap_t0, self.tap_dt)
     n = meta["N"]
+    if phase_count is not None and phase_count != phases:
+        # a launch that produces only some of the phases: scatter its rows into the interleaved output
+        assert residual is None and out2 is None and not reflect
+        cs = n // phase_count
+        v = v.reshape(B, T, phase_count, cs)
+        a = _ACT[self.act](v)
+        rows = (torch.arange(T)[:, None] * phases + phase0 + torch.arange(phase_count)[None, :]).reshape(-1)
+        if out_raw is not None:
+            out_raw.view(B, T * phases, -1)[:, rows, :packing.act_channels(cs, raw_fmt)] = \
+                packing.to_act(v.reshape(B, -1, cs).float(), raw_fmt)
+        if out is not None:
+            out[:, out_row0 + rows, :packing.act_channels(cs, out_fmt)] = packing.to_act(a.reshape(B, -1, cs).float(), out_fmt)
+        return out if out is not None else out_raw
     cs = n // phases
     tl = T * phases
     v = v.reshape(B, tl, cs)
@@ -381,7 +395,15 @@ def _emu_resblock2_call(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=Fals
     return out2
 
 
+def _emu_reflect_halo(buf, row0, L, reflect):
+    for k in range(1, reflect + 1):
+        buf[:, row0 - k] = buf[:, row0 + k]
+        buf[:, row0 + L - 1 + k] = buf[:, row0 + L - 1 - k]
+    return buf
+
+
 def install_cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops, "reflect_halo", _emu_reflect_halo)
     monkeypatch.setattr(ops.Resblock, "__call__", _emu_resblock_call)
     monkeypatch.setattr(ops.Resblock2, "__call__", _emu_resblock2_call)
     monkeypatch.setattr(ops, "audio_frames", _emu_audio_frames)
