@@ -14,9 +14,11 @@
 //
 // Shared memory (single-buffered: 512 TMEM columns and 220 KB leave no room for a second set):
 //   region A  76 KB  raw window [term][chunk] (128 + 2d rows x 128 B each)
-//   region B  64 KB  xa [chunk] (GEMM1's operand), later the intermediate [term][chunk] (GEMM2's operand), later the
-//                    output staging tiles of the TMA stores
-//   ring      5 x 16 KB  weight tiles (this CTA's half)
+//   region B  70 KB  [0, 38 KB) xa [chunk] (GEMM1's operand); [0, 64 KB) later the intermediate [term][chunk] (GEMM2's
+//                    operand); [38 KB, 70 KB) the staging tiles of the TMA stores.  The output goes out in two passes, the hi
+//                    terms then the lo terms of all 128 channels (32 KB each), so that staging and the NEXT tile's xa
+//                    never overlap: xa is formed the moment the next window lands, while this tile is still being stored
+//   ring      4 x 16 KB  weight tiles (this CTA's half)
 // Per tile:  window load -> xa -> GEMM1 (3 taps x 2 chunks) -> epilogue 1 -> GEMM2 (k1 + shortcut, three products each)
 // -> epilogue 2 -> TMA stores; the next window is requested as soon as GEMM2 has read the centre rows, and was
 // prefetched into L2 while this tile computed.
@@ -37,10 +39,11 @@ constexpr int kMaxDilation = 12;
 constexpr int kWinRowsMax = kBlockM + 2 * kMaxDilation;          // 152
 constexpr int kWinTile = kWinRowsMax * kRowBytes;                // 19 KB
 constexpr int kBStage = 128 * kRowBytes;                         // this CTA's half of a weight tile: 16 KB
-constexpr int kStages = 5;
+constexpr int kStages = 4;
 constexpr int kOffWin = 0;
 constexpr int kOffB = kOffWin + 2 * KC * kWinTile;               // region B
-constexpr int kRegionB = 2 * KC * kATileBytes;                   // 64 KB
+constexpr int kOffStage = KC * kWinTile;                         // staging tiles inside region B, behind the xa tiles
+constexpr int kRegionB = kOffStage + KC * kATileBytes;           // 70 KB (the intermediate takes the first 64 KB)
 constexpr int kOffRing = kOffB + kRegionB;
 constexpr int kOffBias = kOffRing + kStages * kBStage;
 constexpr int kOffBar = kOffBias + 2 * C * 4;
@@ -49,7 +52,7 @@ constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024 /* alignment slack
 constexpr int kXaWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * kXaWarps;    // 576
 constexpr int kStagesPerTile = 3 * KC + 2 * KC;                  // 10 weight tiles per 128-sample tile
-static_assert(KC * kWinTile <= kRegionB, "xa tiles must fit region B");
+static_assert(2 * KC * kATileBytes <= kRegionB, "the intermediate must fit region B");
 static_assert(kWinTile % 1024 == 0 && kOffB % 1024 == 0 && kOffRing % 1024 == 0, "tiles must stay 1024-byte aligned");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 
@@ -127,8 +130,8 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
   uint64_t* d1_full = bars + 2 * kStages + 2;     // GEMM1 done (both CTAs)
   uint64_t* mid_ready = bars + 2 * kStages + 3;   // leader: intermediate written by the epilogue warps of BOTH CTAs
   uint64_t* d2_full = bars + 2 * kStages + 4;     // GEMM2 done (both CTAs): window and intermediate are free
-  uint64_t* stage_free = bars + 2 * kStages + 5;  // this CTA's TMA stores have read the staging tiles: region B is free
   uint64_t* d2_free = bars + 2 * kStages + 6;     // leader: the epilogue warps of BOTH CTAs have read accumulator 2
+  uint64_t* win_free = bars + 2 * kStages + 5;    // the shortcut MMAs have read the window (both CTAs): it may be reloaded
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + kNumBars);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,8 +151,8 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
     mbar_init(d1_full, 1);
     mbar_init(mid_ready, 2 * kEpiWarps);
     mbar_init(d2_full, 1);
-    mbar_init(stage_free, 1);
     mbar_init(d2_free, 2 * kEpiWarps);
+    mbar_init(win_free, 1);
     fence_mbar_init();
     prefetch_tmap(&p.tmap_x);
     prefetch_tmap(&p.tmap_w);
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
         int b, t0;
         bool real;
         tile_coords(u, b, t0, real);
-        if (it > 0) mbar_wait(d2_full, (it - 1) & 1);          // GEMM2 of the previous tile has read the window
+        if (it > 0) mbar_wait(win_free, (it - 1) & 1);         // the previous tile's shortcut MMAs have read the window
         stamp(it, 0);                                          // window requested
         mbar_arrive_expect_tx(win_full, 2 * KC * win_rows * kRowBytes);
 #pragma unroll
@@ -250,6 +253,7 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
         tc_fence_after();
         for (int m = 0; m < 2; ++m) {
           if (m == 1) {
+            umma_commit_2sm(win_free, 0x3);                    // GEMM1 (xa) and the shortcut (window) are the window's last readers
             mbar_spin_cluster(mid_ready, it & 1);
             stamp(it, 4);                                      // intermediate of both CTAs ready
             tc_fence_after();
@@ -281,10 +285,11 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
     const int tid = threadIdx.x - (64 + 32 * kEpiWarps);
     int it = 0;
     for (int u = pair0; u < p.n_pairs; u += pair_stride, ++it) {
+      // (the window is requested as soon as the previous tile's shortcut MMAs have read the old one, i.e. while its k1
+      // MMAs still run; the previous tile's staging tiles lie behind the xa tiles)
       mbar_wait(win_full, it & 1);
       if (tid == 0) stamp(it, 6);                               // window landed
-      if (it > 0) mbar_wait(stage_free, (it - 1) & 1);          // region B: the previous tile's stores have been read
-      if (tid == 0) stamp(it, 7);                               // region B free
+      if (it > 0) mbar_wait(d2_full, (it - 1) & 1);             // ... and the intermediate under the xa tiles is dead
       // a warp takes 4 rows x 8 chunks per step; the (at most 5) steps of a chunk are unrolled so their shared-memory
       // loads and conversions overlap
       const int c = lane & 7, r0 = (warp - (2 + kEpiWarps)) * 4 + (lane >> 3);
@@ -348,53 +353,68 @@ __global__ void __launch_bounds__(big::kThreads, 1) resblock2_big_kernel(const _
       __syncwarp();
       if (storer) stamp(it, 10);                                // intermediate written
       if (lane == 0) mbar_arrive_leader(mid_ready);
-      // ---- epilogue 2: y = k1(mid) + shortcut(x) + bias -> staging tiles (over the intermediate) -> TMA stores
+      // ---- epilogue 2: y = k1(mid) + shortcut(x) + bias, stored in two passes (hi terms, then lo terms) through the
+      // 32 KB staging tiles; the accumulator is simply read twice
       mbar_wait(d2_full, it & 1);
       if (storer) stamp(it, 11);                                // accumulator 2 ready
       tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = h * 64 + sub * 32;
-        load_sum32(d2 + lane_off + h * 128 + sub * 32, v);
+      for (int term = 0; term < 2; ++term) {
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c0 = h * 64 + sub * 32;
+          load_sum32(d2 + lane_off + h * 128 + sub * 32, v);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] += s_bias[C + c0 + e];
-        if (p.y_act) {
+          for (int e = 0; e < 32; ++e) v[e] += s_bias[C + c0 + e];
+          if (p.y_act) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = lrelu(v[e]);
-        }
-        write_split32(s_b, row, c0, v, hi, lo);
-        if (p.y_reflect > 0 && real) {   // ReflectionPad1d rows of the consumer: time -k = time k, time L-1+k = time L-1-k
-          const int t = t0 + row;
-          int dst[2] = {-1, -1};
-          if (t >= 1 && t <= p.y_reflect) dst[0] = p.y_row0 - t;
-          if (t <= p.L - 2 && t >= p.L - 1 - p.y_reflect) dst[1] = p.y_row0 + 2 * (p.L - 1) - t;
+            for (int e = 0; e < 32; ++e) v[e] = lrelu(v[e]);
+          }
+          uint4 part[4];
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            if (dst[s] < 0) continue;
-            __half* o = p.y + ((long long)b * p.y_rows_per_utt + dst[s]) * p.y_ld + c0;
+          for (int j = 0; j < 4; ++j) {
+            uint4 hq, lq;
+            split_f16_pair_trunc(v[j * 8], v[j * 8 + 1], hq.x, lq.x);
+            split_f16_pair_trunc(v[j * 8 + 2], v[j * 8 + 3], hq.y, lq.y);
+            split_f16_pair_trunc(v[j * 8 + 4], v[j * 8 + 5], hq.z, lq.z);
+            split_f16_pair_trunc(v[j * 8 + 6], v[j * 8 + 7], hq.w, lq.w);
+            part[j] = term == 0 ? hq : lq;
+            const int chunk = ((c0 & 63) >> 3) + j;
+            *reinterpret_cast<uint4*>(s_b + kOffStage + (c0 >> 6) * kATileBytes + row * kRowBytes +
+                                      ((chunk ^ (row & 7)) << 4)) = part[j];
+          }
+          if (p.y_reflect > 0 && real) {   // ReflectionPad1d rows of the consumer: time -k = time k, time L-1+k = time L-1-k
+            const int t = t0 + row;
+            int dst[2] = {-1, -1};
+            if (t >= 1 && t <= p.y_reflect) dst[0] = p.y_row0 - t;
+            if (t <= p.L - 2 && t >= p.L - 1 - p.y_reflect) dst[1] = p.y_row0 + 2 * (p.L - 1) - t;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(o + j * 8) = hi[j];
-              *reinterpret_cast<uint4*>(o + C + j * 8) = lo[j];
+            for (int s = 0; s < 2; ++s) {
+              if (dst[s] < 0) continue;
+              __half* o = p.y + ((long long)b * p.y_rows_per_utt + dst[s]) * p.y_ld + term * C + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(o + j * 8) = part[j];
             }
           }
         }
-      }
-      tc_fence_before();     // this warp's reads of accumulator 2 are complete: the next tile's shortcut may overwrite it
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(d2_free);
-      fence_proxy_async();   // staging tiles -> TMA store (async proxy)
-      epilogue_bar();
-      if (storer) stamp(it, 12);                                // staging tiles written by all epilogue warps
-      if (storer) {
-        if (real) {
-#pragma unroll
-          for (int i = 0; i < 2 * KC; ++i) tma_store_3d(&p.tmap_y, s_b + i * kATileBytes, i * 64, p.y_row0 + t0, b);
-          bulk_commit();
-          bulk_wait_read();
+        if (term == 1) {       // this warp's reads of accumulator 2 are complete: the next tile's shortcut may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(d2_free);
         }
-        stamp(it, 13);                                          // stores have read the staging tiles
-        mbar_arrive(stage_free);
+        fence_proxy_async();   // staging tiles -> TMA store (async proxy)
+        epilogue_bar();
+        if (storer) {
+          stamp(it, 12 + term);                                 // staging tiles of this pass written by all epilogue warps
+          if (real) {
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc)
+              tma_store_3d(&p.tmap_y, s_b + kOffStage + kc * kATileBytes, term * C + kc * 64, p.y_row0 + t0, b);
+            bulk_commit();
+            bulk_wait_read();
+          }
+        }
+        epilogue_bar();        // the staging tiles are free again (for the next pass / the next tile's intermediate)
       }
     }
     if (storer) bulk_wait_all();

@@ -27,8 +27,8 @@ blk.debug_clk = clk
 blk(x, B, L, y=y, y_row0=9, y_reflect=9)
 torch.cuda.synchronize()
 c = clk.view(64, 16).cpu()
-names = ["win_req", "w_req_done", "xa_ready", "gemm1_issued", "mid_ready", "gemm2_issued", "win_landed", "regionB_free",
-         "xa_written", "d1_full", "mid_written", "d2_full", "staged", "store_read"]
+names = ["win_req", "w_req_done", "xa_ready", "gemm1_issued", "mid_ready", "gemm2_issued", "win_landed", "-",
+         "xa_written", "d1_full", "mid_written", "d2_full", "staged_hi", "staged_lo"]
 base = int(c[2, 0])
 for it in (2, 3, 4, 20):
     row = c[it]
