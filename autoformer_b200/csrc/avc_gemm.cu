@@ -321,6 +321,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         // per-unit stamps of CTA 0 (profiling aid): 8 slots per unit after the 4-per-CTA block
         long long* ud = (p.debug_clk && blockIdx.x == 0 && itp < 256) ? p.debug_clk + 4LL * gridDim.x + 8 * itp : nullptr;
         if (ud) ud[0] = clock64();                                         // producer starts the unit
+        // (Tried and measured slower, r02: L2-prefetching the next unit's activation rows from here with
+        // cp.async.bulk.prefetch.tensor -- the up-sampling GEMMs of the long MelGAN stages went from 0.82 to 0.96 ms.
+        // Their producer already spends ~700 cycles per k-block ISSUING the two TMA operations of a stage, against 128
+        // cycles of MMAs (scripts/up_unit_timing.py): more TMA operations make it worse, not fewer misses better.)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           while (kb >= p.kb_end[src]) {
             base = p.kb_end[src];
