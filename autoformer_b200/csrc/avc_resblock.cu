@@ -366,11 +366,11 @@ static int launch(const RbParams& p, cudaStream_t stream) {
 //   mid   = LeakyReLU(D1 + b3) as two fp16 terms in shared memory
 //   GEMM2: D2 = [mid_hi, mid_lo] . W1 + [x_hi, x_lo](centre rows) . Wsc   (three products each)
 //
-// The output is staged in the window buffer the tile has just finished with (GEMM2's shortcut is its last reader) and
-// stored by the PRODUCER thread, which reloads that buffer for tile i+2 only after the store has read it: no epilogue
-// warp ever waits for a TMA store, and the intermediate tiles are free for the next tile the moment GEMM2 is done
-// (with the staging aliased to the intermediate, as in version 1, the next epilogue 1 waited for the store).
-// Warp roles: 0 = TMA producer + TMA stores, 1 = MMA issuer, 2..9 = epilogue (two per TMEM lane quarter), 10..13 = xa warps.
+// (Tried and measured slower, r02: staging the output in the window buffer the tile has just finished with and letting
+// the producer thread issue the TMA stores, so that no epilogue warp waits for a store -- the reload of that buffer for
+// tile i+2 then starts a store later, the window's HBM latency is no longer covered by one tile period, and a block takes
+// 0.73 ms (C = 64) / 0.68 ms (C = 32) instead of 0.60 ms.)
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..9 = epilogue (two per TMEM lane quarter), 10..13 = xa warps.
 // Schedule per CTA: the xa warps form xa(i+1) as soon as GEMM1(i) has read the xa tile, the epilogue warps run
 // ep1(i) -> ep2(i), the MMA thread GEMM1(i) -> GEMM2(i): GEMM2(i) and ep1/ep2(i) overlap the xa pass of the next tile,
 // GEMM1(i+1) overlaps ep2(i); the window of tile i+2 is loaded as soon as GEMM2(i) has read the centre rows of its buffer.
@@ -423,7 +423,7 @@ struct alignas(64) Rb2Params {
 // NCH channels starting at c0 of row `row` as two fp16 terms into operand tile(s) at `tiles`, 128-byte swizzle.
 template <int C, int NCH>
 __device__ __forceinline__ void write_split_f16(uint8_t* tiles, int row, int c0, const float (&v)[NCH], uint4 (&hi)[NCH / 8],
-                                                uint4 (&lo)[NCH / 8], int lo_tile = kATileBytes) {
+                                                uint4 (&lo)[NCH / 8]) {
 #pragma unroll
   for (int j = 0; j < NCH / 8; ++j) {
     split_f16_pair_trunc(v[j * 8], v[j * 8 + 1], hi[j].x, lo[j].x);
@@ -434,7 +434,7 @@ __device__ __forceinline__ void write_split_f16(uint8_t* tiles, int row, int c0,
     uint8_t* r = tiles + row * kRowBytes;
     if (C == 64) {
       *reinterpret_cast<uint4*>(r + ((chunk ^ (row & 7)) << 4)) = hi[j];
-      *reinterpret_cast<uint4*>(r + lo_tile + ((chunk ^ (row & 7)) << 4)) = lo[j];
+      *reinterpret_cast<uint4*>(r + kATileBytes + ((chunk ^ (row & 7)) << 4)) = lo[j];
     } else {
       *reinterpret_cast<uint4*>(r + ((chunk ^ (row & 7)) << 4)) = hi[j];
       *reinterpret_cast<uint4*>(r + (((chunk + 4) ^ (row & 7)) << 4)) = lo[j];
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
   float* s_bias = reinterpret_cast<float*>(base + Cfg::kOffBias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + Cfg::kOffBar);
   uint64_t* win_full = bars + 0;     // [2] TMA bytes of a window buffer have landed
-  uint64_t* staged = bars + 2;       // [2] the output of the tile that used a window buffer is staged in it (all epilogue warps)
+  uint64_t* win_free = bars + 2;     // [2] GEMM2 has read the centre rows of a window buffer (and xa was formed from it)
   uint64_t* xa_ready = bars + 4;     // xa tile written by all epilogue warps
   uint64_t* d1_full = bars + 5;      // GEMM1 done: accumulator 1 ready, xa tile free
   uint64_t* mid_ready = bars + 6;    // intermediate written (and accumulator 1 drained) by all epilogue warps
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&win_full[i], 1);
-      mbar_init(&staged[i], kEpi);
+      mbar_init(&win_free[i], 1);
     }
     mbar_init(xa_ready, kXaWarps);
     mbar_init(d1_full, 1);
@@ -564,34 +564,16 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
 
   if (warp == 0) {
     if (lane == 0) {
-      // iteration j: store the output of tile j-2 out of window buffer j & 1 (staged there by the epilogue warps), wait
-      // until the TMA engine has read it, then load the window of tile j into the same buffer
-      const int my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-      for (int j = 0; j < my_tiles + 2; ++j) {
-        const int buf = j & 1;
-        if (j >= 2) {
-          const int tile = blockIdx.x + (j - 2) * gridDim.x;
-          const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
-          mbar_wait(&staged[buf], ((j - 2) >> 1) & 1);
-          uint8_t* stg = s_win + buf * P * Cfg::kWinTile;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
+        const int buf = it & 1, use = it >> 1;
+        if (use > 0) mbar_wait(&win_free[buf], (use - 1) & 1);
+        mbar_arrive_expect_tx(&win_full[buf], P * win_rows * kRowBytes);
 #pragma unroll
-          for (int part = 0; part < P; ++part) {
-            if (p.has_y) tma_store_3d(&p.tmap_y[part], stg + part * Cfg::kWinTile, 0, p.y_row0 + t0, b);
-            else tma_store_2d(&p.tmap_out2[part], stg + part * Cfg::kWinTile, 0, b * p.L + t0);
-          }
-          bulk_commit();
-          bulk_wait_read();
-        }
-        if (j < my_tiles) {
-          const int tile = blockIdx.x + j * gridDim.x;
-          const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
-          mbar_arrive_expect_tx(&win_full[buf], P * win_rows * kRowBytes);
-#pragma unroll
-          for (int part = 0; part < P; ++part)
-            tma_load_3d(s_win + (buf * P + part) * Cfg::kWinTile, &p.tmap_win[part], &win_full[buf], 0, t0, b);
-        }
+        for (int part = 0; part < P; ++part)
+          tma_load_3d(s_win + (buf * P + part) * Cfg::kWinTile, &p.tmap_win[part], &win_full[buf], 0, t0, b);
       }
-      bulk_wait_all();
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -611,6 +593,7 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
         issue_src_f16<C>(mid, mid + kATileBytes, w + Cfg::kOffW1, d2, true);
         issue_src_f16<C>(xc, xc + Cfg::kWinTile, w + Cfg::kOffWsc, d2, false);
         umma_commit(d2_full);
+        umma_commit(&win_free[buf]);
       }
     }
     __syncwarp();
@@ -633,6 +616,7 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
     const int row = q * 32 + lane;
     const int c0 = h * NCH;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const bool storer = threadIdx.x == 64;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_utt, t0 = (tile % p.tiles_per_utt) * kBlockM;
@@ -652,7 +636,11 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
       }
 #pragma unroll
       for (int e = 0; e < NCH; ++e) v[e] = lrelu(v[e] + s_bias[c0 + e]);
-      write_split_f16<C, NCH>(s_mid, row, c0, v, hi, lo);      // (free since GEMM2 of the previous tile: d2_full was waited for)
+      if (it > 0) {          // the previous tile's TMA stores must have read the staging tiles (= the intermediate tiles)
+        if (storer) bulk_wait_read();
+        epilogue_bar_n<32 * kEpi>();
+      }
+      write_split_f16<C, NCH>(s_mid, row, c0, v, hi, lo);
       fence_proxy_async();   // generic-proxy writes -> tensor-core (async proxy) reads
       tc_fence_before();     // ... and this warp's reads of accumulator 1 before the next GEMM1
       __syncwarp();
@@ -667,9 +655,8 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
 #pragma unroll
         for (int e = 0; e < NCH; ++e) v[e] = lrelu(v[e]);
       }
-      uint8_t* stg = s_win + (it & 1) * P * Cfg::kWinTile;       // this tile's window buffer: GEMM2 was its last reader
       if (p.has_y) {
-        write_split_f16<C, NCH>(stg, row, c0, v, hi, lo, Cfg::kWinTile);
+        write_split_f16<C, NCH>(s_mid, row, c0, v, hi, lo);      // GEMM2 has consumed the intermediate
         if (p.y_reflect > 0) {         // ReflectionPad1d rows of the consumer: time -k = time k, time L-1+k = time L-1-k
           const int t = t0 + row;
           int dst[2] = {-1, -1};
@@ -690,16 +677,24 @@ __global__ void __launch_bounds__(Rb2Cfg<C>::kThreads, Rb2Cfg<C>::kCtasPerSm) re
 #pragma unroll
         for (int j = 0; j < NCH / 4; ++j) {
           const int f = c0 + j * 4;
-          uint8_t* r = stg + (f >> 5) * Cfg::kWinTile + row * kRowBytes;
+          uint8_t* r = s_mid + (f >> 5) * kATileBytes + row * kRowBytes;
           *reinterpret_cast<float4*>(r + ((((f & 31) >> 2) ^ (row & 7)) << 4)) =
               make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         }
       }
-      fence_proxy_async();   // staging tiles -> TMA store (async proxy), issued by the producer thread
+      fence_proxy_async();   // staging tiles -> TMA store (async proxy)
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&staged[it & 1]);
+      epilogue_bar_n<32 * kEpi>();
+      if (storer) {
+#pragma unroll
+        for (int part = 0; part < P; ++part) {
+          if (p.has_y) tma_store_3d(&p.tmap_y[part], s_mid + part * kATileBytes, 0, p.y_row0 + t0, b);
+          else tma_store_2d(&p.tmap_out2[part], s_mid + part * kATileBytes, 0, b * p.L + t0);
+        }
+        bulk_commit();
+      }
     }
+    if (storer) bulk_wait_all();
   }
   __syncwarp();
   tc_fence_before();
