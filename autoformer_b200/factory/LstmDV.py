@@ -14,6 +14,10 @@ from .. import layers, ops
 class LstmDV(layers.PlanOwner, nn.Module):
     def __init__(self, num_layers=3, dim_input=80, dim_cell=768, dim_emb=256):
         super().__init__()
+        # the kernels cover a subset of what nn.LSTM / nn.Linear accept: say so here, not as an error code in the C ABI
+        if dim_cell % 64 != 0 or dim_input % 8 != 0 or not 1 <= dim_emb <= 1024:
+            raise ValueError(f"autoformer_b200.LstmDV supports dim_cell % 64 == 0, dim_input % 8 == 0, dim_emb <= 1024; "
+                             f"got dim_cell={dim_cell}, dim_input={dim_input}, dim_emb={dim_emb}")
         self.lstm = nn.LSTM(input_size=dim_input, hidden_size=dim_cell, num_layers=num_layers, batch_first=True)
         self.embedding = nn.Linear(dim_cell, dim_emb)
         self.num_layers, self.dim_cell = num_layers, dim_cell

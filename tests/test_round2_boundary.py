@@ -179,6 +179,10 @@ def test_hyper_parameter_validation():
     for bad in [(65, 256, 512, 32), (32, 256, 500, 32), (32, 250, 512, 32), (33, 256, 512, 32)]:
         with pytest.raises(ValueError):
             AutoVC(*bad)
+    from autoformer_b200.factory.LstmDV import LstmDV
+    LstmDV()
+    with pytest.raises(ValueError):
+        LstmDV(dim_cell=700)
 
 
 # ----------------------------------------------------------------------------------------------- GPU parity
