@@ -108,6 +108,28 @@ class LstmWsDesc(ctypes.Structure):
     ]
 
 
+STACK_MAX_LAYERS = 4
+
+
+class LstmStackDesc(ctypes.Structure):
+    """struct avc_lstm_stack_desc"""
+    _fields_ = [
+        ("xproj0", ctypes.c_void_p),
+        ("w_hh0", ctypes.c_void_p),
+        ("w_ih", ctypes.c_void_p * STACK_MAX_LAYERS),
+        ("w_hh", ctypes.c_void_p * STACK_MAX_LAYERS),
+        ("bias", ctypes.c_void_p * STACK_MAX_LAYERS),
+        ("hs", ctypes.c_void_p),
+        ("h_last", ctypes.c_void_p),
+        ("grid_barrier", ctypes.c_void_p),
+        ("B", ctypes.c_int),
+        ("T", ctypes.c_int),
+        ("H", ctypes.c_int),
+        ("L", ctypes.c_int),
+        ("debug_clk", ctypes.c_void_p),
+    ]
+
+
 class ResblockDesc(ctypes.Structure):
     """struct avc_resblock_desc"""
     _fields_ = [
@@ -180,6 +202,8 @@ def load():
     lib.avc_lstm_seq.restype = ctypes.c_int
     lib.avc_lstm_seq_ws.argtypes = [ctypes.POINTER(LstmWsDesc), ctypes.c_void_p]
     lib.avc_lstm_seq_ws.restype = ctypes.c_int
+    lib.avc_lstm_stack_ws.argtypes = [ctypes.POINTER(LstmStackDesc), ctypes.c_void_p]
+    lib.avc_lstm_stack_ws.restype = ctypes.c_int
     lib.avc_resblock.argtypes = [ctypes.POINTER(ResblockDesc), ctypes.c_void_p]
     lib.avc_resblock.restype = ctypes.c_int
     lib.avc_reflect_halo.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_int,

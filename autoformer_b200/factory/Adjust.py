@@ -19,7 +19,7 @@ class AdjustPlan:
         p = prefix + "." if prefix else ""
         self.precision = precision
         self.convs = [layers.conv_bn_layer(sd, f"{p}convolutions.{i}", precision, "relu") for i in range(3)]
-        self.lstm = layers.lstm_layers(sd, f"{p}lstm", 3, precision)
+        self.lstm = layers.LstmStack(layers.lstm_layers(sd, f"{p}lstm", 3, precision), precision)
         self.w = sd[f"{p}embedding.linear_layer.weight"].float().contiguous()
         self.b = sd[f"{p}embedding.linear_layer.bias"].float().contiguous()
         self.dim_cell = self.w.shape[1]
@@ -34,8 +34,7 @@ class AdjustPlan:
             conv(h, B, T, out=o)
             h = o
         h_last = torch.empty(B, self.dim_cell, dtype=torch.float32, device=x.device)
-        for i, layer in enumerate(self.lstm):                           # :38-39 (only the last step is used)
-            h = layer(h, B, T, h_last=h_last if i == len(self.lstm) - 1 else None, persistent=persistent)
+        self.lstm.last_hidden(h, B, T, h_last, persistent=persistent)   # :38-39 (only the last step is used)
         return ops.linear_l2norm(h_last, self.w, self.b)               # :40-42
 
 

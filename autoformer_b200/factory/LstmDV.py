@@ -4,6 +4,8 @@ Same constructor defaults, ``forward(x)`` contract and state_dict keys as the re
 (factory/LstmDV.py:4-24): 3 x LSTM(80 -> 768), last time step, Linear(768 -> 256), L2 normalisation.
 Each LSTM layer is one dense input-projection GEMM plus the tensor-core recurrence; only h_T of the top
 layer leaves the recurrence kernel (``h_last``), and the Linear + normalisation is one fused kernel.
+Small batches in "fp16x2" run the three layers as one wavefront launch (``layers.LstmStack``, ``avc_lstm_stack_ws``);
+``model.wavefront = False`` keeps them layer by layer (two-term weights everywhere, half the rounding error, ~3x the time).
 """
 import torch
 import torch.nn as nn
@@ -23,15 +25,17 @@ class LstmDV(layers.PlanOwner, nn.Module):
         self.num_layers, self.dim_cell = num_layers, dim_cell
         self.precision = "fp32"
         self.persistent_lstm = True
+        self.wavefront = None           # None: the library default (on; AVC_LSTM_STACK=0 turns it off)
         self._cache = layers.PlanCache()
 
     def _build_plan(self):
         sd = layers.state_for_packing(self)
-        return dict(lstm=layers.lstm_layers(sd, "lstm", self.num_layers, self.precision),
+        return dict(lstm=layers.LstmStack(layers.lstm_layers(sd, "lstm", self.num_layers, self.precision), self.precision,
+                                          self.wavefront),
                     w=sd["embedding.weight"].float().contiguous(), b=sd["embedding.bias"].float().contiguous())
 
     def _plan(self):
-        return self._cache.get(self, (self.precision,), self._build_plan)
+        return self._cache.get(self, (self.precision, self.wavefront), self._build_plan)
 
     def _last_hidden(self, plan, x):
         """h_T of the top LSTM layer, fp32 (B, dim_cell)   (LstmDV.py:20-21: ``lstm_out[:, -1, :]``)."""
@@ -40,10 +44,7 @@ class LstmDV(layers.PlanOwner, nn.Module):
         B, T, _ = x.shape
         h = ops.to_act(x, self.precision)
         h_last = torch.empty(B, self.dim_cell, dtype=torch.float32, device=x.device)
-        for i, layer in enumerate(plan["lstm"]):
-            last = i == self.num_layers - 1
-            h = layer(h, B, T, h_last=h_last if last else None, persistent=self.persistent_lstm)
-        return h_last
+        return plan["lstm"].last_hidden(h, B, T, h_last, persistent=self.persistent_lstm)
 
     @ops.on_device_of_input
     @torch.no_grad()

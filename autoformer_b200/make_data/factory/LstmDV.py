@@ -29,7 +29,7 @@ class LstmDV(_Embedder):
             plan["w_out"] = sd["output.weight"].float().contiguous()
             plan["b_out"] = sd["output.bias"].float().contiguous()
             return plan
-        return self._cache.get(self, (self.precision,), build)
+        return self._cache.get(self, (self.precision, self.wavefront), build)
 
     @ops.on_device_of_input
     @torch.no_grad()

@@ -424,6 +424,58 @@ def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, deb
     return hseq
 
 
+def stack_supported(B, H, L, precision, n_sm=148):
+    """Shapes the wavefront stack kernel (avc_lstm_stack_ws) takes: fp16 operands ("fp16x2"), 2 <= L <= 4 layers of the
+    same width, B <= 64, H a multiple of 128 whose H/2 tensor-memory columns of weights fit beside the accumulator, and
+    L x 4H/128 x 2 CTAs within one wave."""
+    if precision != "fp16x2" or not 1 <= B <= WS_MAX_BATCH or not 2 <= L <= _lib.STACK_MAX_LAYERS:
+        return False
+    if H % 128 or H // 2 + 64 > 512 or L * (4 * H // 128) * 2 > n_sm:
+        return False
+    ar = 16 if B <= 16 else (32 if B <= 32 else 64)
+    tiles = 3 * ((H // 64 + 2) // 3)                  # whole operand-load groups
+    return tiles * ar * 128 + 2 * ar * 64 * 4 + 4096 + 1152 <= 227 * 1024
+
+
+def lstm_stack_ws(xproj0, w_hh0, upper, B, T, H, h_last=None, hs=None, debug_clk=None):
+    """All layers of a small-batch LSTM stack as one wavefront launch.  xproj0 [B*T][4H] fp32 (layer 0's dense input
+    projection, biases included), w_hh0 [4H][2H] fp16 two-term, `upper` = [(w_ih, w_hh, bias)] of the layers above
+    (packing.pack_lstm_stack_upper); all in the packing.WS_GROUP gate order.  Returns the scratch sequences
+    hs [L][T+1][B][H] fp16 (frame t+1 of layer l = h^l_t), or None when the device cannot hold the grid (nothing was
+    launched)."""
+    lib = _lib.load()
+    _require_cuda(xproj0, w_hh0)
+    dev = w_hh0.device
+    L = 1 + len(upper)
+    assert xproj0.dtype == torch.float32 and xproj0.is_contiguous() and xproj0.numel() == B * T * 4 * H
+    assert w_hh0.dtype == torch.float16 and w_hh0.shape == (4 * H, 2 * H) and w_hh0.is_contiguous()
+    if hs is None:
+        hs = torch.empty(L, T + 1, B, H, dtype=torch.float16, device=dev)
+    assert hs.is_contiguous() and hs.shape == (L, T + 1, B, H) and hs.dtype == torch.float16
+    d = _lib.LstmStackDesc()
+    d.xproj0, d.w_hh0, d.hs = xproj0.data_ptr(), w_hh0.data_ptr(), hs.data_ptr()
+    for l, (w_ih, w_hh, bias) in enumerate(upper, start=1):
+        for w in (w_ih, w_hh):
+            assert w.dtype == torch.float16 and w.shape == (4 * H, H) and w.is_contiguous() and w.device == dev
+        assert bias.dtype == torch.float32 and bias.shape == (4 * H,) and bias.is_contiguous() and bias.device == dev
+        d.w_ih[l], d.w_hh[l], d.bias[l] = w_ih.data_ptr(), w_hh.data_ptr(), bias.data_ptr()
+    if h_last is not None:
+        assert h_last.is_contiguous() and h_last.shape == (B, H) and h_last.dtype == torch.float32
+        d.h_last = h_last.data_ptr()
+    bar = torch.empty(256, dtype=torch.int32, device=dev)             # zeroed by the library
+    d.grid_barrier = bar.data_ptr()
+    d.B, d.T, d.H, d.L = B, T, H, L
+    if debug_clk is not None:
+        d.debug_clk = debug_clk.data_ptr()
+    flops = 2.0 * 4 * H * H * B * T * (2 * L - 1)      # W_hh of every layer + W_ih of the layers above the first
+    with PROFILER.span("lstm_stack", flops=flops, launches=1):
+        rc = lib.avc_lstm_stack_ws(ctypes.byref(d), _stream())
+    if rc == _lib.ERR_NOT_RESIDENT:
+        return None
+    _lib.check(rc, "avc_lstm_stack_ws")
+    return hs
+
+
 def bilstm_small(xproj, w_hh, B, T, H, out=None, codes=None, freq=1, round_tf32=True, split=False):
     """xproj [B*T][8H] fp32; w_hh [2][4H][H] fp32; out [B][T][2H] (fp32/bf16; split: [B][T][4H] bf16) and/or
     codes [B][T/freq][2H] fp32."""

@@ -314,6 +314,16 @@ def pack_lstm_hh(w_hh, precision, group):
     return to_operand(w, precision).contiguous()
 
 
+def pack_lstm_stack_upper(w_ih, w_hh, b_ih, b_hh):
+    """A layer above the first for the wavefront stack kernel (avc_lstm_stack_ws): W_ih and W_hh as ONE fp16 term each,
+    rows in the WS_GROUP gate order, plus the fp32 bias b_ih + b_hh in the same order."""
+    h = w_hh.shape[1]
+    assert w_ih.shape == (4 * h, h), "the layers above the first take the hidden sequence of the layer below"
+    perm = gate_permutation(h, WS_GROUP, w_hh.device)
+    one = lambda w: sat_f16(take_rows(w.float(), perm)).to(torch.float16).contiguous()
+    return one(w_ih), one(w_hh), take_rows(b_ih.float() + b_hh.float(), perm).contiguous()
+
+
 def pack_bilstm_ih(w_ih_f, b_ih_f, b_hh_f, w_ih_r, b_ih_r, b_hh_r, precision):
     """Both directions of a bidirectional layer in one projection: columns dir*4H + gate*H + u."""
     w = torch.cat([w_ih_f, w_ih_r], dim=0)

@@ -143,6 +143,54 @@ def test_lstm_ws_matches_explicit_lstm(B, T, I, H, precision):
     assert rel_l2(f32_b, f32) < (2e-5 if precision == "fp32" else 1e-3)
 
 
+@pytest.mark.parametrize("B,T,I,H,L", [(2, 40, 80, 768, 3), (17, 33, 80, 512, 2), (64, 64, 80, 768, 3), (33, 21, 512, 256, 4),
+                                       (1, 1, 80, 768, 3), (64, 300, 512, 768, 3)])
+def test_lstm_stack_wavefront_matches_explicit_lstm(B, T, I, H, L):
+    """All layers of a small-batch stack as one wavefront launch (avc_lstm_stack_ws): every activation-row variant (16 /
+    32 / 64), 2-4 layers, ragged batches, T = 1 (ramp-up and ramp-down ticks only); h_last against the fp64 explicit LSTM
+    and against the layer-by-layer kernels; every frame of every layer's scratch sequence against the explicit LSTM."""
+    from autoformer_b200 import layers, ops, packing
+    assert ops.stack_supported(B, H, L, "fp16x2")
+    torch.manual_seed(H + T + B)
+    k = 1.0 / H ** 0.5
+    ws, refs = [], []
+    x = torch.randn(B, T, I)
+    ref = x.double()
+    for l in range(L):
+        w_ih = (torch.rand(4 * H, I if l == 0 else H) * 2 - 1) * k * 2
+        w_hh, b_ih, b_hh = (torch.rand(4 * H, H) * 2 - 1) * k * 2, (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
+        ws.append(tuple(w.cuda() for w in (w_ih, w_hh, b_ih, b_hh)))
+        ref = lstm_explicit(ref, w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
+        refs.append(ref)
+    xa = packing.to_act(x, "fp16x2").cuda()
+    stack = layers.LstmStack([layers.LstmLayer(*w, "fp16x2") for w in ws], "fp16x2", True)
+    assert stack.eligible(B, True)
+    last = torch.full((B, H), float("nan"), device="cuda")
+    stack.last_hidden(xa, B, T, last, persistent=True)
+    torch.cuda.synchronize()
+    assert stack.wavefront, "the wavefront grid was not co-resident on this device"
+    assert rel_l2(last, ref[:, -1]) < 1e-3
+    # the scratch sequences, through the op itself
+    first = stack.layers[0]
+    ih, hh = first.packs(packing.WS_GROUP)
+    xp = torch.empty(B * T, 4 * H, dtype=torch.float32, device="cuda")
+    ih(xa, B, T, out2=xp)
+    hs = ops.lstm_stack_ws(xp, hh, stack.upper(), B, T, H)
+    torch.cuda.synchronize()
+    assert float(hs[:, 0].float().abs().max()) == 0.0
+    for l in range(L):
+        assert rel_l2(hs[l, 1:].float().transpose(0, 1), refs[l]) < 2e-3, l
+    # layer by layer (two-term weights everywhere) on the same inputs
+    plain = layers.LstmStack([layers.LstmLayer(*w, "fp16x2") for w in ws], "fp16x2", False)
+    last_b = torch.full((B, H), float("nan"), device="cuda")
+    plain.last_hidden(xa, B, T, last_b, persistent=True)
+    assert rel_l2(last, last_b) < 1e-3
+    # deterministic: a second launch gives the same bits
+    last2 = torch.empty_like(last)
+    stack.last_hidden(xa, B, T, last2, persistent=True)
+    assert torch.equal(last, last2)
+
+
 @pytest.mark.parametrize("H,freq,B,T", [(32, 32, 5, 64), (44, 22, 3, 88), (32, 32, 1, 32)])
 def test_bilstm_small_and_code_downsampling(H, freq, B, T):
     from autoformer_b200 import layers, packing

@@ -193,6 +193,52 @@ def test_lstm_layer_small_batch_takes_weight_stationary_packing(cpu_kernels, B, 
     assert rel_l2(f32, ref) < tol and rel_l2(last, ref[:, -1]) < tol
 
 
+@pytest.mark.parametrize("B,H,L", [(2, 768, 3), (40, 512, 2), (64, 256, 4)])
+def test_lstm_stack_wavefront_packing_and_fallback(cpu_kernels, B, H, L):
+    """Small-batch fp16x2 stacks take the wavefront kernel (avc_lstm_stack_ws): two-term W_hh0, one fp16 term of W_ih / W_hh
+    above, biases in the same packed gate order; `wavefront=False`, other precisions and unsupported shapes fall back to
+    the layer-by-layer kernels with the same result."""
+    from autoformer_b200 import layers, ops, packing
+    from oracle.layers import lstm_explicit
+    assert ops.stack_supported(B, H, L, "fp16x2") and not ops.stack_supported(B, H, L, "fp32")
+    assert not ops.stack_supported(65, H, L, "fp16x2") and not ops.stack_supported(B, H, 1, "fp16x2")
+    assert ops.stack_supported(64, 768, 3, "fp16x2") and not ops.stack_supported(64, 1024, 2, "fp16x2")   # TMEM columns
+    assert not ops.stack_supported(64, 768, 4, "fp16x2")                                                  # 192 CTAs
+    torch.manual_seed(B)
+    T, I = 5, 80
+    k = 1.0 / H ** 0.5
+    ws = []
+    x = torch.randn(B, T, I)
+    ref = x.double()
+    for l in range(L):
+        w_ih = (torch.rand(4 * H, I if l == 0 else H) * 2 - 1) * k
+        w_hh, b_ih, b_hh = (torch.rand(4 * H, H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k, (torch.rand(4 * H) * 2 - 1) * k
+        ws.append((w_ih, w_hh, b_ih, b_hh))
+        ref = lstm_explicit(ref, w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
+    calls = []
+    real = ops.lstm_stack_ws
+    ops.lstm_stack_ws = lambda *a, **kw: calls.append(1) or real(*a, **kw)
+    try:
+        outs = {}
+        for name, precision, wavefront in (("stack", "fp16x2", True), ("layers", "fp16x2", False), ("fp32", "fp32", True)):
+            stack = layers.LstmStack([layers.LstmLayer(*w, precision) for w in ws], precision, wavefront)
+            last = torch.full((B, H), float("nan"))
+            n0 = len(calls)
+            stack.last_hidden(packing.to_act(x, precision), B, T, last, persistent=True)
+            assert (len(calls) - n0 == 1) == (name == "stack")
+            outs[name] = last
+        # persistent=False (one launch per frame) never takes the wavefront
+        stack = layers.LstmStack([layers.LstmLayer(*w, "fp16x2") for w in ws], "fp16x2", True)
+        n0 = len(calls)
+        stack.last_hidden(packing.to_act(x, "fp16x2"), B, T, torch.empty(B, H), persistent=False)
+        assert len(calls) == n0
+    finally:
+        ops.lstm_stack_ws = real
+    assert rel_l2(outs["fp32"], ref[:, -1]) < 1e-4
+    assert rel_l2(outs["layers"], ref[:, -1]) < 1e-3 and rel_l2(outs["stack"], ref[:, -1]) < 1e-3
+    assert rel_l2(outs["stack"], outs["layers"]) < 1e-3
+
+
 def test_lstm_layer_sub_batches_when_persistent_grid_exceeds_one_wave(cpu_kernels):
     """B = 600 at H = 1024 needs 192 CTAs > 148 SMs: the layer must split the batch (utterances are independent) and
     still fill every output the caller asked for."""
