@@ -3,27 +3,33 @@
 // avc_lstm_seq_ws runs one layer: a frame is a chain of L2 round trips (grid barrier, h slice, reduction) of about
 // 4.3 us whatever the batch is, and the layers of a stack run one after another -- LstmDV (factory/LstmDV.py:12,20:
 // 3 x LSTM(768), 1000 frames) spends 3 x 1000 such frames.  Layer l at frame t needs only layer l-1 at frame t and its own
-// frame t-1, so the layers can run ONE TICK APART: at tick k layer l works on frame k - l, all layers at once, on
-// disjoint SMs, and the stack costs T + L - 1 ticks instead of L x T frames.
+// frame t-1, so the layers can run a fixed number of TICKS APART, all at once, on disjoint SMs, and the stack costs
+// T + 2 (L - 1) ticks instead of L x T frames.
 //
 // For that the input projection of the layers above the first has to move into the recurrence (a dense projection in
 // front needs the whole sequence of the layer below), and every weight has to stay on chip for the whole sequence:
 //   layer 0:   z = xproj_0[t] (dense GEMM in front, as before)     + W_hh0 h0_{t-1}
 //   layer l>0: z = bias_l + W_ih_l h^{l-1}_t                       + W_hh_l h^l_{t-1}
-// The grid is L layers x R = 4H/128 row blocks x 2 CTAs, each pair a thread-block cluster.  In layer 0 the two CTAs split
-// the K range of W_hh0 (two fp16 terms each, as in "fp16x2"); above, CTA 0 holds the row block of W_ih and CTA 1 that of
-// W_hh as ONE fp16 term each -- that is what fits: 128 rows x 768 channels x 2 bytes = 384 of the 512 tensor-memory
-// columns per CTA beside the accumulator, 144 CTAs for LstmDV.  (Two terms for every matrix would need 47 MB on chip.
-// The single-term layers cost precision: embedding rel-L2 2.6e-4 instead of 1.4e-4 on the test weights, 5.5e-4 instead of
-// 2.3e-4 on the x3-gain stress weights, gate 1e-3 -- scripts/lstm_stack_precision.py; the caller chooses.)
-// The weights are the A operand of tcgen05.mma read from tensor memory; per tick a CTA TMA-loads its operand rows
-// (h^{l-1}_t or h^l_{t-1}: B rows x K channels, in three groups so the MMAs start on the first), issues K/16 MMAs of
-// width N = B', and the pair reduces its two partial sums through distributed shared memory exactly like
-// avc_lstm_seq_ws (st.async crediting the owner's mbarrier); each CTA finalises 16 hidden units: cell update with c in
-// registers, h_t written as fp16 into the stack's scratch sequence hs[l][t+1] (frame 0 is the zero initial state).
-// One release/acquire grid barrier per tick orders the h stores of tick k before the TMA reads of tick k + 1.
+// The grid is L layers x R = 4H/128 row blocks x 2 CTAs, each pair a thread-block cluster; CTA s of a pair holds the K
+// half s of its row block of W_hh and (above the first layer) of W_ih, ONE fp16 term each -- that is what fits: 128 rows
+// x 768 channels x 2 bytes = 384 of the 512 tensor-memory columns per CTA beside two accumulators, 144 CTAs for LstmDV.
+// (Two terms for every matrix would need 47 MB on chip.  One term costs precision: embedding rel-L2 2.7e-4 instead of
+// 1.4e-4 on the test weights, 6e-4 instead of 2.3e-4 on the x3-gain stress weights, gate 1e-3 --
+// scripts/lstm_stack_precision.py; the caller chooses.)
+// The weights are the A operand of tcgen05.mma read from tensor memory.  Measured (profiles/r02_lstm_stack_v1_*): such an
+// MMA takes ~85 cycles whatever its width, so the MMAs are the longest link of a tick's serial chain, and only those on
+// h^l_{t-1} have to be on it: layer l runs TWO ticks behind layer l-1, so h^{l-1}_{t+1} already exists while frame t is
+// being finished, and its product with W_ih is issued right behind the frame's own MMAs into the OTHER of two
+// accumulators -- it runs while the cell warps, the reduction and the grid barrier of frame t are in flight.  At the
+// next tick the W_hh products accumulate on top of it.  Per tick a CTA TMA-loads its K half of h^l_{t-1} (two groups, so
+// the MMAs start on the first) and of h^{l-1}_{t+1}, issues H/32 + H/32 MMAs of width N = B', and the pair reduces its two
+// partial sums through distributed shared memory exactly like avc_lstm_seq_ws (st.async crediting the owner's
+// mbarrier); each CTA finalises 16 hidden units: cell update with c in registers, h_t written as fp16 into the stack's
+// scratch sequence hs[l][t+1] (frame 0 is the zero initial state).  One release/acquire grid barrier per tick orders
+// the h stores of tick k before the TMA reads of tick k + 1.
 //
-// Warp roles: 0 = grid barrier + operand producer, 1 = MMA issuer, 2..5 = reduction + cell (warps 2, 3 store h_t).
+// Warp roles: 0 = grid barrier + operand producer, 1 = MMA issuer, 2..5 (2..9 at 64 utterances) = reduction + cell
+// (warps 2, 3 store h_t).
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
@@ -34,21 +40,19 @@
 
 namespace avc {
 
-constexpr int kStThreads = 192;
-constexpr int kStCellThreads = 128;
 constexpr int kStMaxLayers = AVC_STACK_MAX_LAYERS;
 constexpr int kStRowsOwn = kBlockM / 2;        // gate rows each CTA of the pair finalises
 constexpr int kStUnitsOwn = kStRowsOwn / 4;    // = 16 hidden units
-constexpr int kStGroups = 3;                   // operand-load groups per tick (one mbarrier each)
+constexpr int kStGroups = 2;                   // load groups of the h^l_{t-1} operand (one mbarrier each)
+constexpr int kStSkew = 2;                     // ticks between consecutive layers
 
 struct alignas(64) StackParams {
-  // hs[l] as (64 channels, B rows, H/64 chunks, T + 1 frames), box {64, AR, chunks of one load group, 1}: one TMA
-  // operation brings a whole group of 64-channel operand tiles (rows >= B and chunks >= H/64 are zero-filled)
-  CUtensorMap tmap_h[kStMaxLayers];   // groups of the layers above the first (ceil(H/64 / 3) chunks)
-  CUtensorMap tmap_h0;                // hs[0] in the groups of layer 0's own CTAs (ceil(H/128 / 3) chunks)
-  const __half* w_hh0;                // [4H][2H] = [hi | lo]
+  // hs[l] as (64 channels, B rows, H/64 chunks, T + 1 frames): one TMA operation brings a whole group of 64-channel
+  // operand tiles (rows >= B and chunks >= H/64 are zero-filled)
+  CUtensorMap tmap_c[kStMaxLayers];   // box {64, AR, ceil(H/128 / 2), 1}: a group of the K half of h^l_{t-1}
+  CUtensorMap tmap_p[kStMaxLayers];   // box {64, AR, H/128, 1}: the K half of h^{l-1}_{t+1} (read by layer l + 1)
   const __half* w_ih[kStMaxLayers];   // l >= 1: [4H][H]
-  const __half* w_hh[kStMaxLayers];   // l >= 1: [4H][H]
+  const __half* w_hh[kStMaxLayers];   // [4H][H]
   const float* bias[kStMaxLayers];    // l >= 1: [4H]
   const float* xproj0;
   __half* hs;
@@ -71,21 +75,28 @@ __device__ __forceinline__ void st_async_f4(uint32_t addr, uint32_t mbar, float 
 
 template <int AR>
 struct StackCfg {
+  // 64 utterances: two cell warps per TMEM lane quarter (each drains half of the accumulator columns and finalises half
+  // of the cells) -- measured 1.0 K cycles per tick less than four warps walking everything twice
+  static constexpr int kCellWarps = AR > 32 ? 8 : 4;
+  static constexpr int kCellThreads = 32 * kCellWarps;
+  static constexpr int kThreads = 64 + kCellThreads;
   static constexpr int NQ = AR / 4;                                   // groups of 4 utterances
   static constexpr int kItems = kStUnitsOwn * NQ;                     // (unit, utterance group) pairs an owner finalises
-  static constexpr int IT = (kItems + kStCellThreads - 1) / kStCellThreads;
+  static constexpr int IT = (kItems + kCellThreads - 1) / kCellThreads;
   static constexpr int kHTile = AR * kRowBytes;                       // one 64-channel chunk of the operand rows
   static constexpr int kRedFrameBytes = 2 * AR * kStRowsOwn * 4;      // what one tick pushes into an owner
   static constexpr int kRedBytes = (kRedFrameBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = (AR * kStUnitsOwn * 4 + 1023) / 1024 * 1024;
-  static constexpr uint32_t kAccCols = AR < 32 ? 32 : AR;
-  // operand tiles: whole load groups (the last group of a K range that does not divide by 3 is zero-filled)
-  __host__ __device__ static int h_tiles(int H) { return kStGroups * ((H / 64 + kStGroups - 1) / kStGroups); }
+  static constexpr uint32_t kAccCols = AR < 32 ? 32 : AR;             // one accumulator; there are two
+  // operand tiles: the h^l_{t-1} half in whole load groups (a zero-filled / unused tile when H/128 is odd), then the
+  // h^{l-1}_{t+1} half
+  __host__ __device__ static int crit_tiles(int H) { return kStGroups * ((H / 128 + kStGroups - 1) / kStGroups); }
+  __host__ __device__ static int h_tiles(int H) { return crit_tiles(H) + H / 128; }
   static int smem_bytes(int H) { return h_tiles(H) * kHTile + kRedBytes + kStageBytes + 128 + 1024 /* alignment slack */; }
 };
 
 template <int AR>
-__global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_constant__ StackParams p) {
+__global__ void __launch_bounds__(StackCfg<AR>::kThreads, 1) lstm_stack_kernel(const __grid_constant__ StackParams p) {
   using Cfg = StackCfg<AR>;
   constexpr int NQ = Cfg::NQ, IT = Cfg::IT;
   extern __shared__ uint8_t smem_raw[];
@@ -112,29 +123,27 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
 #define AVC_ST_STAMP(k_, i_) \
   if (clk) clk[((long long)(k_) * n_ctas + blockIdx.x) * 16 + (i_)] = clock64()
 
-  // what this CTA multiplies: `chunks` 64-channel chunks starting at channel k0 of sequence `src`, frame t + frame_off
-  int chunks, terms, k0, src, frame_off;
-  const __half* w;
-  long long w_ld;
-  if (layer == 0) {
-    chunks = p.H / 128; terms = 2; k0 = (int)rank * (p.H / 2); src = 0; frame_off = 0; w = p.w_hh0; w_ld = 2LL * p.H;
-  } else if (rank == 0) {
-    chunks = p.H / 64; terms = 1; k0 = 0; src = layer - 1; frame_off = 1; w = p.w_ih[layer]; w_ld = p.H;
-  } else {
-    chunks = p.H / 64; terms = 1; k0 = 0; src = layer; frame_off = 0; w = p.w_hh[layer]; w_ld = p.H;
-  }
-  const int cpg = (chunks + kStGroups - 1) / kStGroups;          // chunks per load group
-  const int ngroups = (chunks + cpg - 1) / cpg;
-  const CUtensorMap* const tmap = layer == 0 ? &p.tmap_h0 : &p.tmap_h[src];
+  // this CTA multiplies the K half [k0, k0 + H/2) of W_hh (and of W_ih above the first layer): nc 64-channel chunks each
+  const int nc = p.H / 128;
+  const int k0c = (int)rank * nc;                                // first chunk of the half
+  const int cpg = (nc + kStGroups - 1) / kStGroups;              // chunks per load group of the h^l_{t-1} operand
+  const int ngroups = (nc + cpg - 1) / cpg;
+  const bool upper = layer > 0;
+  uint8_t* const s_hp = s_h + Cfg::crit_tiles(p.H) * Cfg::kHTile;   // tiles of h^{l-1}_{t+1}
+  uint64_t* const h_pre = bars + 6;     // the K half of h^{l-1}_{t+1} has landed
+  uint64_t* const pre_done = bars + 7;  // the MMAs that read it have completed (its tiles may be overwritten)
 
   if (threadIdx.x == 0) {
-    mbar_init(w_full, kStCellThreads / 32);
+    mbar_init(w_full, Cfg::kCellWarps);
     mbar_init(d_full, 1);
     mbar_init(red_full, 1);
     mbar_init(epi_done, AR > 32 ? 2 : 1);     // one arrival per warp that stores h_t
     for (int g = 0; g < kStGroups; ++g) mbar_init(h_full + g, 1);
+    mbar_init(h_pre, 1);
+    mbar_init(pre_done, 1);
     fence_mbar_init();
-    prefetch_tmap(tmap);
+    prefetch_tmap(&p.tmap_c[layer]);
+    if (upper) prefetch_tmap(&p.tmap_p[layer - 1]);
   }
   constexpr uint32_t tmem_cols = 512;
   if (warp == 1) {
@@ -145,13 +154,13 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
   cluster_sync_all();                 // the peer credits bytes to this CTA's red_full: its init must be visible cluster-wide
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_ptr);
-  const uint32_t tmem_w = tmem_base + Cfg::kAccCols;        // term 0 at columns [0, 32 chunks), term 1 behind it
-  const int nticks = p.T + p.L - 1;
+  const uint32_t tmem_w = tmem_base + 2 * Cfg::kAccCols;    // W_hh half at columns [0, 32 nc), W_ih half behind it
+  const int nticks = p.T + kStSkew * (p.L - 1);
 
   if (warp == 0) {
     if (lane == 0) {
       for (int k = 0; k < nticks; ++k) {
-        const int t = k - layer;
+        const int t = k - kStSkew * layer;     // the frame this CTA finishes at tick k (t = -1: only the W_ih part of frame 0)
         if (k > 0) {
           // this CTA's part of the previous tick's h is stored, then every CTA's
           if (t - 1 >= 0 && t - 1 < p.T) mbar_wait(epi_done, (t - 1) & 1);
@@ -159,18 +168,25 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
                            clk ? clk + ((long long)k * n_ctas + blockIdx.x) * 16 : nullptr);  // stamp 0: arrival issued
         }
         AVC_ST_STAMP(k, 1);
-        if (t >= 0 && t < p.T) {
-          fence_proxy_async_global();   // the operand rows were written with generic stores
+        const bool crit = t >= 0 && t < p.T, pre = upper && t + 1 >= 0 && t + 1 < p.T;
+        if (crit || pre) fence_proxy_async_global();   // the operand rows were written with generic stores
+        if (crit)
           for (int g = 0; g < ngroups; ++g) {
             mbar_arrive_expect_tx(h_full + g, cpg * Cfg::kHTile);          // the whole box, zero-filled part included
-            tma_load_4d(s_h + g * cpg * Cfg::kHTile, tmap, h_full + g, 0, 0, k0 / 64 + g * cpg, t + frame_off);
+            tma_load_4d(s_h + g * cpg * Cfg::kHTile, &p.tmap_c[layer], h_full + g, 0, 0, k0c + g * cpg, t);
           }
-          if (clk)                       // profiling only: when each group really landed (the MMA thread sees a group
-            for (int g = 0; g < ngroups; ++g) {   // only after it has issued the previous group's MMAs)
-              mbar_wait(h_full + g, t & 1);
-              AVC_ST_STAMP(k, 11 + g);
-            }
+        if (pre) {
+          // h^{l-1}_{t+1} = frame t + 2 of the sequence below (stored a tick ago); its tiles are free once the MMAs of the
+          // previous W_ih part have completed (long ago: they were issued a tick earlier)
+          if (t + 1 > 0) mbar_wait(pre_done, t & 1);
+          mbar_arrive_expect_tx(h_pre, nc * Cfg::kHTile);
+          tma_load_4d(s_hp, &p.tmap_p[layer - 1], h_pre, 0, 0, k0c, t + 2);
         }
+        if (clk && crit)                 // profiling only: when each group really landed (the MMA thread sees a group
+          for (int g = 0; g < ngroups; ++g) {   // only after it has issued the previous group's MMAs)
+            mbar_wait(h_full + g, t & 1);
+            AVC_ST_STAMP(k, 11 + g);
+          }
       }
     }
     __syncwarp();
@@ -179,33 +195,52 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
       constexpr uint32_t idesc = umma_idesc(kBlockM, AR, false) ^ kIdescF16Xor;
       mbar_wait(w_full, 0);
       tc_fence_after();
-      for (int t = 0; t < p.T; ++t) {
-        // (the accumulator is free: the operands of frame t exist only after this CTA's cell warps drained frame t - 1)
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(h_full + g, t & 1);
-          AVC_ST_STAMP(t + layer, g == 0 ? 2 : 7 + g);              // 2, 8, 9: operand group g landed
-          tc_fence_after();             // also orders the cell warps' accumulator reads of frame t - 1 before these MMAs
-          const int c0 = g * cpg, c1 = min(chunks, c0 + cpg);
-          for (int c = c0; c < c1; ++c) {
-            const uint32_t h = smem_u32(s_h + c * Cfg::kHTile);
-            for (int term = 0; term < terms; ++term) {
-              const uint32_t wt = tmem_w + (term * chunks + c) * 32;       // 8 columns per K = 16
+      for (int t = upper ? -1 : 0; t < p.T; ++t) {
+        const int k = t + kStSkew * layer;
+        if (t >= 0) {
+          // frame t: W_hh h_{t-1} on top of the W_ih part issued a tick ago (layer 0: a fresh accumulator)
+          const uint32_t acc = tmem_base + (t & 1) * Cfg::kAccCols;
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(h_full + g, t & 1);
+            AVC_ST_STAMP(k, g == 0 ? 2 : 7 + g);                      // 2, 8: operand group g landed
+            tc_fence_after();
+            const int c0 = g * cpg, c1 = min(nc, c0 + cpg);
+            for (int c = c0; c < c1; ++c) {
+              const uint32_t h = smem_u32(s_h + c * Cfg::kHTile);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_bf16_ts(tmem_base, wt + kk * 8, umma_desc_sw128(h + kk * 32), idesc,
-                             (c == 0 && term == 0 && kk == 0) ? 0u : 1u);
+                umma_bf16_ts(acc, tmem_w + c * 32 + kk * 8, umma_desc_sw128(h + kk * 32), idesc,
+                             (!upper && c == 0 && kk == 0) ? 0u : 1u);
             }
           }
+          umma_commit(d_full);
+          AVC_ST_STAMP(k, 10);                                        // the frame's MMAs issued
         }
-        umma_commit(d_full);
-        AVC_ST_STAMP(t + layer, 10);                                  // all MMAs of the frame issued
+        if (upper && t + 1 < p.T) {
+          // W_ih h^{l-1}_{t+1} into the other accumulator (drained two frames ago: that drain is ordered before these
+          // MMAs through epi_done -> grid barrier -> h_pre), off the serial chain of the tick
+          const uint32_t acc = tmem_base + ((t + 1) & 1) * Cfg::kAccCols;
+          mbar_wait(h_pre, (t + 1) & 1);
+          tc_fence_after();
+          for (int c = 0; c < nc; ++c) {
+            const uint32_t h = smem_u32(s_hp + c * Cfg::kHTile);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(acc, tmem_w + (nc + c) * 32 + kk * 8, umma_desc_sw128(h + kk * 32), idesc,
+                           (c == 0 && kk == 0) ? 0u : 1u);
+          }
+          umma_commit(pre_done);
+          AVC_ST_STAMP(k, 9);                                         // the W_ih part of the next frame issued
+        }
       }
     }
     __syncwarp();
   } else {
     const int q = warp & 3;                           // TMEM lane quarter
     const int row = q * 32 + lane;                    // accumulator row = packed gate row within the row block
-    const int ctid = threadIdx.x - 64;                // 0..127
+    const int ctid = threadIdx.x - 64;                // 0 .. kCellThreads - 1
+    constexpr int HW = Cfg::kCellWarps / 4;           // warps per lane quarter
+    const int half = (warp - 2) / 4;                  // which of them
     // reduction buffer of an owner: [source rank][group of 4 utterances][gate][owned unit][4] fp32 -- a warp's 16-byte
     // stores of one group fill one contiguous 512-byte run, and the cell threads of adjacent units read adjacent float4
     const uint32_t owner = row / kStRowsOwn;
@@ -213,19 +248,19 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
     const uint32_t push_addr = st_map_to_cta(smem_u32(s_red + ((int)rank * NQ * kStRowsOwn + slot) * 4), owner);
     const uint32_t owner_bar = st_map_to_cta(smem_u32(red_full), owner);
     {
-      // this thread's W row -> its TMEM lane, once: 32 fp16 (16 columns) per store
+      // this thread's W rows -> its TMEM lane, once: 32 fp16 (16 columns) per store; W_hh half, then W_ih half
       const uint32_t lane_base = tmem_w + (static_cast<uint32_t>(q * 32) << 16);
-      for (int term = 0; term < terms; ++term) {
-        const uint4* srcw =
-            reinterpret_cast<const uint4*>(w + ((long long)r * kBlockM + row) * w_ld + (long long)term * p.H + k0);
-        for (int g = 0; g < 2 * chunks; ++g) {
+      for (int m = 0; m < (upper ? 2 : 1); ++m) {
+        const __half* w = m == 0 ? p.w_hh[layer] : p.w_ih[layer];
+        const uint4* srcw = reinterpret_cast<const uint4*>(w + ((long long)r * kBlockM + row) * p.H + k0c * 64);
+        for (int g = half * (2 * nc / HW); g < (half + 1) * (2 * nc / HW); ++g) {
           uint32_t v[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 u = __ldg(srcw + g * 4 + i);
             v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
           }
-          tmem_st_32x16(lane_base + term * chunks * 32 + g * 16, v);
+          tmem_st_32x16(lane_base + m * nc * 32 + g * 16, v);
         }
       }
       tmem_st_wait();
@@ -239,7 +274,7 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
     float c_state[IT][4];
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
-      const int e = it * kStCellThreads + ctid;       // adjacent threads: adjacent units (contiguous reads)
+      const int e = it * Cfg::kCellThreads + ctid;    // adjacent threads: adjacent units (contiguous reads)
       u_own[it] = e % kStUnitsOwn;
       n4[it] = e / kStUnitsOwn;
       active[it] = n4[it] < NQ;
@@ -269,25 +304,29 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
         }
       if (threadIdx.x == 64) mbar_arrive_expect_tx(red_full, Cfg::kRedFrameBytes);
       mbar_wait(d_full, t & 1);
-      if (threadIdx.x == 64) AVC_ST_STAMP(t + layer, 3);
+      if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 3);
       tc_fence_after();
       // this thread's accumulator row, pushed to the CTA that owns it
       {
-        uint32_t a[AR / 16][16];
+        constexpr int JN = AR / 16 / HW;              // groups of 16 utterances this warp drains
+        uint32_t a[JN][16];
 #pragma unroll
-        for (int j = 0; j < AR / 16; ++j) tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 16, a[j]);
+        for (int jj = 0; jj < JN; ++jj)
+          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (t & 1) * Cfg::kAccCols + (half * JN + jj) * 16,
+                        a[jj]);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < AR / 16; ++j)
+        for (int jj = 0; jj < JN; ++jj)
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            st_async_f4(push_addr + (j * 4 + i) * kStRowsOwn * 16, owner_bar, __uint_as_float(a[j][i * 4]),
-                        __uint_as_float(a[j][i * 4 + 1]), __uint_as_float(a[j][i * 4 + 2]), __uint_as_float(a[j][i * 4 + 3]));
+            st_async_f4(push_addr + ((half * JN + jj) * 4 + i) * kStRowsOwn * 16, owner_bar, __uint_as_float(a[jj][i * 4]),
+                        __uint_as_float(a[jj][i * 4 + 1]), __uint_as_float(a[jj][i * 4 + 2]),
+                        __uint_as_float(a[jj][i * 4 + 3]));
       }
       tc_fence_before();                // accumulator reads before the next frame's MMAs (via epi_done -> h_full)
-      if (threadIdx.x == 64) AVC_ST_STAMP(t + layer, 4);
+      if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 4);
       mbar_wait_cluster(red_full, t & 1);
-      if (threadIdx.x == 64) AVC_ST_STAMP(t + layer, 5);
+      if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 5);
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
         if (!active[it]) continue;
@@ -307,8 +346,8 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
           s_stage[(n4[it] * 4 + j) * kStUnitsOwn + u_own[it]] = hn;
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kStCellThreads) : "memory");
-      if (threadIdx.x == 64) AVC_ST_STAMP(t + layer, 6);
+      asm volatile("bar.sync 1, %0;" ::"n"(Cfg::kCellThreads) : "memory");
+      if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 6);
       if (warp == 2 || (AR > 32 && warp == 3)) {
         // utterance n: the 16 units this CTA finalised = 32 bytes of fp16 in frame t + 1 of this layer's sequence
         const int n = (warp - 2) * 32 + lane;
@@ -327,7 +366,7 @@ __global__ void __launch_bounds__(kStThreads, 1) lstm_stack_kernel(const __grid_
         }
         __syncwarp();
         if (lane == 0) {
-          AVC_ST_STAMP(t + layer, 7);
+          AVC_ST_STAMP(t + kStSkew * layer, 7);
           mbar_arrive(epi_done);        // after bar.sync 1: every cell warp has drained the accumulator too
         }
       }
@@ -360,7 +399,7 @@ static int launch_stack(const StackParams& p, const avc_lstm_stack_desc* d, cuda
   const int grid = d->L * (4 * d->H / kBlockM) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kStThreads);
+  cfg.blockDim = dim3(Cfg::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -402,10 +441,10 @@ extern "C" int avc_lstm_stack_ws(const avc_lstm_stack_desc* d, void* stream_v) {
   AVC_REQUIRE(d != nullptr, "avc_lstm_stack_ws: null descriptor");
   AVC_REQUIRE(d->B > 0 && d->B <= 64 && d->T > 0, "avc_lstm_stack_ws: B=%d T=%d (1 <= B <= 64)", d->B, d->T);
   AVC_REQUIRE(d->L >= 1 && d->L <= kStMaxLayers, "avc_lstm_stack_ws: L=%d (1..%d layers)", d->L, kStMaxLayers);
-  AVC_REQUIRE(d->H > 0 && d->H % 128 == 0 && d->H / 2 + 64 <= 512,
-              "avc_lstm_stack_ws: unsupported H=%d (multiple of 128, at most 896: the weights of a CTA fill H/2 "
-              "tensor-memory columns beside the accumulator)", d->H);
-  AVC_REQUIRE(d->xproj0 && d->w_hh0 && d->hs && d->grid_barrier, "avc_lstm_stack_ws: missing buffer");
+  AVC_REQUIRE(d->H > 0 && d->H % 128 == 0 && d->H / 2 + 128 <= 512,
+              "avc_lstm_stack_ws: unsupported H=%d (multiple of 128, at most 768: the weights of a CTA fill H/2 "
+              "tensor-memory columns beside the two accumulators)", d->H);
+  AVC_REQUIRE(d->xproj0 && d->w_hh[0] && d->hs && d->grid_barrier, "avc_lstm_stack_ws: missing buffer");
   for (int l = 1; l < d->L; ++l)
     AVC_REQUIRE(d->w_ih[l] && d->w_hh[l] && d->bias[l], "avc_lstm_stack_ws: missing weights of layer %d", l);
   if (d->L * (4 * d->H / kBlockM) * 2 > num_sms()) {
@@ -417,20 +456,17 @@ extern "C" int avc_lstm_stack_ws(const avc_lstm_stack_desc* d, void* stream_v) {
   StackParams p;
   memset(&p, 0, sizeof(p));
   const uint64_t frame_bytes = (uint64_t)d->B * H * 2, layer_bytes = frame_bytes * (uint64_t)(d->T + 1);
-  const uint32_t cpg_upper = (uint32_t)((d->H / 64 + kStGroups - 1) / kStGroups);
-  const uint32_t cpg_first = (uint32_t)((d->H / 128 + kStGroups - 1) / kStGroups);
+  const uint32_t nc = (uint32_t)(d->H / 128);
   const uint64_t dh[4] = {64, (uint64_t)d->B, H / 64, (uint64_t)d->T + 1};
   const uint64_t sh[3] = {H * 2, 128, frame_bytes};
-  const uint32_t box_first[4] = {64, (uint32_t)ar, cpg_first, 1};
-  if (!encode_tmap_4d(&p.tmap_h0, 2, d->hs, dh, sh, box_first)) return -3;
+  const uint32_t box_c[4] = {64, (uint32_t)ar, (nc + kStGroups - 1) / kStGroups, 1}, box_p[4] = {64, (uint32_t)ar, nc, 1};
   for (int l = 0; l < d->L; ++l) {
-    const uint32_t box[4] = {64, (uint32_t)ar, cpg_upper, 1};
-    if (!encode_tmap_4d(&p.tmap_h[l], 2, static_cast<uint8_t*>(d->hs) + l * layer_bytes, dh, sh, box)) return -3;
+    const void* seq = static_cast<uint8_t*>(d->hs) + l * layer_bytes;
+    if (!encode_tmap_4d(&p.tmap_c[l], 2, seq, dh, sh, box_c) || !encode_tmap_4d(&p.tmap_p[l], 2, seq, dh, sh, box_p)) return -3;
     p.w_ih[l] = static_cast<const __half*>(d->w_ih[l]);
     p.w_hh[l] = static_cast<const __half*>(d->w_hh[l]);
     p.bias[l] = d->bias[l];
   }
-  p.w_hh0 = static_cast<const __half*>(d->w_hh0);
   p.xproj0 = d->xproj0;
   p.hs = static_cast<__half*>(d->hs);
   p.h_last = d->h_last;

@@ -234,9 +234,9 @@ def lstm_stack_default():
 class LstmStack:
     """nn.LSTM(num_layers = L) of which only the top layer's last frame is used (LstmDV.py:20-21, Adjust.py:40-41).
 
-    Small batches in "fp16x2" run all layers as ONE wavefront launch (avc_lstm_stack_ws: layer l one frame behind layer
-    l - 1, T + L - 1 frame times instead of L x T).  On that path the weights of the layers above the first are one fp16
-    term instead of two -- what fits on chip -- which roughly doubles the rounding error of the embedding (2.6e-4
+    Small batches in "fp16x2" run all layers as ONE wavefront launch (avc_lstm_stack_ws: layer l two ticks behind layer
+    l - 1, T + 2 (L - 1) frame times instead of L x T).  On that path the recurrent and inter-layer weights are one fp16
+    term instead of two -- what fits on chip -- which roughly doubles the rounding error of the embedding (2.7e-4
     instead of 1.4e-4 on the test weights, scripts/lstm_stack_precision.py; gate 1e-3); `wavefront=False` keeps the
     two-term layer-by-layer kernels."""
 
@@ -245,16 +245,16 @@ class LstmStack:
         self.precision = precision
         self.H = layers_[0].H
         self.wavefront = lstm_stack_default() if wavefront is None else wavefront
-        self._upper = None
+        self._packs = None
 
-    def upper(self):
-        if self._upper is None:
+    def packs(self):
+        if self._packs is None:
             packs = []
-            for layer in self.layers[1:]:
-                w_ih, w_hh, b_ih, b_hh = layer._raw()
-                packs.append(tuple(t.to(layer.w_hh.device) for t in packing.pack_lstm_stack_upper(w_ih, w_hh, b_ih, b_hh)))
-            self._upper = packs
-        return self._upper
+            for i, layer in enumerate(self.layers):
+                pk = packing.pack_lstm_stack(*layer._raw(), first=i == 0)
+                packs.append(tuple(None if t is None else t.to(layer.w_hh.device) for t in pk))
+            self._packs = packs
+        return self._packs
 
     def eligible(self, B, persistent):
         first = self.layers[0]
@@ -266,10 +266,10 @@ class LstmStack:
         """x: the first layer's input in the operand format; fills h_last [B][H] fp32 with h_{T-1} of the top layer."""
         if self.eligible(B, persistent):
             first = self.layers[0]
-            ih, hh = first.packs(packing.WS_GROUP)
+            ih, _ = first.packs(packing.WS_GROUP)
             xp = torch.empty(B * T, 4 * self.H, dtype=torch.float32, device=x.device)
             ih(x, B, T, out2=xp)
-            if ops.lstm_stack_ws(xp, hh, self.upper(), B, T, self.H, h_last=h_last) is not None:
+            if ops.lstm_stack_ws(xp, self.packs(), B, T, self.H, h_last=h_last) is not None:
                 return h_last
             self.wavefront = False      # the device cannot hold the grid: layer by layer from now on
         h = x

@@ -426,39 +426,40 @@ def lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None, deb
 
 def stack_supported(B, H, L, precision, n_sm=148):
     """Shapes the wavefront stack kernel (avc_lstm_stack_ws) takes: fp16 operands ("fp16x2"), 2 <= L <= 4 layers of the
-    same width, B <= 64, H a multiple of 128 whose H/2 tensor-memory columns of weights fit beside the accumulator, and
-    L x 4H/128 x 2 CTAs within one wave."""
+    same width, B <= 64, H a multiple of 128 whose H/2 tensor-memory columns of weights fit beside the two accumulators,
+    and L x 4H/128 x 2 CTAs within one wave."""
     if precision != "fp16x2" or not 1 <= B <= WS_MAX_BATCH or not 2 <= L <= _lib.STACK_MAX_LAYERS:
         return False
-    if H % 128 or H // 2 + 64 > 512 or L * (4 * H // 128) * 2 > n_sm:
+    if H % 128 or H // 2 + 128 > 512 or L * (4 * H // 128) * 2 > n_sm:
         return False
     ar = 16 if B <= 16 else (32 if B <= 32 else 64)
-    tiles = 3 * ((H // 64 + 2) // 3)                  # whole operand-load groups
+    nc = H // 128
+    tiles = 2 * ((nc + 1) // 2) + nc                  # h^l_{t-1} half in whole load groups + h^{l-1}_{t+1} half
     return tiles * ar * 128 + 2 * ar * 64 * 4 + 4096 + 1152 <= 227 * 1024
 
 
-def lstm_stack_ws(xproj0, w_hh0, upper, B, T, H, h_last=None, hs=None, debug_clk=None):
+def lstm_stack_ws(xproj0, packs, B, T, H, h_last=None, hs=None, debug_clk=None):
     """All layers of a small-batch LSTM stack as one wavefront launch.  xproj0 [B*T][4H] fp32 (layer 0's dense input
-    projection, biases included), w_hh0 [4H][2H] fp16 two-term, `upper` = [(w_ih, w_hh, bias)] of the layers above
-    (packing.pack_lstm_stack_upper); all in the packing.WS_GROUP gate order.  Returns the scratch sequences
-    hs [L][T+1][B][H] fp16 (frame t+1 of layer l = h^l_t), or None when the device cannot hold the grid (nothing was
-    launched)."""
+    projection, biases included), `packs` = [(w_ih, w_hh, bias)] per layer (packing.pack_lstm_stack; w_ih and bias are
+    None for layer 0); all in the packing.WS_GROUP gate order.  Returns the scratch sequences hs [L][T+1][B][H] fp16
+    (frame t+1 of layer l = h^l_t), or None when the device cannot hold the grid (nothing was launched)."""
     lib = _lib.load()
-    _require_cuda(xproj0, w_hh0)
-    dev = w_hh0.device
-    L = 1 + len(upper)
+    _require_cuda(xproj0, packs[0][1])
+    dev = packs[0][1].device
+    L = len(packs)
     assert xproj0.dtype == torch.float32 and xproj0.is_contiguous() and xproj0.numel() == B * T * 4 * H
-    assert w_hh0.dtype == torch.float16 and w_hh0.shape == (4 * H, 2 * H) and w_hh0.is_contiguous()
     if hs is None:
         hs = torch.empty(L, T + 1, B, H, dtype=torch.float16, device=dev)
     assert hs.is_contiguous() and hs.shape == (L, T + 1, B, H) and hs.dtype == torch.float16
     d = _lib.LstmStackDesc()
-    d.xproj0, d.w_hh0, d.hs = xproj0.data_ptr(), w_hh0.data_ptr(), hs.data_ptr()
-    for l, (w_ih, w_hh, bias) in enumerate(upper, start=1):
-        for w in (w_ih, w_hh):
+    d.xproj0, d.hs = xproj0.data_ptr(), hs.data_ptr()
+    for l, (w_ih, w_hh, bias) in enumerate(packs):
+        for w in (w_hh,) if l == 0 else (w_ih, w_hh):
             assert w.dtype == torch.float16 and w.shape == (4 * H, H) and w.is_contiguous() and w.device == dev
-        assert bias.dtype == torch.float32 and bias.shape == (4 * H,) and bias.is_contiguous() and bias.device == dev
-        d.w_ih[l], d.w_hh[l], d.bias[l] = w_ih.data_ptr(), w_hh.data_ptr(), bias.data_ptr()
+        d.w_hh[l] = w_hh.data_ptr()
+        if l > 0:
+            assert bias.dtype == torch.float32 and bias.shape == (4 * H,) and bias.is_contiguous() and bias.device == dev
+            d.w_ih[l], d.bias[l] = w_ih.data_ptr(), bias.data_ptr()
     if h_last is not None:
         assert h_last.is_contiguous() and h_last.shape == (B, H) and h_last.dtype == torch.float32
         d.h_last = h_last.data_ptr()

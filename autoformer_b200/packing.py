@@ -314,13 +314,16 @@ def pack_lstm_hh(w_hh, precision, group):
     return to_operand(w, precision).contiguous()
 
 
-def pack_lstm_stack_upper(w_ih, w_hh, b_ih, b_hh):
-    """A layer above the first for the wavefront stack kernel (avc_lstm_stack_ws): W_ih and W_hh as ONE fp16 term each,
-    rows in the WS_GROUP gate order, plus the fp32 bias b_ih + b_hh in the same order."""
+def pack_lstm_stack(w_ih, w_hh, b_ih, b_hh, first):
+    """One layer for the wavefront stack kernel (avc_lstm_stack_ws): W_hh (and, above the first layer, W_ih) as ONE fp16
+    term, rows in the WS_GROUP gate order, plus the fp32 bias b_ih + b_hh in the same order.  The first layer's W_ih and
+    bias go through the dense projection in front (pack_lstm_ih) and are None here."""
     h = w_hh.shape[1]
-    assert w_ih.shape == (4 * h, h), "the layers above the first take the hidden sequence of the layer below"
     perm = gate_permutation(h, WS_GROUP, w_hh.device)
     one = lambda w: sat_f16(take_rows(w.float(), perm)).to(torch.float16).contiguous()
+    if first:
+        return None, one(w_hh), None
+    assert w_ih.shape == (4 * h, h), "the layers above the first take the hidden sequence of the layer below"
     return one(w_ih), one(w_hh), take_rows(b_ih.float() + b_hh.float(), perm).contiguous()
 
 

@@ -264,31 +264,31 @@ typedef struct avc_lstm_ws_desc {
 int avc_lstm_seq_ws(const avc_lstm_ws_desc* d, void* stream);
 
 /*
- * A whole STACK of small-batch LSTM layers as one wavefront (B <= 64, fp16 operands): layer l works on frame k - l at
- * tick k, all layers at once on disjoint SMs, so nn.LSTM(num_layers = L) costs T + L - 1 frame times instead of L x T.
+ * A whole STACK of small-batch LSTM layers as one wavefront (B <= 64, fp16 operands): layer l runs two ticks behind layer
+ * l - 1, all layers at once on disjoint SMs, so nn.LSTM(num_layers = L) costs T + 2 (L - 1) frame times instead of L x T.
  * Replaces the layer-by-layer loop of factory/LstmDV.py:12,20 (3 x LSTM(80 -> 768), only the last frame of the top
  * layer is used, :21) and factory/Adjust.py:26,40-41.
  *   layer 0:   z_t = xproj0[t]                         + W_hh0 h0_{t-1}      (dense input projection in front, as for
- *                                                                             avc_lstm_seq_ws; W_hh0 as two fp16 terms)
- *   layer l>0: z_t = bias_l + W_ih_l h^{l-1}_t         + W_hh_l h^l_{t-1}    (both matrices resident in tensor memory as
- *                                                                             ONE fp16 term each: that is what fits on chip)
- * Grid: L x (4H / 128) x 2 CTAs (clusters of 2), all co-resident; H % 128 == 0, H <= 896.  Gate rows of every weight
+ *                                                                             avc_lstm_seq_ws)
+ *   layer l>0: z_t = bias_l + W_ih_l h^{l-1}_t         + W_hh_l h^l_{t-1}    (the W_ih product is issued one tick early,
+ *                                                                             off the serial chain of the frame)
+ * Every matrix is resident in tensor memory as ONE fp16 term (that is what fits on chip; avc_lstm_seq_ws keeps two).
+ * Grid: L x (4H / 128) x 2 CTAs (clusters of 2), all co-resident; H % 128 == 0, H <= 768.  Gate rows of every weight
  * matrix, of xproj0 and of the biases are packed  p = 128 (u / 32) + 4 (u % 32) + gate.
  * Returns AVC_ERR_NOT_RESIDENT (nothing launched) when the grid cannot be co-resident.
  */
 #define AVC_STACK_MAX_LAYERS 4
 typedef struct avc_lstm_stack_desc {
   const float* xproj0;                        /* [B*T][4H] fp32, packed column order, biases of layer 0 included */
-  const void* w_hh0;                          /* [4H][2H] = [w_hi | w_lo] fp16, packed row order */
   const void* w_ih[AVC_STACK_MAX_LAYERS];     /* l >= 1: [4H][H] fp16, packed row order (entry 0 unused) */
-  const void* w_hh[AVC_STACK_MAX_LAYERS];     /* l >= 1: [4H][H] fp16 */
-  const float* bias[AVC_STACK_MAX_LAYERS];    /* l >= 1: [4H] fp32 = b_ih + b_hh, packed order */
+  const void* w_hh[AVC_STACK_MAX_LAYERS];     /* [4H][H] fp16, packed row order */
+  const float* bias[AVC_STACK_MAX_LAYERS];    /* l >= 1: [4H] fp32 = b_ih + b_hh, packed order (entry 0 unused) */
   void* hs;                                   /* scratch [L][T+1][B][H] fp16: frame t+1 of layer l = h^l_t (frame 0 is zeroed
                                                  by the library); on return hs[L-1] holds the top layer's sequence */
   float* h_last;                              /* optional [B][H] fp32: h_{T-1} of the top layer (may be NULL) */
   unsigned int* grid_barrier;                 /* one counter; zeroed by the library */
   int B, T, H, L;
-  long long* debug_clk;                       /* optional device buffer, 16 x int64 per (tick, CTA), T + L - 1 ticks */
+  long long* debug_clk;                       /* optional device buffer, 16 x int64 per (tick, CTA), T + 2 (L - 1) ticks */
 } avc_lstm_stack_desc;
 
 int avc_lstm_stack_ws(const avc_lstm_stack_desc* d, void* stream);

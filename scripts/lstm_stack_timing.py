@@ -2,7 +2,7 @@
 the LstmDV recurrence and a per-tick clock64 breakdown (profiling aid).
 Stamps per (tick, CTA): 0 barrier arrival issued (own h stored, membar done), 1 grid barrier passed, 2 first operand group
 landed (MMA thread), 3 accumulator ready (cell warps), 4 partial sums pushed, 5 both partial sums of the owned rows landed,
-6 cell update done, 7 h stored, 8 / 9 second / third operand group landed, 10 all MMAs issued, 11-13 operand groups landed (polled by the producer thread).  clock64 is per SM: only differences within one CTA are meaningful."""
+6 cell update done, 7 h stored, 8 second operand group landed, 9 next frame's W_ih part issued, 10 the frame's MMAs issued, 11-12 operand groups landed (polled by the producer thread).  clock64 is per SM: only differences within one CTA are meaningful."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -40,14 +40,14 @@ def run(B=64, T=1000, H=768, L=3, I=80):
         out[name] = timed(lambda: st.last_hidden(x, B, T, last, persistent=True))
         out[name + "_h"] = last.clone()
     st = build(H, L, I, True)
-    ih, hh = st.layers[0].packs(packing.WS_GROUP)
+    ih, _ = st.layers[0].packs(packing.WS_GROUP)
     xp = torch.empty(B * T, 4 * H, dtype=torch.float32, device="cuda")
     ih(x, B, T, out2=xp)
-    rec = timed(lambda: ops.lstm_stack_ws(xp, hh, st.upper(), B, T, H))
+    rec = timed(lambda: ops.lstm_stack_ws(xp, st.packs(), B, T, H))
     grid = L * (4 * H // 128) * 2
-    nt = T + L - 1
+    nt = T + 2 * (L - 1)
     dbg = torch.zeros(nt * grid * 16, dtype=torch.int64, device="cuda")
-    ops.lstm_stack_ws(xp, hh, st.upper(), B, T, H, debug_clk=dbg)
+    ops.lstm_stack_ws(xp, st.packs(), B, T, H, debug_clk=dbg)
     torch.cuda.synchronize()
     d = dbg.cpu().view(nt, grid, 16).double()
     diff = float((out["wavefront_h"] - out["layer by layer_h"]).norm() / out["layer by layer_h"].norm())
@@ -56,13 +56,13 @@ def run(B=64, T=1000, H=768, L=3, I=80):
           f"h_last rel diff {diff:.2e}")
     R2 = (4 * H // 128) * 2
     for l in range(L):
-        cur, nxt = d[10 + L:T - 1, l * R2:(l + 1) * R2], d[11 + L:T, l * R2:(l + 1) * R2]
+        cur, nxt = d[10 + 2 * L:T - 1, l * R2:(l + 1) * R2], d[11 + 2 * L:T, l * R2:(l + 1) * R2]
         f = lambda a: f"{a.mean():.0f}"
-        for nm, sl in (("even CTAs (layer 0: K half 0, above: W_ih)", slice(0, None, 2)), ("odd CTAs (K half 1 / W_hh)", slice(1, None, 2))):
+        for nm, sl in (("even CTAs (K half 0)", slice(0, None, 2)), ("odd CTAs (K half 1)", slice(1, None, 2))):
             c, n = cur[:, sl], nxt[:, sl]
             print(f"  layer {l} {nm}: h stored -> barrier passed {f(n[..., 1] - c[..., 7])} (after the arrival was issued "
-                  f"{f(n[..., 1] - n[..., 0])}), passed -> operand groups landed {f(c[..., 11] - c[..., 1])} / {f(c[..., 12] - c[..., 1])} / {f(c[..., 13] - c[..., 1])} "
-                  f"(seen by the MMA thread {f(c[..., 2] - c[..., 1])} / {f(c[..., 8] - c[..., 1])} / {f(c[..., 9] - c[..., 1])}), "
+                  f"{f(n[..., 1] - n[..., 0])}), passed -> operand groups landed {f(c[..., 11] - c[..., 1])} / {f(c[..., 12] - c[..., 1])} "
+                  f"(seen by the MMA thread {f(c[..., 2] - c[..., 1])} / {f(c[..., 8] - c[..., 1])}), next frame's W_ih part issued {f(c[..., 9] - c[..., 2])} after the first group, "
                   f"first group -> all MMAs issued {f(c[..., 10] - c[..., 2])}, -> accumulator ready "
                   f"{f(c[..., 3] - c[..., 2])}, tmem ld + push {f(c[..., 4] - c[..., 3])}, wait for the pair's sums "
                   f"{f(c[..., 5] - c[..., 4])}, cell {f(c[..., 6] - c[..., 5])}, h store {f(c[..., 7] - c[..., 6])}, tick "

@@ -185,38 +185,40 @@ def _emu_lstm_seq_ws(xproj, w_hh, B, T, H, hseq=None, hseq_f32=None, h_last=None
     return hseq
 
 
-def _emu_lstm_stack_ws(xproj0, w_hh0, upper, B, T, H, h_last=None, hs=None, debug_clk=None):
-    """Mirror of lstm_stack_kernel: tick k runs frame k - l of layer l; hs[l][t + 1] = fp16(h^l_t), frame 0 zero; layer 0
-    adds xproj0 and multiplies the two-term W_hh0, the layers above multiply ONE fp16 term of W_ih (rows of the layer
-    below at frame t + 1) and of W_hh (own rows at frame t); gate rows packed p = 128 (u//32) + 4 (u%32) + gate."""
-    L = 1 + len(upper)
+def _emu_lstm_stack_ws(xproj0, packs, B, T, H, h_last=None, hs=None, debug_clk=None):
+    """Mirror of lstm_stack_kernel: tick k finishes frame k - 2 l of layer l; hs[l][t + 1] = fp16(h^l_t), frame 0 zero;
+    layer 0 adds xproj0, the layers above add the bias and ONE fp16 term of W_ih times the rows of the layer below at frame
+    t + 1; every layer multiplies ONE fp16 term of W_hh with its own rows at frame t; gate rows packed
+    p = 128 (u//32) + 4 (u%32) + gate."""
+    L = len(packs)
     assert ops.stack_supported(B, H, L, "fp16x2")
     if hs is None:
         hs = torch.full((L, T + 1, B, H), float("nan"), dtype=torch.float16)
     hs[:, 0] = 0                                      # the library zeroes frame 0 of every layer
-    w0 = w_hh0[:, :H].double() + w_hh0[:, H:].double()
     xp = xproj0.double().reshape(B, T, 4 * H)
     u = torch.arange(H)
     base = 128 * (u // 32) + 4 * (u % 32)
     c = torch.zeros(L, B, H, dtype=torch.float64)
-    for k in range(T + L - 1):
+    for k in range(T + 2 * (L - 1)):
         new = {}
         for l in range(L):
-            t = k - l
+            t = k - 2 * l
             if not 0 <= t < T:
                 continue
+            w_ih, w_hh, bias = packs[l]
+            assert w_hh.dtype == torch.float16
+            z = hs[l, t].double() @ w_hh.double().t()
             if l == 0:
-                z = xp[:, t] + hs[0, t].double() @ w0.t()
+                z = z + xp[:, t]
             else:
-                w_ih, w_hh, bias = upper[l - 1]
-                assert w_ih.dtype == torch.float16 and w_hh.dtype == torch.float16
-                z = bias.double() + hs[l - 1, t + 1].double() @ w_ih.double().t() + hs[l, t].double() @ w_hh.double().t()
+                assert w_ih.dtype == torch.float16 and not torch.isnan(hs[l - 1, t + 1].float()).any()
+                z = z + bias.double() + hs[l - 1, t + 1].double() @ w_ih.double().t()
             zi, zf, zg, zo = (z[:, base + g] for g in range(4))
             c[l] = torch.sigmoid(zf) * c[l] + torch.sigmoid(zi) * torch.tanh(zg)
             new[l] = torch.sigmoid(zo) * torch.tanh(c[l])
         for l, h in new.items():                      # stores of a tick become visible at the grid barrier
-            hs[l, k - l + 1] = h.to(torch.float16)
-            if l == L - 1 and k - l == T - 1 and h_last is not None:
+            hs[l, k - 2 * l + 1] = h.to(torch.float16)
+            if l == L - 1 and k - 2 * l == T - 1 and h_last is not None:
                 h_last.copy_(h.float())
     return hs
 

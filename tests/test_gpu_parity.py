@@ -172,10 +172,10 @@ def test_lstm_stack_wavefront_matches_explicit_lstm(B, T, I, H, L):
     assert rel_l2(last, ref[:, -1]) < 1e-3
     # the scratch sequences, through the op itself
     first = stack.layers[0]
-    ih, hh = first.packs(packing.WS_GROUP)
+    ih, _ = first.packs(packing.WS_GROUP)
     xp = torch.empty(B * T, 4 * H, dtype=torch.float32, device="cuda")
     ih(xa, B, T, out2=xp)
-    hs = ops.lstm_stack_ws(xp, hh, stack.upper(), B, T, H)
+    hs = ops.lstm_stack_ws(xp, stack.packs(), B, T, H)
     torch.cuda.synchronize()
     assert float(hs[:, 0].float().abs().max()) == 0.0
     for l in range(L):
