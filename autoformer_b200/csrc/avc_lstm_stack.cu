@@ -247,6 +247,10 @@ __global__ void __launch_bounds__(StackCfg<AR>::kThreads, 1) lstm_stack_kernel(c
     const int slot = (row & 3) * kStUnitsOwn + (row % kStRowsOwn) / 4;
     const uint32_t push_addr = st_map_to_cta(smem_u32(s_red + ((int)rank * NQ * kStRowsOwn + slot) * 4), owner);
     const uint32_t owner_bar = st_map_to_cta(smem_u32(red_full), owner);
+    // the half of the rows this CTA owns itself stays local (plain shared-memory stores + a barrier among the cell warps):
+    // only the peer's half crosses the cluster (~21 B/clk: 16 KB per tick at 64 utterances)
+    const bool local = owner == rank;
+    float* const local_ptr = s_red + ((int)rank * NQ * kStRowsOwn + slot) * 4;
     {
       // this thread's W rows -> its TMEM lane, once: 32 fp16 (16 columns) per store; W_hh half, then W_ih half
       const uint32_t lane_base = tmem_w + (static_cast<uint32_t>(q * 32) << 16);
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(StackCfg<AR>::kThreads, 1) lstm_stack_kernel(c
                                                        4 * ((int)rank * kStUnitsOwn + u_own[it])));
           z[it][j][0] = xp.x; z[it][j][1] = xp.y; z[it][j][2] = xp.z; z[it][j][3] = xp.w;
         }
-      if (threadIdx.x == 64) mbar_arrive_expect_tx(red_full, Cfg::kRedFrameBytes);
+      if (threadIdx.x == 64) mbar_arrive_expect_tx(red_full, Cfg::kRedFrameBytes / 2);   // the peer's half
       mbar_wait(d_full, t & 1);
       if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 3);
       tc_fence_after();
@@ -318,13 +322,21 @@ __global__ void __launch_bounds__(StackCfg<AR>::kThreads, 1) lstm_stack_kernel(c
 #pragma unroll
         for (int jj = 0; jj < JN; ++jj)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            st_async_f4(push_addr + ((half * JN + jj) * 4 + i) * kStRowsOwn * 16, owner_bar, __uint_as_float(a[jj][i * 4]),
-                        __uint_as_float(a[jj][i * 4 + 1]), __uint_as_float(a[jj][i * 4 + 2]),
-                        __uint_as_float(a[jj][i * 4 + 3]));
+          for (int i = 0; i < 4; ++i) {
+            const int grp = (half * JN + jj) * 4 + i;             // group of 4 utterances
+            if (local)
+              *reinterpret_cast<float4*>(local_ptr + grp * kStRowsOwn * 4) =
+                  make_float4(__uint_as_float(a[jj][i * 4]), __uint_as_float(a[jj][i * 4 + 1]),
+                              __uint_as_float(a[jj][i * 4 + 2]), __uint_as_float(a[jj][i * 4 + 3]));
+            else
+              st_async_f4(push_addr + grp * kStRowsOwn * 16, owner_bar, __uint_as_float(a[jj][i * 4]),
+                          __uint_as_float(a[jj][i * 4 + 1]), __uint_as_float(a[jj][i * 4 + 2]),
+                          __uint_as_float(a[jj][i * 4 + 3]));
+          }
       }
       tc_fence_before();                // accumulator reads before the next frame's MMAs (via epi_done -> h_full)
       if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 4);
+      asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kCellThreads) : "memory");   // the local half is in place
       mbar_wait_cluster(red_full, t & 1);
       if (threadIdx.x == 64) AVC_ST_STAMP(t + kStSkew * layer, 5);
 #pragma unroll
