@@ -176,6 +176,10 @@ class Resblock2Desc(ctypes.Structure):
         ("out2", ctypes.c_void_p),
         ("out2_ld", ctypes.c_longlong),
         ("debug_clk", ctypes.c_void_p),
+        ("wav", ctypes.c_void_p),
+        ("mono_w", ctypes.c_void_p),
+        ("mono_bias", ctypes.c_float),
+        ("mono_taps", ctypes.c_int),
     ]
 
 

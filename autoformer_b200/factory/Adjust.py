@@ -15,11 +15,11 @@ from .Norm import ConvNorm, LinearNorm
 class AdjustPlan:
     """Packed weights of one ``Adjust`` block taken from a (possibly enclosing) state_dict under ``prefix``."""
 
-    def __init__(self, sd, prefix, precision):
+    def __init__(self, sd, prefix, precision, wavefront=None):
         p = prefix + "." if prefix else ""
         self.precision = precision
         self.convs = [layers.conv_bn_layer(sd, f"{p}convolutions.{i}", precision, "relu") for i in range(3)]
-        self.lstm = layers.LstmStack(layers.lstm_layers(sd, f"{p}lstm", 3, precision), precision)
+        self.lstm = layers.LstmStack(layers.lstm_layers(sd, f"{p}lstm", 3, precision), precision, wavefront)
         self.w = sd[f"{p}embedding.linear_layer.weight"].float().contiguous()
         self.b = sd[f"{p}embedding.linear_layer.bias"].float().contiguous()
         self.dim_cell = self.w.shape[1]
@@ -48,13 +48,14 @@ class Adjust(layers.PlanOwner, nn.Module):
         self.embedding = LinearNorm(dim_cell, 256)
         self.precision = "fp32"
         self.persistent_lstm = True
+        self.wavefront = None           # None: the library default (layers.LstmStack)
         self._cache = layers.PlanCache()
 
     def _plan(self):
         def build():
             sd = layers.state_for_packing(self)
-            return AdjustPlan(sd, "", self.precision)
-        return self._cache.get(self, (self.precision,), build)
+            return AdjustPlan(sd, "", self.precision, self.wavefront)
+        return self._cache.get(self, (self.precision, self.wavefront), build)
 
     @ops.on_device_of_input
     @torch.no_grad()

@@ -237,6 +237,8 @@ class Generator(layers.PlanOwner, nn.Module):
         self.taps = {}
         # AVC_MELGAN_FUSED=0 (profiling aid): run every ResnetBlock as two avc_conv_gemm launches
         self.fuse_resblocks = os.environ.get("AVC_MELGAN_FUSED", "1") != "0"
+        # AVC_MELGAN_FUSED_OUT=0 (A/B timing): the output convolution as its own pass (avc_conv_to_mono_tanh)
+        self.fuse_output_conv = os.environ.get("AVC_MELGAN_FUSED_OUT", "1") != "0"
         self._cache = layers.PlanCache()
 
     def _plan(self):
@@ -253,7 +255,7 @@ class Generator(layers.PlanOwner, nn.Module):
         cur = ops.alloc_act(B, T, plan.stem.meta["N"], P, dev)
         plan.stem(m0, B, T, out=cur)                                      # model.1 (+ model.2's LeakyReLU)
         L = T
-        final = None
+        final = wav = None
         n_stage = len(plan.stages)
         for si, (r, C, up_raw, up_act, blocks) in enumerate(plan.stages):
             Lr = r * L
@@ -277,6 +279,11 @@ class Generator(layers.PlanOwner, nn.Module):
                         fused(xs, B, Lr, y=cur, y_act=True)                              # + the next model.{i} LeakyReLU
                         if taps is not None:
                             taps[f"stage{si}"] = _inv_lrelu(packing.act_to_float(cur, P))
+                    elif taps is None and self.fuse_output_conv and C == 32:
+                        # model.22-25 (LeakyReLU, ReflectionPad1d(3), Conv1d(32 -> 1, k7), tanh) in the block's epilogue:
+                        # the block's output (1 GB at B = 32) is neither written nor re-read
+                        wav = torch.empty(B, Lr, dtype=torch.float32, device=dev)
+                        fused(xs, B, Lr, wav=wav, mono=(plan.w_out, plan.b_out))
                     else:
                         final = torch.empty(B * Lr, C, dtype=torch.float32, device=dev)
                         fused(xs, B, Lr, out2=final)
@@ -312,7 +319,8 @@ class Generator(layers.PlanOwner, nn.Module):
                         if taps is not None:
                             taps[f"stage{si}"] = _inv_lrelu(final.view(B, Lr, C))
             L = Lr
-        wav = ops.conv_to_mono_tanh(final.view(B, L, -1), plan.w_out, plan.b_out)      # model.22-25
+        if wav is None:
+            wav = ops.conv_to_mono_tanh(final.view(B, L, -1), plan.w_out, plan.b_out)  # model.22-25
         return wav.unsqueeze(1)
 
     @ops.on_device_of_input

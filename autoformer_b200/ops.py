@@ -647,16 +647,18 @@ class Resblock2:
         self.w, self.bias3, self.bias1 = self.w.to(device), self.bias3.to(device), self.bias1.to(device)
         return self
 
-    def __call__(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=False, out2=None):
+    def __call__(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=False, out2=None, wav=None, mono=None):
         """x [B][L + 2d][2C] fp16 two-term residual stream with reflected halo rows (time t at row t + d).
         y: raw output (y_act False) or LeakyReLU(output) (True) as two fp16 terms [B][rows][2C] at rows y_row0 + t
-        (+ `y_reflect` mirrored halo rows); out2: LeakyReLU(output) as exact fp32 [B*L][C].  Exactly one of y / out2."""
+        (+ `y_reflect` mirrored halo rows); out2: LeakyReLU(output) as exact fp32 [B*L][C]; wav [B][L] fp32 with
+        mono = (w [K][C] fp32, bias): the generator's output layer applied in the block's epilogue (C = 32).
+        Exactly one of y / out2 / wav."""
         lib = _lib.load()
         C, d = self.C, self.dilation
         _require_cuda(self.w, x)
         assert x.dtype == torch.float16 and x.dim() == 3 and x.shape == (B, L + 2 * d, 2 * C), (x.shape, (B, L + 2 * d, 2 * C))
         assert x.stride(2) == 1 and x.stride(0) == x.shape[1] * x.stride(1)
-        assert (y is None) != (out2 is None)
+        assert (y is not None) + (out2 is not None) + (wav is not None) == 1
         desc = _lib.Resblock2Desc()
         desc.x, desc.x_ld = x.data_ptr(), x.stride(1)
         desc.w, desc.bias3, desc.bias1 = self.w.data_ptr(), self.bias3.data_ptr(), self.bias1.data_ptr()
@@ -666,16 +668,23 @@ class Resblock2:
             assert y.stride(2) == 1 and y.stride(0) == y.shape[1] * y.stride(1)
             desc.y, desc.y_ld = y.data_ptr(), y.stride(1)
             desc.y_rows_per_utt, desc.y_row0, desc.y_reflect, desc.y_act = y.shape[1], y_row0, y_reflect, 1 if y_act else 0
-        else:
+        elif out2 is not None:
             assert out2.is_cuda and out2.dtype == torch.float32 and out2.shape == (B * L, C) and out2.is_contiguous()
             desc.out2, desc.out2_ld = out2.data_ptr(), out2.stride(0)
+        else:
+            w_out, b_out = mono
+            _require_cuda(wav, w_out)
+            assert wav.dtype == torch.float32 and wav.shape == (B, L) and wav.is_contiguous()
+            assert w_out.dtype == torch.float32 and w_out.is_contiguous() and w_out.shape[1] == C and w_out.shape[0] in (3, 5, 7)
+            desc.wav, desc.mono_w, desc.mono_bias, desc.mono_taps = wav.data_ptr(), w_out.data_ptr(), float(b_out), w_out.shape[0]
         dbg = getattr(self, "debug_clk", None)
         if dbg is not None:
             desc.debug_clk = dbg.data_ptr()
-        with PROFILER.span(self.tag, flops=2.0 * 5 * C * C * B * L,
-                           bytes=float(x.numel() * 2 + (B * L * C * 4))):
+        extra = 2.0 * mono[0].numel() * B * L if wav is not None else 0.0
+        with PROFILER.span(self.tag, flops=2.0 * 5 * C * C * B * L + extra,
+                           bytes=float(x.numel() * 2 + (B * L * 4 if wav is not None else B * L * C * 4))):
             _lib.check(lib.avc_resblock2(ctypes.byref(desc), _stream()), "avc_resblock2")
-        return y if y is not None else out2
+        return y if y is not None else (out2 if out2 is not None else wav)
 
 
 # ------------------------------------------------------------------------------------------------ Meta glue

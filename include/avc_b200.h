@@ -181,7 +181,7 @@ int avc_resblock(const avc_resblock_desc* d, void* stream);
  *   bias3 [C] fp32 (block.2);  bias1 [C] fp32 (block.4 bias + shortcut bias)
  *   y     y (y_act = 0) or LeakyReLU(y) (y_act = 1) as two fp16 terms [B][y_rows_per_utt][y_ld] at row y_row0 + t, plus
  *         y_reflect mirrored halo rows each side (the next block's ReflectionPad1d)
- *   out2  LeakyReLU(y), exact fp32 [B*L][out2_ld]           -- exactly one of y / out2
+ *   out2  LeakyReLU(y), exact fp32 [B*L][out2_ld]           -- exactly one of y / out2 / wav (below)
  * C is 32, 64 or 128, L a multiple of 128, 1 <= dilation <= 16 (C = 128: <= 12).  C = 128 runs on CTA pairs
  * (tcgen05 cta_group::2) with the weights streamed through a TMA ring -- w is then [5][C/64][256][64]: per matrix and
  * 64-channel k-chunk the rows [w_hi[0:64] ; w_lo[0:64] ; w_hi[64:128] ; w_lo[64:128]] -- and writes y only.
@@ -200,6 +200,13 @@ typedef struct avc_resblock2_desc {
   long long out2_ld;
   long long* debug_clk;      /* optional (C = 128 only): 16 x int64 clock64 stamps per tile of CTA 0, first 64 tiles
                                 (profiling aid; NULL in production) */
+  /* Fused generator output layer (C = 32; melgan/modules.py:119-124: LeakyReLU, ReflectionPad1d(K/2), Conv1d(C -> 1, K),
+   * tanh): with wav != NULL the block's LeakyReLU(y) never leaves the SM -- tiles overlap by K - 1 samples, the K-tap
+   * convolution runs on the staged rows in the epilogue, and only wav is written (y and out2 must be NULL). */
+  float* wav;                /* [B][L] fp32 */
+  const float* mono_w;       /* [K][C] fp32 */
+  float mono_bias;
+  int mono_taps;             /* K: 3, 5 or 7 */
 } avc_resblock2_desc;
 
 int avc_resblock2(const avc_resblock2_desc* d, void* stream);

@@ -391,7 +391,7 @@ def _emu_resblock_call(self, xa, x, B, L, out=None, out_row0=0, reflect=0, out_r
     return out if out is not None else (out2 if out2 is not None else out_raw)
 
 
-def _emu_resblock2_call(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=False, out2=None):
+def _emu_resblock2_call(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=False, out2=None, wav=None, mono=None):
     """Mirror of avc_resblock2: reads the PACKED tiles (packing.pack_resblock2 is what gets validated), forms the k3
     operand as ONE fp16 value from the two-term window, keeps the intermediate as two fp16 terms, reads the shortcut
     operand from the centre rows of the same window."""
@@ -429,6 +429,28 @@ def _emu_resblock2_call(self, x, B, L, y=None, y_row0=0, y_reflect=0, y_act=Fals
         full = F.pad(a.transpose(1, 2), (y_reflect, y_reflect), mode="reflect").transpose(1, 2) if y_reflect else a
         y[:, y_row0 - y_reflect:y_row0 + L + y_reflect] = packing.to_act(full.float(), "fp16s")
         return y
+    if wav is not None:
+        # the fused output layer, tile by tile like the kernel: tiles of 128 staged rows overlap by K - 1, output r of a
+        # tile reads rows r .. r + K - 1, mirrored at the ends of the utterance
+        w_out, b_out = mono
+        K, lead = w_out.shape[0], w_out.shape[0] // 2
+        assert C == 32 and wav.shape == (B, L) and w_out.shape == (K, C)
+        a = F.leaky_relu(v, 0.2).float()                                              # staged as exact fp32
+        stride = 128 - (K - 1)
+        for j in range((L + stride - 1) // stride):
+            t0 = j * stride - lead
+            for r in range(stride):
+                t = t0 + lead + r
+                if t >= L:
+                    break
+                acc = torch.zeros(B, dtype=torch.float64)
+                for k in range(K):
+                    tau = t + k - lead
+                    tau = -tau if tau < 0 else (2 * (L - 1) - tau if tau >= L else tau)
+                    assert 0 <= tau - t0 < 128
+                    acc += a[:, tau].double() @ w_out[k].double()
+                wav[:, t] = torch.tanh(acc + b_out).float()
+        return wav
     out2[:] = F.leaky_relu(v, 0.2).float().reshape(B * L, C)
     return out2
 
