@@ -196,7 +196,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
       const int pidx = p.phases == 1 ? 0 : n / p.cs;       // constant over the chunk (cs % 32 == 0)
       const int c = n - pidx * p.cs;
       const int phase = p.phase0 + pidx;
-#pragma unroll
+      // NOT unrolled either: eight copies of the body (x six activations) made the kernel 21.6 K SASS instructions and the
+      // epilogue warps waited for instruction fetch again (ncu: stall_no_instruction on top) -- measured on the mixers'
+      // 344 -> 1376 GEMM at B = 512 (scripts/mixer_unit_timing.py): exact-erf GELU 4.70 ms unrolled x8, 3.64 ms x2,
+      // 3.12 ms x1; no activation 2.48 / 2.28 / 2.21 ms; 11.9 K instructions now
+#pragma unroll 1
       for (int i = 0; i < 8; ++i) {          // (simple excludes split_rows: all eight row groups are this warp's)
         {
           const int m = q * 32 + 4 * i + rsub;
