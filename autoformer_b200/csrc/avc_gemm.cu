@@ -200,6 +200,69 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
       // epilogue warps waited for instruction fetch again (ncu: stall_no_instruction on top) -- measured on the mixers'
       // 344 -> 1376 GEMM at B = 512 (scripts/mixer_unit_timing.py): exact-erf GELU 4.70 ms unrolled x8, 3.64 ms x2,
       // 3.12 ms x1; no activation 2.48 / 2.28 / 2.21 ms; 11.9 K instructions now
+      if (p.tb_log2 >= 5) {
+        // Tiles of >= 32 frames per utterance (every long-sequence layer): the 32 rows of this lane quarter belong to ONE
+        // utterance, so the row part of the address is computed once per chunk and advanced by 4 rows per iteration.
+        // The source-level profile of the loop below (profiles/r02_gemm_epilogue_source.txt) shows ~60 instructions per
+        // iteration, most of them the (utterance, frame) -> 64-bit offset arithmetic and the branches around the output
+        // formats, each waiting on the one before (stall_wait / branch_resolving with two warps per scheduler): 300
+        // cycles per iteration, 10 K per 128 x 256 tile whatever the mainloop does.
+        const int m0 = q * 32 + rsub;
+        const int b = b0 + (m0 >> p.tb_log2);
+        const int t = t0 + (m0 & (tb - 1));
+        const bool b_ok = b < p.B;
+        if (simple == 1) {
+          const long long time0 = (long long)t * p.phases + phase;
+          __nv_bfloat16* po = static_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.out_rows_per_utt + p.out_row0 + time0) * p.out_ld + c;
+          const long long po_step = 4LL * p.phases * p.out_ld;
+          if (!p.out_raw && p.out_mode == 3) {
+            // one fp16 value per element, nothing else ("fp16x2" activations): the commonest shape gets its own loop
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
+              const float o0 = apply_act<ACT>(a.x + bv.x), o1 = apply_act<ACT>(a.y + bv.y);
+              const float o2 = apply_act<ACT>(a.z + bv.z), o3 = apply_act<ACT>(a.w + bv.w);
+              if (b_ok && t + 4 * i < p.T) *reinterpret_cast<uint2*>(po) = make_uint2(pack_f16(o0, o1), pack_f16(o2, o3));
+              po += po_step;
+            }
+          } else {
+            __nv_bfloat16* pr = static_cast<__nv_bfloat16*>(p.out_raw) + ((long long)b * t_out + time0) * p.out_raw_ld + c;
+            const long long pr_step = 4LL * p.phases * p.out_raw_ld;
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = b_ok && t + 4 * i < p.T;
+              const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
+              float o[4] = {a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w};
+              if (p.out_raw) store16(pr, p.raw_mode, p.cs, o, ok);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
+              store16(po, p.out_mode, p.cs, o, ok);
+              po += po_step;
+              pr += pr_step;
+            }
+          }
+        } else {
+          const long long lr0 = (long long)b * p.T + t;
+          float* po = p.out2 + lr0 * p.out2_ld + n;
+          const float* pres = p.residual + lr0 * p.res_ld + n;
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = b_ok && t + 4 * i < p.T;
+            const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
+            float o[4] = {a.x + bv.x, a.y + bv.y, a.z + bv.z, a.w + bv.w};
+            if (has_res) {
+              float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) rv = __ldg(reinterpret_cast<const float4*>(pres));
+              o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
+              pres += 4LL * p.res_ld;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = apply_act<ACT>(o[e]);
+            if (ok) *reinterpret_cast<float4*>(po) = make_float4(o[0], o[1], o[2], o[3]);
+            po += 4LL * p.out2_ld;
+          }
+        }
+      } else
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {          // (simple excludes split_rows: all eight row groups are this warp's)
         {
