@@ -1,6 +1,8 @@
 // HBM-bound glue and the small-H bidirectional LSTM (see include/avc_b200.h).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "../../include/avc_b200.h"
 #include "avc_host.h"
 #include "avc_pipe.cuh"
@@ -187,6 +189,101 @@ __global__ void __launch_bounds__(kSmallWarps * 32) bilstm_small_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
+// H == 32 (AutoVC "A"): FOUR lanes per hidden unit, one CTA of 4 warps per (utterance, direction).
+// ncu on the warp-per-(utterance, direction) kernel above: a step is ~365 instructions of ONE warp at an IPC of 0.5 --
+// fixed-latency dependencies (32 shuffles + 128 FMAs + the cell) that nothing hides, 1.1 K cycles per step whatever the
+// batch is.  Here lane (u, p) keeps the weights of its unit's four gates for the 8 inputs k = 8 p .. 8 p + 7 in registers
+// (32 floats), reads those 8 values of h_{t-1} from shared memory (two 16-byte broadcast loads), and the four partial
+// sums of a unit meet in two butterfly shuffles; all four lanes then run the cell redundantly (no divergence, c replicated)
+// and lane p = 0 publishes h_t.  The serial chain of a step is ~90 instructions instead of ~365.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bilstm32_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh,
+                                                       void* __restrict__ out, int out_mode, int round,
+                                                       float* __restrict__ codes, int T, int freq) {
+  constexpr int H = 32;
+  __shared__ __align__(16) float hb[2][H];
+  const int tid = threadIdx.x;
+  const int u = tid >> 2, part = tid & 3;
+  const int b = blockIdx.x >> 1, dir = blockIdx.x & 1;
+  // w[g][j] = W_hh[dir][g * H + u][8 part + j]
+  float w[4][8];
+  {
+    const float* base = w_hh + (long long)dir * 4 * H * H;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(base + (g * H + u) * H + 8 * part));
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(base + (g * H + u) * H + 8 * part + 4));
+      w[g][0] = a.x; w[g][1] = a.y; w[g][2] = a.z; w[g][3] = a.w;
+      w[g][4] = c4.x; w[g][5] = c4.y; w[g][6] = c4.z; w[g][7] = c4.w;
+    }
+  }
+  if (tid < 2 * H) (&hb[0][0])[tid] = 0.0f;
+  __syncthreads();
+  const int n_codes = T / freq;
+  // this lane adds the input projection of gate `part` of its unit to its partial sum (the butterfly spreads it)
+  const float* xp = xproj + (long long)b * T * (8LL * H) + dir * 4 * H + part * H + u;
+  auto frame = [&](int s) { return dir ? T - 1 - s : s; };
+  constexpr int kPre = 4;                      // projections in flight
+  float xq[kPre];
+#pragma unroll
+  for (int i = 0; i < kPre; ++i) xq[i] = i < T ? __ldg(xp + (long long)frame(i) * (8LL * H)) : 0.0f;
+  float c = 0.0f;
+  for (int s0 = 0; s0 < T; s0 += kPre) {
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+      const int s = s0 + i;
+      if (s >= T) break;
+      const int t = frame(s);
+      const float xv = xq[i];
+      if (s + kPre < T) xq[i] = __ldg(xp + (long long)frame(s + kPre) * (8LL * H));
+      const float4 h0 = *reinterpret_cast<const float4*>(&hb[s & 1][8 * part]);
+      const float4 h1 = *reinterpret_cast<const float4*>(&hb[s & 1][8 * part + 4]);
+      const float hk[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+      float z[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float a = g == part ? xv : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a = fmaf(w[g][j], hk[j], a);
+        z[g] = a;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        z[g] += __shfl_xor_sync(0xffffffffu, z[g], 1);
+        z[g] += __shfl_xor_sync(0xffffffffu, z[g], 2);
+      }
+      float cn, hn;
+      lstm_cell(z[0], z[1], z[2], z[3], c, cn, hn);
+      c = cn;
+      if (part == 0) {
+        hb[(s + 1) & 1][u] = hn;
+        if (out) {
+          const long long o = ((long long)b * T + t) * (2LL * H) + dir * H + u;
+          if (out_mode == 2) {   // split bf16: [hi(2H) | lo(2H)]
+            const __nv_bfloat16 hi = __float2bfloat16_rn(hn);
+            __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out) + ((long long)b * T + t) * (4LL * H) + dir * H + u;
+            ob[0] = hi;
+            ob[2 * H] = __float2bfloat16_rn(hn - __bfloat162float(hi));
+          } else if (out_mode == 1)
+            static_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(hn);
+          else if (out_mode == 3)
+            static_cast<__half*>(out)[o] = __float2half_rn(sat_f16(hn));
+          else
+            static_cast<float*>(out)[o] = round ? round_tf32(hn) : hn;
+        }
+        if (codes) {
+          // code_j = [h_fwd[j*freq + freq-1] || h_bwd[j*freq]]  (factory/AutoVC.py:56-66)
+          const int r = t % freq;
+          if (dir == 0 ? (r == freq - 1) : (r == 0))
+            codes[((long long)b * n_codes + t / freq) * (2LL * H) + dir * H + u] = hn;
+        }
+      }
+      __syncthreads();      // h_t complete (and every lane done with h_{t-1}) before the next step
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LstmDV tail: e = W h + b; out = e / ||e||   one CTA per utterance, one thread per output
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_l2norm_kernel(const float* __restrict__ h, const float* __restrict__ w,
@@ -362,7 +459,12 @@ extern "C" int avc_bilstm_small(const float* xproj, const float* w_hh, void* out
   const int hp = upl * 32;
   const size_t smem = (size_t)2 * H * hp * sizeof(float4) + (size_t)kSmallWarps * hp * sizeof(float);
   const int grid = (B + kSmallWarps / 2 - 1) / (kSmallWarps / 2);
-  if (H == 32) {          // AutoVC "A" (dim_neck = 32): recurrent weights in registers
+  // four lanes per unit: a 2.9x shorter dependent chain per step, four times the warps.  Measured (T = 1024 / 128, two
+  // layers): B = 1 1.15 -> 0.78 ms, B = 32 1.47 -> 0.79 ms, but B = 512 0.21 -> 0.24 ms (issue-bound there): small batches only
+  static const bool lanes4 = getenv("AVC_BILSTM_WARP") == nullptr;   // AVC_BILSTM_WARP=1: the warp-per-direction kernel (A/B timing)
+  if (H == 32 && lanes4 && B <= 128) {
+    bilstm32_kernel<<<2 * B, 128, 0, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32, codes, T, freq);
+  } else if (H == 32) {   // AutoVC "A" (dim_neck = 32): recurrent weights in registers
     auto kern = bilstm_small_kernel<1, true>;
     AVC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kSmallWarps * 32, smem, stream>>>(xproj, w_hh, out, out_dtype, out_round_tf32, codes, B, T, H, freq);
