@@ -143,6 +143,30 @@ def test_lstm_ws_matches_explicit_lstm(B, T, I, H, precision):
     assert rel_l2(f32_b, f32) < (2e-5 if precision == "fp32" else 1e-3)
 
 
+def test_bilstm_small_batch_kernel_agrees_with_the_warp_kernel():
+    """H = 32: batches of <= 128 utterances take four lanes per hidden unit (bilstm32_kernel), larger ones one warp per
+    (utterance, direction); the same utterances through both must agree to fp32 rounding, in every output format."""
+    from autoformer_b200 import ops
+    torch.manual_seed(5)
+    H, T, freq = 32, 96, 32
+    w_hh = ((torch.rand(2, 4 * H, H) * 2 - 1) * 0.5).cuda()
+    xp = (torch.randn(130 * T, 8 * H) * 1.5).cuda()
+    big_out = torch.empty(130, T, 2 * H, device="cuda")
+    big_codes = torch.empty(130, T // freq, 2 * H, device="cuda")
+    ops.bilstm_small(xp, w_hh, 130, T, H, out=big_out, codes=big_codes, freq=freq, round_tf32=False)      # warp kernel
+    for B in (1, 7, 128):
+        out = torch.full((B, T, 2 * H), float("nan"), device="cuda")
+        codes = torch.full((B, T // freq, 2 * H), float("nan"), device="cuda")
+        ops.bilstm_small(xp[:B * T], w_hh, B, T, H, out=out, codes=codes, freq=freq, round_tf32=False)     # four lanes per unit
+        assert rel_l2(out, big_out[:B]) < 1e-5 and rel_l2(codes, big_codes[:B]) < 1e-5
+    half = torch.empty(7, T, 2 * H, dtype=torch.float16, device="cuda")
+    ops.bilstm_small(xp[:7 * T], w_hh, 7, T, H, out=half)
+    assert rel_l2(half.float(), big_out[:7]) < 1e-3
+    split = torch.empty(7, T, 4 * H, dtype=torch.bfloat16, device="cuda")
+    ops.bilstm_small(xp[:7 * T], w_hh, 7, T, H, out=split, split=True)
+    assert rel_l2(split[..., :2 * H].float() + split[..., 2 * H:].float(), big_out[:7]) < 1e-4
+
+
 @pytest.mark.parametrize("B,T,I,H,L", [(2, 40, 80, 768, 3), (17, 33, 80, 512, 2), (64, 64, 80, 768, 3), (33, 21, 512, 256, 4),
                                        (1, 1, 80, 768, 3), (64, 300, 512, 768, 3)])
 def test_lstm_stack_wavefront_matches_explicit_lstm(B, T, I, H, L):
