@@ -225,6 +225,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const PipeSme
               if (b_ok && t + 4 * i < p.T) *reinterpret_cast<uint2*>(po) = make_uint2(pack_f16(o0, o1), pack_f16(o2, o3));
               po += po_step;
             }
+          } else if (!p.out_raw && p.out_mode == 4) {
+            // two fp16 terms per element, nothing else (MelGAN's "fp16s" residual stream and ConvTranspose outputs)
+            __half* ph = reinterpret_cast<__half*>(po);
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * kStagingLd + cl);
+              const float o0 = apply_act<ACT>(a.x + bv.x), o1 = apply_act<ACT>(a.y + bv.y);
+              const float o2 = apply_act<ACT>(a.z + bv.z), o3 = apply_act<ACT>(a.w + bv.w);
+              uint2 hi, lo;
+              split_f16_pair(o0, o1, hi.x, lo.x);
+              split_f16_pair(o2, o3, hi.y, lo.y);
+              if (b_ok && t + 4 * i < p.T) {
+                *reinterpret_cast<uint2*>(ph) = hi;
+                *reinterpret_cast<uint2*>(ph + p.cs) = lo;
+              }
+              ph += po_step;
+            }
           } else {
             __nv_bfloat16* pr = static_cast<__nv_bfloat16*>(p.out_raw) + ((long long)b * t_out + time0) * p.out_raw_ld + c;
             const long long pr_step = 4LL * p.phases * p.out_raw_ld;

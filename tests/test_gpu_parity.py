@@ -168,10 +168,12 @@ def test_bilstm_small_batch_kernel_agrees_with_the_warp_kernel():
 
 
 @pytest.mark.parametrize("B,T,I,H,L", [(2, 40, 80, 768, 3), (17, 33, 80, 512, 2), (64, 64, 80, 768, 3), (33, 21, 512, 256, 4),
-                                       (1, 1, 80, 768, 3), (64, 300, 512, 768, 3)])
+                                       (1, 1, 80, 768, 3), (64, 300, 512, 768, 3), (3, 9, 80, 640, 2), (5, 7, 80, 128, 4),
+                                       (64, 2, 80, 384, 3)])
 def test_lstm_stack_wavefront_matches_explicit_lstm(B, T, I, H, L):
     """All layers of a small-batch stack as one wavefront launch (avc_lstm_stack_ws): every activation-row variant (16 /
-    32 / 64), 2-4 layers, ragged batches, T = 1 (ramp-up and ramp-down ticks only); h_last against the fp64 explicit LSTM
+    32 / 64), 2-4 layers, ragged batches, T = 1 and 2 (ramp-up and ramp-down ticks only), an odd number of 64-channel chunks
+    per K half (H = 640: the second load group reaches into the other half) and a single one (H = 128); h_last against the fp64 explicit LSTM
     and against the layer-by-layer kernels; every frame of every layer's scratch sequence against the explicit LSTM."""
     from autoformer_b200 import layers, ops, packing
     assert ops.stack_supported(B, H, L, "fp16x2")
