@@ -286,23 +286,50 @@ __global__ void __launch_bounds__(256) ln_transpose_kernel(const float* __restri
           if (c + e < C) v[e] = __ldg(xb + (long long)r * C + c + e);
       }
     }
-    float rm = 0.f, rs = 0.f;
-    if (ln_axis == 1 && r < R) {
-      const float* st = stats + 2 * ((long long)b * R + r);
-      rm = st[0];
-      rs = st[1];
+    // normalisation terms as (scale, shift) per element, fetched with 16-byte loads where the four columns are whole
+    // (one scalar load per term and element made this pass issue 17 loads per float4 of data)
+    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      if (ln_axis == 1) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(stats + 2 * ((long long)b * R + r)));
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec && c + 3 < C) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c)), b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+          g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+          be[0] = b4.x; be[1] = b4.y; be[2] = b4.z; be[3] = b4.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c + e < C) { g[e] = __ldg(gamma + c + e); be[e] = __ldg(beta + c + e); }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sc[e] = st.y * g[e];
+          sh[e] = be[e] - st.x * sc[e];
+        }
+      } else if (ln_axis == 2) {
+        const float gr = __ldg(gamma + r), br = __ldg(beta + r);
+        const float* st = stats + 2 * ((long long)b * C + c);
+        float m[4] = {0.f, 0.f, 0.f, 0.f}, rs4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec && c + 3 < C) {      // (mean, rstd) pairs of four consecutive columns: 32 contiguous bytes, 16-byte aligned
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(st)), s1 = __ldg(reinterpret_cast<const float4*>(st + 4));
+          m[0] = s0.x; rs4[0] = s0.y; m[1] = s0.z; rs4[1] = s0.w; m[2] = s1.x; rs4[2] = s1.y; m[3] = s1.z; rs4[3] = s1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c + e < C) { m[e] = st[2 * e]; rs4[e] = st[2 * e + 1]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sc[e] = rs4[e] * gr;
+          sh[e] = br - m[e] * sc[e];
+        }
+      }
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float n = v[e];
-      if (r < R && c + e < C) {
-        if (ln_axis == 1) {
-          n = (v[e] - rm) * rs * __ldg(gamma + c + e) + __ldg(beta + c + e);
-        } else if (ln_axis == 2) {
-          const float* st = stats + 2 * ((long long)b * C + c + e);
-          n = (v[e] - st[0]) * st[1] * __ldg(gamma + r) + __ldg(beta + r);
-        }
-      }
+      if (ln_axis != 0 && r < R && c + e < C) n = fmaf(v[e], sc[e], sh[e]);
       raw[lr][4 * tx + e] = v[e];
       nrm[lr][4 * tx + e] = n;
     }
