@@ -256,6 +256,11 @@ def reflect_halo(buf, row0, L, reflect):
     return buf
 
 
+# Cap on the CTAs one persistent LSTM launch may take (None: the whole device).  pipeline.convert_pairs sets it to half
+# the SMs while it runs two under-filled batches on two streams, so that both cooperative grids are resident together.
+LSTM_CTA_BUDGET = None
+
+
 def persistent_batch_cap(H, n_sm=148):
     """Largest batch whose persistent LSTM grid (m-tiles x H/G n-tiles, one CTA each) fits one wave of the SMs."""
     best = 0
@@ -274,6 +279,8 @@ def choose_gate_group(B, H, persistent=False, n_sm=148, fused=False, precision=N
 
     G = 28 (the fused kernel, two-term 16-bit precisions, CTA pairs): ceil(H / 28) tiles with a ragged last one -- for
     H = 1024 and two batch groups that is 37 x 4 = 148 CTAs, every SM of a B200, where G = 32 leaves 20 idle."""
+    if LSTM_CTA_BUDGET is not None:                # two batches side by side on two streams: each takes half the SMs
+        n_sm = min(n_sm, LSTM_CTA_BUDGET)
     m_tiles = (B + 127) // 128
     if m_tiles >= 2:
         m_tiles = (m_tiles + 1) // 2 * 2          # CTA pairs: an odd tile count is rounded up with a masked tile

@@ -621,7 +621,7 @@ def sub_cfg5(ctx, ref, pk, args, precision):
     of <= 512, LPT-assigned to the ranks by the measured cost model; no data-path collective; strong scaling."""
     import random
     import torch
-    from autoformer_b200 import _lib, sharding
+    from autoformer_b200 import _lib, pipeline, sharding
     from autoformer_b200.factory.AutoVC import AutoVC
     model, sd = bench_state_dict()
     model = model.to(ctx.dev).eval()
@@ -643,23 +643,23 @@ def sub_cfg5(ctx, ref, pk, args, precision):
         return x[:n], co[:n], ct[:n]
 
     def one_pass():
-        acc = torch.zeros((), device=ctx.dev, dtype=torch.float64)
-        for T, ids in mine:
-            x, co, ct = inputs(T, len(ids))
-            acc += model(x, co, ct)[1].double().sum()
-        return acc
+        # pipeline.convert_batches: full batches one after the other, the under-filled last batch of every length bucket
+        # two at a time on two streams (AVC_BENCH_PAIR=0: everything one after the other, for A/B timing)
+        batches = [inputs(T, len(ids)) for T, ids in mine]
+        sums = pipeline.convert_batches(model, batches, reduce=lambda out: out[1].double().sum(),
+                                        pair_below=pipeline.PAIR_BELOW if os.environ.get("AVC_BENCH_PAIR", "1") != "0" else 0)
+        return torch.stack(sums).sum() if sums else torch.zeros((), device=ctx.dev, dtype=torch.float64)
 
     for T, ids in mine:                                  # allocate every resident input before timing
         inputs(T, len(ids))
-    # warm-up: one untimed conversion per distinct batch shape of this rank (weights packed, kernels loaded, and the
-    # caching allocator has seen every buffer size -- a first-time cudaMalloc inside the timed pass costs milliseconds
-    # and synchronises; with N ranks each rank meets the same ~29 lengths in 1/N of the work, which showed up as a 15 %
-    # strong-scaling loss at N = 2 that had nothing to do with the GPUs)
-    seen_shapes = set()
-    for T, ids in mine:
-        if (T, len(ids)) not in seen_shapes:
-            seen_shapes.add((T, len(ids)))
-            model(*inputs(T, len(ids)))
+    # warm-up: one untimed pass over this rank's batches, through the same schedule as the timed one (weights packed for
+    # every gate-group size, kernels loaded, and the caching allocator has seen every buffer size on every stream -- a
+    # first-time cudaMalloc inside the timed pass costs milliseconds and synchronises; with N ranks each rank meets the
+    # same ~29 lengths in 1/N of the work, which showed up as a 15 % strong-scaling loss at N = 2 that had nothing to do
+    # with the GPUs)
+    model(*inputs(*[(T, len(ids)) for T, ids in mine][0])) if mine else None
+    model.freeze_weights()
+    one_pass()
     model.freeze_weights()
     ctx.sync_all()
     n0 = _lib.launch_count()
@@ -691,7 +691,8 @@ def sub_cfg5(ctx, ref, pk, args, precision):
     tf = total * FLOP_PER_FRAME / (ms_max * 1e-3) / 1e12 / ctx.world
     return dict(workload=f"AutoVC(32,256,512,32) conversion of {args.utterances} utterances x 128..1024 frames "
                          f"(BASELINE configs[4]), bucketed by exact length, batches <= {args.batch}, LPT-sharded over "
-                         f"{ctx.world} rank(s) by a measured per-batch cost model; strong scaling",
+                         f"{ctx.world} rank(s) by a measured per-batch cost model; under-filled batches (<= 256 utterances) two at a "
+                         f"time on two streams (pipeline.convert_batches); strong scaling",
                 precision=precision, scaling="strong", n_gpus=ctx.world, utterances=args.utterances, frames_total=total,
                 ms=ms_max, frames_per_s=total / (ms_max * 1e-3), tflops_per_gpu=tf,
                 frac_of_bf16_burst=tf / pk["tflops_burst"], frac_of_bf16_sustained=tf / pk["tflops_sustained"],

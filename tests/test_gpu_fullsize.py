@@ -242,3 +242,31 @@ def test_two_rank_gpu_outputs_equal_single_gpu(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "EQUAL" in out.stdout
+
+
+@pytest.mark.gpu
+def test_convert_batches_pairs_underfilled_batches_bit_equal():
+    """pipeline.convert_batches runs batches of <= 256 utterances two at a time on two streams with the persistent LSTM
+    grids capped at half the SMs; every output must be bit-equal to the same batch converted alone, whatever the mix of
+    batch sizes (full, under-filled, odd count of under-filled ones, weight-stationary-sized)."""
+    from autoformer_b200 import ops, pipeline
+    from autoformer_b200.factory.AutoVC import AutoVC
+    args = (32, 256, 512, 32)
+    m = AutoVC(*args)
+    m.load_state_dict(seeded_state_dict(templates.autovc_template(*args), 0))
+    m = m.cuda().eval()
+    m.precision = "fp16x2"
+    shapes = [(300, 64), (200, 96), (150, 64), (130, 128), (70, 96), (40, 64), (256, 32)]
+    batches = [(synthetic_mel(B, T, 7 + i).cuda(), synthetic_speaker(B, i, "org").cuda(), synthetic_speaker(B, i, "trg").cuda())
+               for i, (B, T) in enumerate(shapes)]
+    alone = [tuple(t.clone() for t in m(*b)) for b in batches]
+    assert ops.LSTM_CTA_BUDGET is None
+    for _ in range(2):
+        got = pipeline.convert_batches(m, batches)
+        torch.cuda.synchronize()
+        assert ops.LSTM_CTA_BUDGET is None
+        for (B, T), a, g in zip(shapes, alone, got):
+            for x, y in zip(a, g):
+                assert torch.equal(x, y), (B, T)
+    sums = pipeline.convert_batches(m, batches, reduce=lambda out: out[1].double().sum())
+    assert all(float(s) == float(a[1].double().sum()) for s, a in zip(sums, alone))
