@@ -38,13 +38,21 @@ def frames_cost(T, n):
 _AUTOVC_COST = {"fp32": (47.5, 0.0596), "fp16x2": (29.8, 0.0421)}
 
 
-def autovc_cost(T, n, precision="fp32"):
+PAIRED_LSTM_SHARE = 0.6      # of the per-frame term, for a batch that runs beside another one (pipeline.convert_batches)
+
+
+def autovc_cost(T, n, precision="fp32", pair_below=256):
     """Measured cost model of one AutoVC conversion batch on a B200, in microseconds: the LSTM layers run one tile row
     per frame whatever the batch size up to 512 (split format: 47.5 us per frame, profiles/r01_bench_final_1gpu:
     6.08 ms / 128 frames; fp16x2: 29.8 us, profiles/r01_bench_fp16x2_1gpu: 3.82 ms / 128), everything else scales with
     utterances x frames (3.9 ms resp. 2.76 ms / 65,536).  A 212-utterance tail batch therefore costs 77 % of a full
-    one for 41 % of its frames, which a frames-only balance does not see."""
+    one for 41 % of its frames, which a frames-only balance does not see; run beside another tail batch
+    (``pair_below``; 0 = the batches run one after the other) it costs about 0.6 of its frame time."""
     per_frame, per_utt_frame = _AUTOVC_COST.get(precision, _AUTOVC_COST["fp32"])
+    if 64 < n <= pair_below:
+        # pipeline.convert_batches runs such batches two at a time on two streams: the pair shares the frame time of the
+        # recurrences (measured: 212 x 1024 + 180 x 992 frames 71.6 ms one after the other, 52.3 ms side by side)
+        per_frame *= PAIRED_LSTM_SHARE
     return float(T) * (per_frame + per_utt_frame * n)
 
 
