@@ -92,3 +92,27 @@ def test_cost_model_balances_tail_batches():
         spread[cost.__name__] = max(loads) / (sum(loads) / len(loads))
     assert spread["autovc_cost"] <= spread["frames_cost"] + 1e-9
     assert spread["autovc_cost"] < 1.05
+
+
+def test_cost_model_knows_that_tail_batches_run_in_pairs():
+    """pipeline.convert_batches runs batches of 65 .. 256 utterances two at a time: the LPT cost of such a batch carries
+    0.6 of its frame time; full batches, weight-stationary-sized ones and pair_below = 0 keep the whole of it."""
+    from autoformer_b200 import sharding
+    full = sharding.autovc_cost(1024, 512, "fp16x2")
+    tail = sharding.autovc_cost(1024, 212, "fp16x2")
+    tail_alone = sharding.autovc_cost(1024, 212, "fp16x2", pair_below=0)
+    per_frame, per_utt_frame = sharding._AUTOVC_COST["fp16x2"]
+    assert abs(tail_alone - 1024 * (per_frame + per_utt_frame * 212)) < 1e-6
+    assert abs(tail - 1024 * (sharding.PAIRED_LSTM_SHARE * per_frame + per_utt_frame * 212)) < 1e-6
+    assert tail < tail_alone < full
+    assert sharding.autovc_cost(1024, 64, "fp16x2") == sharding.autovc_cost(1024, 64, "fp16x2", pair_below=0)
+    assert sharding.autovc_cost(1024, 300, "fp16x2") == sharding.autovc_cost(1024, 300, "fp16x2", pair_below=0)
+    # the plan stays a partition of the utterances and deterministic
+    lengths = [128 + 32 * (i % 29) for i in range(5000)]
+    a = sharding.plan(lengths, 8, 512, cost=sharding.autovc_cost_for("fp16x2"))
+    b = sharding.plan(lengths, 8, 512, cost=sharding.autovc_cost_for("fp16x2"))
+    assert a == b
+    ids = sorted(i for r in a for _, batch in r for i in batch)
+    assert ids == list(range(5000))
+    loads = [sum(sharding.autovc_cost(t, len(batch), "fp16x2") for t, batch in r) for r in a]
+    assert max(loads) / (sum(loads) / len(loads)) < 1.1
