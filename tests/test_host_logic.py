@@ -38,6 +38,28 @@ def test_autovc_host_logic(cpu_kernels, precision, tol):
     assert rel_l2(mel, ref[0]) < tol and rel_l2(post, ref[1]) < tol and rel_l2(codes, ref[2]) < tol
 
 
+def test_convert_batches_order_and_unpaired_fallback(cpu_kernels, monkeypatch):
+    """pipeline.convert_batches returns one result per batch in the order given; batches it may not pair (<= 64 utterances:
+    the weight-stationary kernels fill the device; any batch when the LSTM kernels run without the cooperative launch
+    attribute) simply run one after the other -- on the CPU stand-ins that is the whole path, no CUDA stream is touched."""
+    from autoformer_b200 import ops, pipeline
+    from autoformer_b200.factory.AutoVC import AutoVC
+    args = (32, 256, 512, 32)
+    m = AutoVC(*args)
+    m.load_state_dict(seeded_state_dict(templates.autovc_template(*args), 0))
+    m.eval()
+    monkeypatch.setenv("AVC_LSTM_NO_COOP", "1")
+    batches = [(synthetic_mel(B, T, 3 + i), synthetic_speaker(B, i, "org"), synthetic_speaker(B, i, "trg"))
+               for i, (B, T) in enumerate([(3, 32), (70, 32), (2, 64)])]
+    calls = []
+    sums = pipeline.convert_batches(m, batches, reduce=lambda out: calls.append(out[1].shape[0]) or out[1].double().sum())
+    assert calls == [3, 70, 2] and ops.LSTM_CTA_BUDGET is None
+    for b, s in zip(batches, sums):
+        assert float(s) == float(m(*b)[1].double().sum())
+    outs = pipeline.convert_batches(m, batches[:1])
+    assert len(outs) == 1 and len(outs[0]) == 3 and outs[0][1].shape == (3, 1, 32, 80)
+
+
 def test_autovc_config_r_host_logic(cpu_kernels):
     from autoformer_b200.factory.AutoVC import AutoVC
     args = (44, 256, 512, 22)
