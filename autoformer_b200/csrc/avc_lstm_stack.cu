@@ -13,8 +13,8 @@
 // The grid is L layers x R = 4H/128 row blocks x 2 CTAs, each pair a thread-block cluster; CTA s of a pair holds the K
 // half s of its row block of W_hh and (above the first layer) of W_ih, ONE fp16 term each -- that is what fits: 128 rows
 // x 768 channels x 2 bytes = 384 of the 512 tensor-memory columns per CTA beside two accumulators, 144 CTAs for LstmDV.
-// (Two terms for every matrix would need 47 MB on chip.  One term costs precision: embedding rel-L2 2.7e-4 instead of
-// 1.4e-4 on the test weights, 6e-4 instead of 2.3e-4 on the x3-gain stress weights, gate 1e-3 --
+// (Two terms for every matrix would need 47 MB on chip.  One term costs precision: embedding rel-L2 2.7 .. 3.0e-4 instead
+// of 1.5 .. 1.7e-4 on the test weights, 6.7e-4 instead of 3.5e-4 on the x3-gain stress weights, gate 1e-3 --
 // scripts/lstm_stack_precision.py; the caller chooses.)
 // The weights are the A operand of tcgen05.mma read from tensor memory.  Measured (profiles/r02_lstm_stack_v1_*): such an
 // MMA takes ~85 cycles whatever its width, so the MMAs are the longest link of a tick's serial chain, and only those on
